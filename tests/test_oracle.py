@@ -1,0 +1,153 @@
+"""Pin the CPU oracle: against committed golden vectors generated from the
+unmodified reference (tests/make_golden.py) and, when /root/reference is
+present, against the live reference."""
+import numpy as np
+import pytest
+import torch
+
+import common as C
+import refharness as RH
+from dual_space_nerf_b200 import scene as S
+from oracle import clib
+from oracle import oracle as O
+
+
+def test_linspace_matches_torch():
+    for n in (2, 3, 5, 16, 32, 33, 64, 65, 128, 192):
+        assert np.array_equal(clib.linspace01(n), torch.linspace(0.0, 1.0, steps=n).numpy()), n
+
+
+def test_geometry_ops_match_torch_bitwise():
+    rng = np.random.RandomState(0)
+    tri = rng.randn(4000, 3, 3).astype(np.float32)
+    pts = rng.randn(4000, 3).astype(np.float32)
+    a, b = torch.from_numpy(tri[:, 1] - tri[:, 0]), torch.from_numpy(tri[:, 2] - tri[:, 0])
+    n = torch.cross(a, b, dim=-1)
+    assert C.bits_equal(clib.norm3(n.numpy()), torch.norm(n, dim=-1).numpy()) == 0
+    verts = rng.randn(500, 3).astype(np.float32)
+    faces = rng.randint(0, 500, size=(900, 3))
+    ref_c = torch.from_numpy(verts)[torch.from_numpy(faces)].mean(dim=-2).numpy()
+    assert C.bits_equal(clib.centroids(verts, faces), ref_c) == 0
+    # brute-force NN agrees with a float64 argmin except on fp32 near-ties
+    cent = rng.randn(3000, 3).astype(np.float32)
+    idx, d2 = clib.nearest(pts, cent, want_d2=True)
+    d64 = ((pts[:, None].astype(np.float64) - cent[None]) ** 2).sum(-1)
+    assert (idx == d64.argmin(1)).mean() > 0.999
+    assert np.allclose(d2, d64.min(1), rtol=1e-6)
+    # ties: duplicate centroid -> lowest index
+    cent2 = np.concatenate([cent, cent[:10]])
+    idx2 = clib.nearest(pts, cent2)
+    assert np.array_equal(idx, idx2)
+
+
+def _oracle_for(sc, sd, n, **kw):
+    return O.Oracle(sd, sc["canonical"], sc["faces"], n, **kw)
+
+
+def test_stages_vs_golden(scene64, state_dict):
+    g = C.golden("stages_64x64x32.npz")
+    rays = g["rays"]
+    sc = scene64
+    st = {}
+    _oracle_for(sc, state_dict, 32).render(sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays],
+                                          sc["posed"], sc["poses"], sc["frame"], stages=st)
+    for k in ("near_gg", "far_gg", "z_vals", "pts", "uv", "h", "xyz_cano"):
+        assert C.bits_equal(st[k], g[k]) == 0, k  # bit-exact geometry
+    assert np.array_equal(st["idx"], g["idx"])
+    assert np.array_equal(st["mask"], g["mask"])
+    act = ~g["mask"]
+    assert np.abs(st["pose_feat"] - g["pose_feat"]).max() < 1e-7
+    assert np.abs(st["density"][act] - g["density"][act]).max() < 2e-3  # |sigma| ~ 170, fp32 GEMM order
+    assert np.abs(st["essence"][act] - g["essence"][act]).max() < 1e-5
+    kink = st["kink_margin"][act] < C.KINK_MARGIN
+    gn = np.abs(st["grad"][act] - g["grad"][act]).max(1) / np.abs(g["grad"][act]).max(1)
+    assert gn[~kink].max() < 1e-4
+    assert np.abs(st["normal_world"][act] - g["normal_world"][act]).max(1)[~kink].max() < 1e-3
+    assert np.abs(st["color"][act] - g["color"][act]).max(1)[~kink].max() < 1e-5
+
+
+def _kink_rays(st, n):
+    return (st["kink_margin"] < C.KINK_MARGIN).reshape(-1, n).any(1)
+
+
+def test_render_view_vs_golden(scene64, state_dict):
+    g = C.golden("render_64x64x32.npz")
+    sc = scene64
+    st = {}
+    out = _oracle_for(sc, state_dict, 32).render(sc["ray_o"], sc["ray_d"], sc["near"], sc["far"], sc["posed"],
+                                                 sc["poses"], sc["frame"], stages=st)
+    ref = {"color": g["coarse_color"].reshape(-1, 3), "depth_map": g["coarse_depth"].ravel(),
+           "acc_map": g["coarse_acc"].ravel(), "disp_map": g["coarse_disp"].ravel()}
+    stats = C.check_rays(out, ref, _kink_rays(st, 32), what="render_view 64x64x32")
+    assert stats["rgb_max_nokink"] < 1e-5
+
+
+def test_uniform_mode_vs_golden(scene64, state_dict):
+    g = C.golden("render_uniform.npz")
+    rays = g["rays"]
+    sc = scene64
+    st = {}
+    out = _oracle_for(sc, state_dict, 16, mode="uniform").render(
+        sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays], sc["posed"], sc["poses"], sc["frame"], stages=st)
+    C.check_rays(out, g, _kink_rays(st, 16), what="uniform")
+    assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0
+    assert np.abs(out["weights"] - g["weights"]).max() < 1e-5
+
+
+def test_novel_pose_vs_golden(state_dict):
+    g = C.golden("render_novelpose.npz")
+    rays = g["rays"]
+    sc = S.make_scene(64, 64, pose_seed=3)
+    st = {}
+    out = _oracle_for(sc, state_dict, 32, zero_code=True, light_center=S.LIGHT_CENTER_313).render(
+        sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays], sc["posed"], sc["poses"], sc["frame"],
+        Th=sc["Th"], stages=st)
+    C.check_rays(out, g, _kink_rays(st, 32), what="novel pose")
+
+
+def test_128x128x64_vs_golden(state_dict):
+    g = C.golden("render_128x128x64.npz")
+    rays = g["rays"]
+    sc = S.make_scene(128, 128)
+    st = {}
+    out = _oracle_for(sc, state_dict, 64).render(
+        sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays], sc["posed"], sc["poses"], sc["frame"], stages=st)
+    C.check_rays(out, g, _kink_rays(st, 64), what="128x128x64")
+    assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0
+
+
+@pytest.mark.skipif(not RH.available(), reason="/root/reference not present")
+def test_live_reference_weights_and_render(scene64, state_dict):
+    RH._install_shims()
+    from model.spacenet import DualSpaceNeRF as RefNet
+
+    from dual_space_nerf_b200 import net as N
+
+    torch.manual_seed(0)
+    ref = RefNet(None)
+    N.synthetic_head_rescale_(ref)
+    rsd = ref.state_dict()
+    assert list(rsd.keys()) == N.STATE_DICT_ORDER
+    for k in state_dict:
+        assert torch.equal(rsd[k], state_dict[k]), k
+    sc = scene64
+    rays = np.nonzero(sc["hit_box"])[0][5::40]
+    rig = RH.ReferenceRig(sc, 32, state_dict)
+    ref_out = rig.render(rays)
+    st = {}
+    out = _oracle_for(sc, state_dict, 32).render(sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays],
+                                                 sc["posed"], sc["poses"], sc["frame"], stages=st)
+    C.check_rays(out, ref_out, _kink_rays(st, 32), what="live reference")
+
+
+def test_sample_pdf_properties():
+    rng = np.random.RandomState(0)
+    z = np.sort(rng.rand(50, 64).astype(np.float32) + 2.0, -1)
+    w = rng.rand(50, 64).astype(np.float32)
+    w[:, :20] = 0
+    z2 = O.sample_pdf(z, w, 128)
+    assert z2.shape == (50, 192)
+    assert np.all(np.diff(z2, axis=-1) >= 0)
+    assert np.all(z2 >= z[:, :1]) and np.all(z2 <= z[:, -1:])
+    for r in range(50):  # the coarse samples survive the merge
+        assert np.all(np.isin(z[r], z2[r]))

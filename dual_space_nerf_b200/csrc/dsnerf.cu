@@ -1,0 +1,788 @@
+// libdsnerf.so -- host side of the C ABI declared in include/dsnerf.h.
+// Owns device buffers, stages weights/meshes, launches the kernels of the render path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/dsnerf.h"
+#include "geom.cuh"
+#include "mlp_simt.cuh"
+#include "mlp_tc.cuh"
+#include "shade.cuh"
+
+using namespace dsn;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct MeshGrid {
+  Grid g{};
+  int ncell = 0;
+  DevBuf cent, counts, start, cursor, sorted, cdist;
+  void release() { cent.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); }
+};
+
+// state_dict order
+enum {
+  T_EMB = 0, T_S1_0_W, T_S1_0_B, T_S1_2_W, T_S1_2_B, T_S1_4_W, T_S1_4_B, T_S1_6_W, T_S1_6_B,
+  T_S2_0_W, T_S2_0_B, T_S2_2_W, T_S2_2_B, T_S2_4_W, T_S2_4_B, T_DENS_W, T_DENS_B,
+  T_RGB1_W, T_RGB1_B, T_RGB3_W, T_RGB3_B, T_L0_W, T_L0_B, T_L2_W, T_L2_B, T_L4_W, T_L4_B,
+  T_P0_W, T_P0_B, T_P2_W, T_P2_B, T_P4_W, T_P4_B
+};
+const int kTensorSize[DSNERF_NUM_WEIGHT_TENSORS] = {
+    500 * 8, 256 * 87, 256, 256 * 256, 256, 256 * 256, 256, 256 * 256, 256,
+    256 * 319, 256, 256 * 256, 256, 256 * 256, 256, 256, 1,
+    128 * 256, 128, 3 * 128, 3, 128 * 9, 128, 128 * 128, 128, 128, 1,
+    64 * 92, 64, 64 * 64, 64, 16 * 64, 16};
+
+}  // namespace
+
+struct dsnerf_ctx {
+  int device = 0;
+  std::string err;
+  int sm_count = 148;
+  // ---- weights
+  bool have_weights = false;
+  std::vector<float> hw[DSNERF_NUM_WEIGHT_TENSORS];
+  DevBuf wblob;      // fp32 SIMT/light layouts
+  DevBuf bias0;      // per-frame folded first-layer bias (256)
+  SimtWeights sw{};
+  LightWeights lw{};
+  TcWeights tw;      // fp16 hi/lo tensor-core layouts
+  // ---- mesh
+  bool have_mesh = false;
+  int F = 0, V = 0;
+  std::vector<int32_t> h_faces;
+  std::vector<float> h_canon;
+  DevBuf faces, canon, posed, vq;
+  MeshGrid g_canon, g_posed;
+  // ---- frame
+  bool have_frame = false;
+  float light_shift[3] = {0, 0, 0};
+  int has_shift = 0;
+  float rot[4] = {1, 0, 0, 1}, rot_center[2] = {0, 0};
+  int has_rot = 0;
+  // ---- workspace
+  DevBuf near2, far2, raw, active, mlp_a, mlp_g, tvals, counters, io;
+  int tvals_n = 0;
+  void* pin = nullptr;
+  size_t pin_cap = 0;
+  cudaEvent_t pin_free = nullptr;
+  bool pin_busy = false;
+  unsigned long long* h_counters = nullptr;  // pinned, 4 entries
+  cudaEvent_t stats_ready = nullptr;
+  dsnerf_stats_t stats{};
+  // ---- profiling
+  int profile = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  double mlp_ms = 0;
+  int64_t mlp_launches = 0;
+};
+
+namespace {
+
+int fail(dsnerf_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(ctx, DSNERF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+#define CKL(what)                                                                                        \
+  do {                                                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                                 \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(ctx, DSNERF_ERR_CUDA, std::string("launch ") + what + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+int ensure_pin(dsnerf_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pin_cap) return 0;
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  ctx->pin = nullptr;
+  ctx->pin_cap = 0;
+  CK(cudaMallocHost(&ctx->pin, bytes + 4096));
+  ctx->pin_cap = bytes + 4096;
+  return 0;
+}
+
+// wait until the previous async upload out of the pinned staging buffer has been consumed
+int pin_acquire(dsnerf_ctx* ctx, size_t bytes) {
+  if (ctx->pin_busy) { CK(cudaEventSynchronize(ctx->pin_free)); ctx->pin_busy = false; }
+  return ensure_pin(ctx, bytes);
+}
+int pin_release(dsnerf_ctx* ctx, cudaStream_t st) {
+  CK(cudaEventRecord(ctx->pin_free, st));
+  ctx->pin_busy = true;
+  return 0;
+}
+
+// Radius beyond which a point cannot be non-transparent w.r.t. triangle T when T's centroid is
+// its nearest centroid: |h| <= 0.1 and uv in [-4,5]^2 (utils/render_utils.py:103) confine the
+// point to a box around T whose farthest corner from the centroid (uv = 1/3,1/3) is R_T.
+float transparency_radius(const float* verts, const int32_t* faces, int F) {
+  double best = 0;
+  const double uvs[2] = {-4.0 - 1.0 / 3.0, 5.0 - 1.0 / 3.0};
+  for (int f = 0; f < F; ++f) {
+    const float* m0 = verts + 3 * faces[3 * f];
+    const float* m1 = verts + 3 * faces[3 * f + 1];
+    const float* m2 = verts + 3 * faces[3 * f + 2];
+    double e0[3], e1[3];
+    for (int k = 0; k < 3; ++k) { e0[k] = (double)m2[k] - m0[k]; e1[k] = (double)m1[k] - m0[k]; }
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) { double d = uvs[a] * e0[k] + uvs[b] * e1[k]; s += d * d; }
+        best = std::max(best, s);
+      }
+  }
+  return (float)(sqrt(0.1 * 0.1 + best) * 1.002 + 1e-4);
+}
+
+// (Re)build the nearest-centroid grid of a mesh: centroids, counting sort by cell, cell-centre
+// distance table.  h_verts is the host copy (bbox and r_cap are computed on the host).
+int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float* h_verts, cudaStream_t st) {
+  const int F = ctx->F, V = ctx->V;
+  float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+  for (int v = 0; v < V; ++v)
+    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], h_verts[3 * v + k]); hi[k] = std::max(hi[k], h_verts[3 * v + k]); }
+  for (int k = 0; k < 3; ++k)
+    if (!(lo[k] <= hi[k]) || !std::isfinite(lo[k]) || !std::isfinite(hi[k])) return fail(ctx, DSNERF_ERR_INVALID, "mesh vertices are not finite");
+  float r_cap = transparency_radius(h_verts, ctx->h_faces.data(), F);
+  float cell = 0.04f;
+  double ext[3];
+  for (;;) {
+    double n = 1;
+    for (int k = 0; k < 3; ++k) { ext[k] = (double)hi[k] - lo[k] + 2.0 * (r_cap + 2.0 * cell); n *= ceil(ext[k] / cell); }
+    if (n <= 3.0e6) break;
+    cell *= 1.26f;
+  }
+  Grid& g = mg.g;
+  g.cell = cell;
+  g.inv_cell = 1.0f / cell;
+  g.ox = lo[0] - (r_cap + 2 * cell); g.oy = lo[1] - (r_cap + 2 * cell); g.oz = lo[2] - (r_cap + 2 * cell);
+  g.nx = (int)ceil(ext[0] / cell); g.ny = (int)ceil(ext[1] / cell); g.nz = (int)ceil(ext[2] / cell);
+  g.half_diag = cell * 0.8660254f * 1.0001f;
+  g.r_cap = r_cap;
+  mg.ncell = g.nx * g.ny * g.nz;
+  CK(mg.cent.ensure(sizeof(float) * 3 * F));
+  CK(mg.counts.ensure(sizeof(int) * mg.ncell));
+  CK(mg.start.ensure(sizeof(int) * (mg.ncell + 1)));
+  CK(mg.cursor.ensure(sizeof(int) * mg.ncell));
+  CK(mg.sorted.ensure(sizeof(float4) * F));
+  CK(mg.cdist.ensure(sizeof(float) * mg.ncell));
+  g.cell_start = mg.start.as<int>();
+  g.sorted = mg.sorted.as<float4>();
+  g.center_dist = mg.cdist.as<float>();
+  int fb = (F + 255) / 256;
+  centroid_kernel<<<fb, 256, 0, st>>>(d_verts, ctx->faces.as<int>(), F, mg.cent.as<float>());
+  CKL("centroid");
+  CK(cudaMemsetAsync(mg.counts.p, 0, sizeof(int) * mg.ncell, st));
+  grid_count_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.counts.as<int>());
+  CKL("grid_count");
+  grid_scan_kernel<<<1, 1024, 0, st>>>(mg.counts.as<int>(), mg.ncell, mg.start.as<int>(), mg.cursor.as<int>());
+  CKL("grid_scan");
+  grid_fill_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.cursor.as<int>(), mg.sorted.as<float4>());
+  CKL("grid_fill");
+  grid_center_dist_kernel<<<(mg.ncell + 255) / 256, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.cdist.as<float>());
+  CKL("grid_center_dist");
+  return 0;
+}
+
+struct BlobBuilder {
+  std::vector<float> data;
+  size_t add(size_t n) {
+    size_t off = (data.size() + 63) / 64 * 64;
+    data.resize(off + n, 0.f);
+    return off;
+  }
+};
+
+void rod2quat_host(const float* poses /*24x3*/, float* q /*92*/) {
+  // model/spacenet.py:314-331 on joints 1..23
+  for (int j = 1; j < 24; ++j) {
+    const float* r = poses + 3 * j;
+    float a0 = r[0] + 1e-16f, a1 = r[1] + 1e-16f, a2 = r[2] + 1e-16f;
+    float angle = sqrtf(fmaf(a2, a2, fmaf(a1, a1, a0 * a0)));
+    float c = cosf(angle / 2.f), s = sinf(angle / 2.f);
+    float* o = q + 4 * (j - 1);
+    o[0] = r[0] / angle * s; o[1] = r[1] / angle * s; o[2] = r[2] / angle * s; o[3] = c - 1.0f;
+  }
+}
+
+void linear_host(const std::vector<float>& w, const std::vector<float>& b, int out, int in, const float* x, float* y, bool relu) {
+  for (int o = 0; o < out; ++o) {
+    float acc = 0.f;
+    for (int i = 0; i < in; ++i) acc += w[(size_t)o * in + i] * x[i];
+    acc += b[o];
+    y[o] = relu ? std::max(acc, 0.f) : acc;
+  }
+}
+
+int ensure_workspace(dsnerf_ctx* ctx, int64_t R, int N) {
+  int64_t P = R * (int64_t)N;
+  CK(ctx->near2.ensure(sizeof(float) * R));
+  CK(ctx->far2.ensure(sizeof(float) * R));
+  CK(ctx->raw.ensure(sizeof(float4) * P));
+  CK(ctx->active.ensure(sizeof(float4) * (P + 128)));
+  CK(ctx->mlp_a.ensure(sizeof(float4) * (P + 128)));
+  CK(ctx->mlp_g.ensure(sizeof(float4) * (P + 128)));
+  CK(ctx->counters.ensure(sizeof(unsigned long long) * 4));
+  return 0;
+}
+
+int ensure_tvals(dsnerf_ctx* ctx, int N, cudaStream_t st) {
+  if (ctx->tvals_n == N) return 0;
+  CK(ctx->tvals.ensure(sizeof(float) * N));
+  if (int e = pin_acquire(ctx, sizeof(float) * N)) return e;
+  float* t = reinterpret_cast<float*>(ctx->pin);
+  for (int i = 0; i < N; ++i) t[i] = linspace01(i, N);
+  CK(cudaMemcpyAsync(ctx->tvals.p, t, sizeof(float) * N, cudaMemcpyHostToDevice, st));
+  if (int e = pin_release(ctx, st)) return e;
+  ctx->tvals_n = N;
+  return 0;
+}
+
+void profile_begin(dsnerf_ctx* ctx, cudaStream_t st, cudaEvent_t* a, cudaEvent_t* b) {
+  *a = *b = nullptr;
+  if (!ctx->profile) return;
+  cudaEventCreate(a);
+  cudaEventCreate(b);
+  cudaEventRecord(*a, st);
+}
+void profile_end(dsnerf_ctx* ctx, cudaStream_t st, cudaEvent_t a, cudaEvent_t b) {
+  if (!ctx->profile || !a) return;
+  cudaEventRecord(b, st);
+  ctx->pending.emplace_back(a, b);
+}
+
+// SpaceNet + gradient on the active list (count on the device or given by the host)
+int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_count, unsigned flags, int density_only, cudaStream_t st) {
+  cudaEvent_t a, b;
+  profile_begin(ctx, st, &a, &b);
+  if (flags & DSNERF_MLP_FP32_SIMT) {
+    mlp_simt_kernel<<<ctx->sm_count, SIMT_THREADS, SIMT_SMEM, st>>>(ctx->sw, ctx->active.as<float4>(), d_count, host_count,
+                                                                    ctx->mlp_a.as<float4>(), ctx->mlp_g.as<float4>(), density_only);
+    CKL("mlp_simt");
+  } else {
+    if (int e = tc_launch(ctx->tw, ctx->bias0.as<float>(), ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
+                          ctx->mlp_g.as<float4>(), density_only, ctx->sm_count, st))
+      return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc: ") + cudaGetErrorString((cudaError_t)e));
+  }
+  profile_end(ctx, st, a, b);
+  return 0;
+}
+
+int check_ready(dsnerf_ctx* ctx, bool need_frame) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (!ctx->have_weights) return fail(ctx, DSNERF_ERR_STATE, "dsnerf_set_weights has not been called");
+  if (!ctx->have_mesh) return fail(ctx, DSNERF_ERR_STATE, "dsnerf_set_mesh has not been called");
+  if (need_frame && !ctx->have_frame) return fail(ctx, DSNERF_ERR_STATE, "dsnerf_set_frame has not been called");
+  return 0;
+}
+
+ShadeArgs base_shade_args(dsnerf_ctx* ctx) {
+  ShadeArgs s{};
+  s.active = ctx->active.as<float4>();
+  s.mlp_a = ctx->mlp_a.as<float4>();
+  s.mlp_g = ctx->mlp_g.as<float4>();
+  s.posed = ctx->posed.as<float>();
+  s.canon = ctx->canon.as<float>();
+  s.faces = ctx->faces.as<int>();
+  s.cent_canon = ctx->g_canon.cent.as<float>();
+  s.F = ctx->F;
+  for (int k = 0; k < 3; ++k) s.light_shift[k] = ctx->light_shift[k];
+  s.has_shift = ctx->has_shift;
+  for (int k = 0; k < 4; ++k) s.rot[k] = ctx->rot[k];
+  s.rot_center[0] = ctx->rot_center[0]; s.rot_center[1] = ctx->rot_center[1];
+  s.has_rot = ctx->has_rot;
+  s.raw = ctx->raw.as<float4>();
+  return s;
+}
+
+// shared body of dsnerf_render / dsnerf_render_z
+int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, const float* z_in,
+                int64_t R, int N, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_out,
+                cudaStream_t st) {
+  if (int e = check_ready(ctx, true)) return e;
+  if (R < 0 || N < 1 || N > 4096) return fail(ctx, DSNERF_ERR_INVALID, "n_rays must be >= 0 and 1 <= n_samples <= 4096");
+  if (!ray_o || !ray_d || (!z_in && (!near || !far)) || !rgb || !depth || !acc || !disp) {
+    if (R > 0) return fail(ctx, DSNERF_ERR_INVALID, "null input/output pointer");
+  }
+  ctx->stats = dsnerf_stats_t{};
+  if (R == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  if (int e = ensure_workspace(ctx, R, N)) return e;
+  if (int e = ensure_tvals(ctx, N, st)) return e;
+  int launches = 0;
+  int64_t P = R * (int64_t)N;
+  unsigned long long* cnt = ctx->counters.as<unsigned long long>();
+  CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 4, st));
+  const float* near_use = near;
+  const float* far_use = far;
+  if (!z_in && (flags & DSNERF_SAMPLE_GG)) {
+    CK(ctx->vq.ensure(sizeof(float4) * ctx->V));
+    gg_prep_kernel<<<(ctx->V + 255) / 256, 256, 0, st>>>(ctx->posed.as<float>(), ctx->V, ray_o, ctx->vq.as<float4>());
+    CKL("gg_prep");
+    float gamma2 = (float)(0.05 * 0.05);  // python double 0.05**2 rounded to fp32 (pts_utils.py:36)
+    gg_bounds_kernel<<<(unsigned)((R + GG_THREADS - 1) / GG_THREADS), GG_THREADS, 0, st>>>(
+        ctx->vq.as<float4>(), ctx->V, ray_d, near, far, R, gamma2, ctx->near2.as<float>(), ctx->far2.as<float>());
+    CKL("gg_bounds");
+    launches += 2;
+    near_use = ctx->near2.as<float>();
+    far_use = ctx->far2.as<float>();
+  }
+  WarpArgs wa{};
+  wa.ray_o = ray_o; wa.ray_d = ray_d; wa.near = near_use; wa.far = far_use; wa.z_in = z_in; wa.tvals = ctx->tvals.as<float>();
+  wa.posed = ctx->posed.as<float>(); wa.canon = ctx->canon.as<float>(); wa.faces = ctx->faces.as<int>();
+  wa.R = R; wa.N = N; wa.raw = ctx->raw.as<float4>(); wa.active = ctx->active.as<float4>(); wa.counters = cnt;
+  wa.count_candidates = ctx->profile;
+  sample_warp_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(wa, ctx->g_posed.g);
+  CKL("sample_warp");
+  ++launches;
+  if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
+  ++launches;
+  ShadeArgs sa = base_shade_args(ctx);
+  sa.n_active = cnt;
+  sa.ray_o = ray_o; sa.ray_d = ray_d; sa.near = near_use; sa.far = far_use; sa.z_in = z_in; sa.tvals = ctx->tvals.as<float>();
+  sa.N = N;
+  shade_kernel<<<ctx->sm_count, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
+  CKL("shade");
+  ++launches;
+  CompositeArgs ca{};
+  ca.raw = ctx->raw.as<float4>(); ca.ray_d = ray_d; ca.near = near_use; ca.far = far_use; ca.tvals = ctx->tvals.as<float>(); ca.z_in = z_in;
+  ca.R = R; ca.N = N; ca.rgb = rgb; ca.depth = depth; ca.acc = acc; ca.disp = disp; ca.weights = weights; ca.z_out = z_out;
+  composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
+  CKL("composite");
+  ++launches;
+  CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->stats_ready, st));
+  ctx->stats.rays = R;
+  ctx->stats.samples = P;
+  ctx->stats.kernel_launches = launches;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dsnerf_abi_version(void) { return DSNERF_ABI_VERSION; }
+
+int dsnerf_create(dsnerf_ctx** out, int device) {
+  if (!out) return DSNERF_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return DSNERF_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return DSNERF_ERR_INVALID;
+  dsnerf_ctx* ctx = new dsnerf_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DSNERF_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return DSNERF_ERR_CUDA; }
+  if (prop.major != 10) { delete ctx; return DSNERF_ERR_NO_DEVICE; }  // built for sm_100a only
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaEventCreateWithFlags(&ctx->pin_free, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->stats_ready, cudaEventDisableTiming);
+  cudaMallocHost(reinterpret_cast<void**>(&ctx->h_counters), sizeof(unsigned long long) * 4);
+  memset(ctx->h_counters, 0, sizeof(unsigned long long) * 4);
+  cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMT_SMEM);
+  cudaFuncSetAttribute(shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHADE_SMEM);
+  tc_configure();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { delete ctx; return DSNERF_ERR_CUDA; }
+  *out = ctx;
+  return 0;
+}
+
+void dsnerf_destroy(dsnerf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->near2, &ctx->far2, &ctx->raw,
+                    &ctx->active, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io};
+  for (DevBuf* b : bufs) b->release();
+  ctx->g_canon.release();
+  ctx->g_posed.release();
+  ctx->tw.release();
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->pin_free) cudaEventDestroy(ctx->pin_free);
+  if (ctx->stats_ready) cudaEventDestroy(ctx->stats_ready);
+  for (auto& p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  delete ctx;
+}
+
+const char* dsnerf_last_error(const dsnerf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dsnerf_set_weights(dsnerf_ctx* ctx, const float* const* t, int n_tensors) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (!t || n_tensors != DSNERF_NUM_WEIGHT_TENSORS) return fail(ctx, DSNERF_ERR_INVALID, "expected 33 tensors in state_dict order");
+  for (int i = 0; i < n_tensors; ++i) {
+    if (!t[i]) return fail(ctx, DSNERF_ERR_INVALID, "null weight tensor");
+    ctx->hw[i].assign(t[i], t[i] + kTensorSize[i]);
+    for (float v : ctx->hw[i])
+      if (!std::isfinite(v)) return fail(ctx, DSNERF_ERR_INVALID, "non-finite weight");
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());  // weights may be in use by work in flight
+  BlobBuilder bb;
+  size_t off_wt[7], off_w[7], off_b[7];
+  const int sw_idx[7] = {T_S1_0_W, T_S1_2_W, T_S1_4_W, T_S1_6_W, T_S2_0_W, T_S2_2_W, T_S2_4_W};
+  const int fwdK[7] = {64, 256, 256, 256, 320, 256, 256};
+  for (int l = 0; l < 7; ++l) {
+    const std::vector<float>& w = ctx->hw[sw_idx[l]];
+    int in_dim = (l == 0) ? 87 : (l == 4 ? 319 : 256);
+    int col0 = (l == 0) ? 8 : 0;                     // layer 0: PE columns 8..70 only (code/pose folded into the bias)
+    int ncol = (l == 0) ? 63 : in_dim;
+    off_wt[l] = bb.add((size_t)fwdK[l] * 256);
+    off_w[l] = bb.add((size_t)256 * fwdK[l]);
+    for (int o = 0; o < 256; ++o)
+      for (int k = 0; k < ncol; ++k) {
+        float v = w[(size_t)o * in_dim + col0 + k];
+        bb.data[off_wt[l] + (size_t)k * 256 + o] = v;
+        bb.data[off_w[l] + (size_t)o * fwdK[l] + k] = v;
+      }
+    off_b[l] = bb.add(256);
+    for (int o = 0; o < 256; ++o) bb.data[off_b[l] + o] = ctx->hw[sw_idx[l] + 1][o];
+  }
+  size_t off_wd = bb.add(256);
+  for (int o = 0; o < 256; ++o) bb.data[off_wd + o] = ctx->hw[T_DENS_W][o];
+  size_t off_r1 = bb.add(256 * 128), off_r1b = bb.add(128), off_r2 = bb.add(3 * 128), off_r2b = bb.add(4);
+  for (int o = 0; o < 128; ++o)
+    for (int k = 0; k < 256; ++k) bb.data[off_r1 + (size_t)k * 128 + o] = ctx->hw[T_RGB1_W][(size_t)o * 256 + k];
+  for (int o = 0; o < 128; ++o) bb.data[off_r1b + o] = ctx->hw[T_RGB1_B][o];
+  for (int i = 0; i < 3 * 128; ++i) bb.data[off_r2 + i] = ctx->hw[T_RGB3_W][i];
+  for (int i = 0; i < 3; ++i) bb.data[off_r2b + i] = ctx->hw[T_RGB3_B][i];
+  size_t off_l1 = bb.add(9 * 128), off_l1b = bb.add(128), off_l2 = bb.add(128 * 128), off_l2b = bb.add(128), off_l3 = bb.add(128);
+  for (int o = 0; o < 128; ++o)
+    for (int k = 0; k < 9; ++k) bb.data[off_l1 + (size_t)k * 128 + o] = ctx->hw[T_L0_W][(size_t)o * 9 + k];
+  for (int o = 0; o < 128; ++o)
+    for (int k = 0; k < 128; ++k) bb.data[off_l2 + (size_t)k * 128 + o] = ctx->hw[T_L2_W][(size_t)o * 128 + k];
+  for (int o = 0; o < 128; ++o) {
+    bb.data[off_l1b + o] = ctx->hw[T_L0_B][o];
+    bb.data[off_l2b + o] = ctx->hw[T_L2_B][o];
+    bb.data[off_l3 + o] = ctx->hw[T_L4_W][o];
+  }
+  CK(ctx->wblob.ensure(bb.data.size() * sizeof(float)));
+  CK(cudaMemcpy(ctx->wblob.p, bb.data.data(), bb.data.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(ctx->bias0.ensure(256 * sizeof(float)));
+  const float* d = ctx->wblob.as<float>();
+  for (int l = 0; l < 7; ++l) { ctx->sw.wt[l] = d + off_wt[l]; ctx->sw.w[l] = d + off_w[l]; ctx->sw.bias[l] = d + off_b[l]; }
+  ctx->sw.bias[0] = ctx->bias0.as<float>();
+  ctx->sw.w_dens = d + off_wd;
+  ctx->sw.b_dens = ctx->hw[T_DENS_B][0];
+  ctx->sw.wt_rgb1 = d + off_r1; ctx->sw.b_rgb1 = d + off_r1b; ctx->sw.w_rgb2 = d + off_r2; ctx->sw.b_rgb2 = d + off_r2b;
+  ctx->lw.w1t = d + off_l1; ctx->lw.b1 = d + off_l1b; ctx->lw.w2t = d + off_l2; ctx->lw.b2 = d + off_l2b; ctx->lw.w3 = d + off_l3;
+  ctx->lw.b3 = ctx->hw[T_L4_B][0];
+  if (int e = ctx->tw.stage(ctx->hw[T_S1_0_W], ctx->hw[T_S1_2_W], ctx->hw[T_S1_4_W], ctx->hw[T_S1_6_W], ctx->hw[T_S2_0_W], ctx->hw[T_S2_2_W],
+                            ctx->hw[T_S2_4_W], ctx->hw[T_S1_2_B], ctx->hw[T_S1_4_B], ctx->hw[T_S1_6_B], ctx->hw[T_S2_0_B], ctx->hw[T_S2_2_B],
+                            ctx->hw[T_S2_4_B], ctx->hw[T_DENS_W], ctx->hw[T_DENS_B][0], ctx->hw[T_RGB1_W], ctx->hw[T_RGB1_B],
+                            ctx->hw[T_RGB3_W], ctx->hw[T_RGB3_B]))
+    return fail(ctx, DSNERF_ERR_CUDA, std::string("staging tensor-core weights: ") + cudaGetErrorString((cudaError_t)e));
+  ctx->have_weights = true;
+  ctx->have_frame = false;  // the folded bias depends on the weights
+  return 0;
+}
+
+int dsnerf_set_mesh(dsnerf_ctx* ctx, const int32_t* faces, int n_faces, const float* canonical_verts, int n_verts) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (!faces || !canonical_verts || n_faces < 1 || n_verts < 3) return fail(ctx, DSNERF_ERR_INVALID, "bad mesh");
+  for (int i = 0; i < 3 * n_faces; ++i)
+    if (faces[i] < 0 || faces[i] >= n_verts) return fail(ctx, DSNERF_ERR_INVALID, "face index out of range");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  ctx->F = n_faces;
+  ctx->V = n_verts;
+  ctx->h_faces.assign(faces, faces + 3 * (size_t)n_faces);
+  ctx->h_canon.assign(canonical_verts, canonical_verts + 3 * (size_t)n_verts);
+  CK(ctx->faces.ensure(sizeof(int) * 3 * n_faces));
+  CK(ctx->canon.ensure(sizeof(float) * 3 * n_verts));
+  CK(ctx->posed.ensure(sizeof(float) * 3 * n_verts));
+  CK(cudaMemcpy(ctx->faces.p, faces, sizeof(int) * 3 * n_faces, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->canon.p, canonical_verts, sizeof(float) * 3 * n_verts, cudaMemcpyHostToDevice));
+  if (int e = build_grid(ctx, ctx->g_canon, ctx->canon.as<float>(), ctx->h_canon.data(), 0)) return e;
+  CK(cudaDeviceSynchronize());
+  ctx->have_mesh = true;
+  ctx->have_frame = false;
+  return 0;
+}
+
+int dsnerf_set_frame(dsnerf_ctx* ctx, const float* posed_verts, const float* poses, int frame, int zero_code, const float* light_shift,
+                     const float* rot, const float* rot_center, void* stream) {
+  if (int e = check_ready(ctx, false)) return e;
+  if (!posed_verts || !poses) return fail(ctx, DSNERF_ERR_INVALID, "null posed_verts/poses");
+  if (frame < 0 || frame >= 500) return fail(ctx, DSNERF_ERR_INVALID, "frame index outside the 500-row code table");
+  if ((rot == nullptr) != (rot_center == nullptr)) return fail(ctx, DSNERF_ERR_INVALID, "rot and rot_center must be given together");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  // pose feature: batch_rod2quat -> pose_mlp (model/spacenet.py:223-236); identical for every sample of the frame
+  float q[92], h1[64], h2[64], pf[16];
+  rod2quat_host(poses, q);
+  linear_host(ctx->hw[T_P0_W], ctx->hw[T_P0_B], 64, 92, q, h1, true);
+  linear_host(ctx->hw[T_P2_W], ctx->hw[T_P2_B], 64, 64, h1, h2, true);
+  linear_host(ctx->hw[T_P4_W], ctx->hw[T_P4_B], 16, 64, h2, pf, false);
+  size_t vbytes = sizeof(float) * 3 * ctx->V;
+  if (int e = pin_acquire(ctx, vbytes + 256 * sizeof(float))) return e;
+  float* pv = reinterpret_cast<float*>(ctx->pin);
+  float* pb = pv + 3 * (size_t)ctx->V;
+  memcpy(pv, posed_verts, vbytes);
+  // fold code (cols 0..7) and pose feature (cols 71..86) of stage1.0 into its bias (spacenet.py:125-130)
+  const std::vector<float>& w0 = ctx->hw[T_S1_0_W];
+  const float* code = ctx->hw[T_EMB].data() + 8 * (size_t)frame;
+  for (int o = 0; o < 256; ++o) {
+    double acc = ctx->hw[T_S1_0_B][o];
+    if (!zero_code)
+      for (int j = 0; j < 8; ++j) acc += (double)w0[(size_t)o * 87 + j] * code[j];
+    for (int j = 0; j < 16; ++j) acc += (double)w0[(size_t)o * 87 + 71 + j] * pf[j];
+    pb[o] = (float)acc;
+  }
+  CK(cudaMemcpyAsync(ctx->posed.p, pv, vbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->bias0.p, pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  int e = build_grid(ctx, ctx->g_posed, ctx->posed.as<float>(), pv, st);
+  if (int e2 = pin_release(ctx, st)) return e2;
+  if (e) return e;
+  ctx->has_shift = light_shift != nullptr;
+  for (int k = 0; k < 3; ++k) ctx->light_shift[k] = light_shift ? light_shift[k] : 0.f;
+  ctx->has_rot = rot != nullptr;
+  if (rot) { for (int k = 0; k < 4; ++k) ctx->rot[k] = rot[k]; ctx->rot_center[0] = rot_center[0]; ctx->rot_center[1] = rot_center[1]; }
+  ctx->have_frame = true;
+  return 0;
+}
+
+int dsnerf_render(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, int64_t n_rays,
+                  int n_samples, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_vals,
+                  void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  return render_impl(ctx, ray_o, ray_d, near, far, nullptr, n_rays, n_samples, flags, rgb, depth, acc, disp, weights, z_vals,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dsnerf_render_z(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* z_vals, int64_t n_rays, int n_samples,
+                    unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (!z_vals && n_rays > 0) return fail(ctx, DSNERF_ERR_INVALID, "null z_vals");
+  return render_impl(ctx, ray_o, ray_d, nullptr, nullptr, z_vals, n_rays, n_samples, flags, rgb, depth, acc, disp, weights, nullptr,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, int64_t R,
+                       int N, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_vals,
+                       void* stream) {
+  if (int e = check_ready(ctx, true)) return e;
+  if (R < 0 || N < 1) return fail(ctx, DSNERF_ERR_INVALID, "bad sizes");
+  if (R == 0) return 0;
+  if (!ray_o || !ray_d || !near || !far || !rgb || !depth || !acc || !disp) return fail(ctx, DSNERF_ERR_INVALID, "null input/output pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  size_t in_f = (size_t)R * 8, out_f = (size_t)R * 6, opt_f = (size_t)R * N;
+  size_t total = in_f + out_f + (weights ? opt_f : 0) + (z_vals ? opt_f : 0);
+  CK(ctx->io.ensure(total * sizeof(float)));
+  float* d = ctx->io.as<float>();
+  float *d_o = d, *d_d = d + 3 * R, *d_n = d + 6 * R, *d_f = d + 7 * R;
+  float *d_rgb = d + 8 * R, *d_dep = d_rgb + 3 * R, *d_acc = d_dep + R, *d_dsp = d_acc + R;
+  float* d_w = weights ? d_dsp + R : nullptr;
+  float* d_z = z_vals ? (d_dsp + R + (weights ? opt_f : 0)) : nullptr;
+  CK(cudaMemcpyAsync(d_o, ray_o, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_d, ray_d, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_n, near, sizeof(float) * R, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_f, far, sizeof(float) * R, cudaMemcpyHostToDevice, st));
+  if (int e = render_impl(ctx, d_o, d_d, d_n, d_f, nullptr, R, N, flags, d_rgb, d_dep, d_acc, d_dsp, d_w, d_z, st)) return e;
+  CK(cudaMemcpyAsync(rgb, d_rgb, sizeof(float) * 3 * R, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(depth, d_dep, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(acc, d_acc, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(disp, d_dsp, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+  if (weights) CK(cudaMemcpyAsync(weights, d_w, sizeof(float) * opt_f, cudaMemcpyDeviceToHost, st));
+  if (z_vals) CK(cudaMemcpyAsync(z_vals, d_z, sizeof(float) * opt_f, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dsnerf_composite(dsnerf_ctx* ctx, const float* raw, const float* z_vals, const float* ray_d, int64_t R, int N, float* rgb,
+                     float* depth, float* acc, float* disp, float* weights, void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (R < 0 || N < 1) return fail(ctx, DSNERF_ERR_INVALID, "bad sizes");
+  if (R == 0) return 0;
+  if (!raw || !z_vals || !ray_d || !rgb || !depth || !acc || !disp) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  CompositeArgs ca{};
+  ca.raw = reinterpret_cast<const float4*>(raw); ca.ray_d = ray_d; ca.z_in = z_vals; ca.R = R; ca.N = N;
+  ca.rgb = rgb; ca.depth = depth; ca.acc = acc; ca.disp = disp; ca.weights = weights; ca.z_out = nullptr;
+  composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
+  CKL("composite");
+  return 0;
+}
+
+int dsnerf_warp_points(dsnerf_ctx* ctx, const float* pts, int64_t P, float* xyz_cano, uint8_t* transparent, int32_t* idx, void* stream) {
+  if (int e = check_ready(ctx, true)) return e;
+  if (P < 0) return fail(ctx, DSNERF_ERR_INVALID, "bad size");
+  if (P == 0) return 0;
+  if (!pts || !xyz_cano) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  warp_points_kernel<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(pts, P, ctx->posed.as<float>(), ctx->canon.as<float>(), ctx->faces.as<int>(),
+                                                                  ctx->g_posed.g, ctx->F, ctx->g_posed.cent.as<float>(), xyz_cano, transparent, idx);
+  CKL("warp_points");
+  return 0;
+}
+
+namespace {
+__global__ void pack_active_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ skip, int64_t P, float4* __restrict__ active,
+                                   unsigned long long* __restrict__ counter, float* __restrict__ zero_a, float* __restrict__ zero_b, int nb) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool act = s < P && !(skip && skip[s]);
+  if (s < P && !act) {
+    if (zero_a) zero_a[s] = 0.f;
+    if (zero_b) for (int k = 0; k < nb; ++k) zero_b[nb * s + k] = 0.f;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, act);
+  if (m) {
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (act) active[base + __popc(m & ((1u << lane) - 1))] = make_float4(xyz[3 * s], xyz[3 * s + 1], xyz[3 * s + 2], __int_as_float((int)s));
+  }
+}
+__global__ void scatter_points_kernel(const float4* __restrict__ active, const float4* __restrict__ raw, const unsigned long long* __restrict__ n,
+                                      float* __restrict__ color, float* __restrict__ density) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)*n) return;
+  int s = __float_as_int(active[t].w);
+  float4 r = raw[s];
+  if (color) { color[3 * (int64_t)s] = r.x; color[3 * (int64_t)s + 1] = r.y; color[3 * (int64_t)s + 2] = r.z; }
+  density[s] = r.w;
+}
+__global__ void scatter_density2_kernel(const float4* __restrict__ active, const float4* __restrict__ mlp_a, const unsigned long long* __restrict__ n,
+                                        float* __restrict__ density) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)*n) return;
+  density[__float_as_int(active[t].w)] = mlp_a[t].x;
+}
+}  // namespace
+
+int dsnerf_query_density(dsnerf_ctx* ctx, const float* xyz_cano, const uint8_t* transparent, int64_t P, float* density, unsigned flags,
+                         void* stream) {
+  if (int e = check_ready(ctx, true)) return e;
+  if (P < 0 || P > 0x7fffffff) return fail(ctx, DSNERF_ERR_INVALID, "bad size");
+  if (P == 0) return 0;
+  if (!xyz_cano || !density) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  if (int e = ensure_workspace(ctx, P, 1)) return e;
+  unsigned long long* cnt = ctx->counters.as<unsigned long long>();
+  CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 4, st));
+  unsigned blocks = (unsigned)((P + 255) / 256);
+  pack_active_kernel<<<blocks, 256, 0, st>>>(xyz_cano, transparent, P, ctx->active.as<float4>(), cnt, density, nullptr, 0);
+  CKL("pack_active");
+  if (int e = launch_mlp(ctx, cnt, 0, flags, 1, st)) return e;
+  scatter_density2_kernel<<<blocks, 256, 0, st>>>(ctx->active.as<float4>(), ctx->mlp_a.as<float4>(), cnt, density);
+  CKL("scatter_density");
+  return 0;
+}
+
+int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz_cano, const float* view_dir, int64_t P, float* color,
+                       float* density, unsigned flags, void* stream) {
+  if (int e = check_ready(ctx, true)) return e;
+  if (P < 0 || P > 0x7fffffff) return fail(ctx, DSNERF_ERR_INVALID, "bad size");
+  if (P == 0) return 0;
+  if (!xyz_world || !xyz_cano || !view_dir || !color || !density) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  if (int e = ensure_workspace(ctx, P, 1)) return e;
+  unsigned long long* cnt = ctx->counters.as<unsigned long long>();
+  CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 4, st));
+  unsigned blocks = (unsigned)((P + 255) / 256);
+  pack_active_kernel<<<blocks, 256, 0, st>>>(xyz_cano, nullptr, P, ctx->active.as<float4>(), cnt, nullptr, nullptr, 0);
+  CKL("pack_active");
+  if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
+  ShadeArgs sa = base_shade_args(ctx);
+  sa.n_active = cnt;
+  sa.xyz_world = xyz_world;
+  sa.view_dir = view_dir;
+  sa.N = 1;
+  shade_kernel<<<ctx->sm_count, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
+  CKL("shade");
+  scatter_points_kernel<<<blocks, 256, 0, st>>>(ctx->active.as<float4>(), ctx->raw.as<float4>(), cnt, color, density);
+  CKL("scatter_points");
+  return 0;
+}
+
+int dsnerf_resample(dsnerf_ctx* ctx, const float* z_in, const float* weights, int64_t R, int N, int n_importance, float* z_out, void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (R < 0 || N < 3 || N > 1024 || n_importance < 1 || n_importance > 1024) return fail(ctx, DSNERF_ERR_INVALID, "bad sizes");
+  if (R == 0) return 0;
+  if (!z_in || !weights || !z_out) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  size_t smem = sizeof(float) * (size_t)(2 * N + n_importance) * 4;
+  resample_kernel<<<(unsigned)((R + 3) / 4), 128, smem, st>>>(z_in, weights, R, N, n_importance, z_out);
+  CKL("resample");
+  return 0;
+}
+
+int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
+  if (!ctx || !out) return DSNERF_ERR_INVALID;
+  if (ctx->stats.rays > 0) {
+    CK(cudaEventSynchronize(ctx->stats_ready));
+    ctx->stats.evaluated_samples = (int64_t)ctx->h_counters[0];
+    ctx->stats.nn_candidates = (int64_t)ctx->h_counters[1];
+    ctx->stats.algorithmic_flop = 1804544.0 * (double)ctx->stats.evaluated_samples;
+  }
+  *out = ctx->stats;
+  return 0;
+}
+
+int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  ctx->profile = enable ? 1 : 0;
+  return 0;
+}
+
+int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int reset) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  for (auto& p : ctx->pending) {
+    CK(cudaEventSynchronize(p.second));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, p.first, p.second));
+    ctx->mlp_ms += ms;
+    ctx->mlp_launches += 1;
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  ctx->pending.clear();
+  if (mlp_ms) *mlp_ms = ctx->mlp_ms;
+  if (mlp_launches) *mlp_launches = ctx->mlp_launches;
+  if (reset) { ctx->mlp_ms = 0; ctx->mlp_launches = 0; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+// Shading (normal_local2world + LightingMLP) and compositing (raw2outputs).
+#pragma once
+#include "geom.cuh"
+
+namespace dsn {
+
+struct LightWeights {
+  const float* w1t;  // [9][128]   lights_encoding.0 transposed
+  const float* b1;   // [128]
+  const float* w2t;  // [128][128] lights_encoding.2 transposed
+  const float* b2;   // [128]
+  const float* w3;   // [128]      lights_encoding.4
+  float b3;
+};
+
+struct ShadeArgs {
+  const float4* active;   // (xyz_cano, bits(sample))
+  const float4* mlp_a;    // (sigma, essence)
+  const float4* mlp_g;    // (d sigma / d xyz_cano, -)
+  const unsigned long long* n_active;
+  int64_t n_active_host;  // used when n_active == NULL
+  const float* ray_o; const float* ray_d; const float* near; const float* far; const float* z_in; const float* tvals;
+  int N;
+  const float* posed; const float* canon; const int* faces; const float* cent_canon; int F;
+  // explicit-point mode (dsnerf_eval_points): world position / view direction per point instead of rays
+  const float* xyz_world; const float* view_dir;
+  float light_shift[3]; int has_shift;
+  float rot[4]; float rot_center[2]; int has_rot;
+  float4* raw;            // (R*N) rgb + sigma, indexed by sample id
+};
+
+constexpr int SHADE_THREADS = 128;
+constexpr size_t SHADE_SMEM = (size_t)(9 * 128 + 128 + 128 * 128 + 128 + 128 + 128 * SHADE_THREADS) * sizeof(float);
+
+// model/spacenet.py:278-298 normal_local2world.  The reference maps xyz_cano and xyz_cano+g onto
+// the posed triangle and normalises the difference; the map is affine in the point, so the
+// difference is the linear part applied to g (scale of g is irrelevant and removed up front).
+__device__ __forceinline__ V3 normal_to_world(V3 g, V3 c0, V3 c1, V3 c2, V3 m0, V3 m1, V3 m2) {
+  float sc = fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fabsf(g.z));
+  if (!(sc > 0.f)) return v3(0.f, 0.f, 0.f);
+  float is = 1.0f / sc;
+  g = v3(g.x * is, g.y * is, g.z * is);
+  V3 e1c = v3(c1.x - c0.x, c1.y - c0.y, c1.z - c0.z), e2c = v3(c2.x - c0.x, c2.y - c0.y, c2.z - c0.z);
+  V3 nc = v3(e1c.y * e2c.z - e1c.z * e2c.y, e1c.z * e2c.x - e1c.x * e2c.z, e1c.x * e2c.y - e1c.y * e2c.x);
+  float inc = rsqrtf(nc.x * nc.x + nc.y * nc.y + nc.z * nc.z);
+  nc = v3(nc.x * inc, nc.y * inc, nc.z * inc);
+  float hg = g.x * nc.x + g.y * nc.y + g.z * nc.z;
+  V3 gp = v3(g.x - hg * nc.x, g.y - hg * nc.y, g.z - hg * nc.z);
+  float d00 = e2c.x * e2c.x + e2c.y * e2c.y + e2c.z * e2c.z;
+  float d01 = e2c.x * e1c.x + e2c.y * e1c.y + e2c.z * e1c.z;
+  float d11 = e1c.x * e1c.x + e1c.y * e1c.y + e1c.z * e1c.z;
+  float d02 = e2c.x * gp.x + e2c.y * gp.y + e2c.z * gp.z;
+  float d12 = e1c.x * gp.x + e1c.y * gp.y + e1c.z * gp.z;
+  float inv = 1.0f / (d00 * d11 - d01 * d01);
+  float u = (d11 * d02 - d01 * d12) * inv, v = (d00 * d12 - d01 * d02) * inv;
+  V3 e1w = v3(m1.x - m0.x, m1.y - m0.y, m1.z - m0.z), e2w = v3(m2.x - m0.x, m2.y - m0.y, m2.z - m0.z);
+  V3 nw = v3(e1w.y * e2w.z - e1w.z * e2w.y, e1w.z * e2w.x - e1w.x * e2w.z, e1w.x * e2w.y - e1w.y * e2w.x);
+  float inw = rsqrtf(nw.x * nw.x + nw.y * nw.y + nw.z * nw.z);
+  V3 r = v3(u * e2w.x + v * e1w.x + hg * nw.x * inw, u * e2w.y + v * e1w.y + hg * nw.y * inw, u * e2w.z + v * e1w.z + hg * nw.z * inw);
+  float n = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z);
+  float in = 1.0f / fmaxf(n, 1e-12f);  // F.normalize eps
+  return v3(r.x * in, r.y * in, r.z * in);
+}
+
+// One thread per active sample; the 128x128 lighting layer runs out of shared memory.
+__global__ void __launch_bounds__(SHADE_THREADS) shade_kernel(ShadeArgs a, LightWeights L, Grid gc) {
+  extern __shared__ __align__(16) float sm[];
+  float* w1t = sm;                 // 9*128
+  float* b1 = w1t + 9 * 128;       // 128
+  float* w2t = b1 + 128;           // 128*128
+  float* b2 = w2t + 128 * 128;     // 128
+  float* w3 = b2 + 128;            // 128
+  float* h1 = w3 + 128;            // [128 units][SHADE_THREADS samples]
+  for (int i = threadIdx.x; i < 9 * 128; i += SHADE_THREADS) w1t[i] = L.w1t[i];
+  for (int i = threadIdx.x; i < 128 * 128; i += SHADE_THREADS) w2t[i] = L.w2t[i];
+  for (int i = threadIdx.x; i < 128; i += SHADE_THREADS) { b1[i] = L.b1[i]; b2[i] = L.b2[i]; w3[i] = L.w3[i]; }
+  __syncthreads();
+  int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
+  int64_t n_round = (n_active + SHADE_THREADS - 1) / SHADE_THREADS * SHADE_THREADS;
+  for (int64_t base = (int64_t)blockIdx.x * SHADE_THREADS; base < n_round; base += (int64_t)gridDim.x * SHADE_THREADS) {
+    int64_t t = base + threadIdx.x;
+    bool live = t < n_active;
+    float in[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float4 ma = make_float4(0, 0, 0, 0);
+    int sample = 0;
+    if (live) {
+      float4 ac = a.active[t];
+      ma = a.mlp_a[t];
+      float4 mg = a.mlp_g[t];
+      sample = __float_as_int(ac.w);
+      int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr);
+      if (idx < 0) {  // cannot happen for warped points; keep the exact answer anyway
+        float best = 3.0e38f;
+        for (int f = 0; f < a.F; ++f) {
+          float dx = xsub(ac.x, a.cent_canon[3 * f]), dy = xsub(ac.y, a.cent_canon[3 * f + 1]), dz = xsub(ac.z, a.cent_canon[3 * f + 2]);
+          float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+          if (d < best) { best = d; idx = f; }
+        }
+      }
+      int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
+      V3 nw = normal_to_world(v3(mg.x, mg.y, mg.z), ldv3(a.canon, i0), ldv3(a.canon, i1), ldv3(a.canon, i2),
+                              ldv3(a.posed, i0), ldv3(a.posed, i1), ldv3(a.posed, i2));
+      float px, py, pz, dx, dy, dz;
+      if (a.xyz_world) {
+        px = a.xyz_world[3 * (int64_t)sample]; py = a.xyz_world[3 * (int64_t)sample + 1]; pz = a.xyz_world[3 * (int64_t)sample + 2];
+        dx = a.view_dir[3 * (int64_t)sample]; dy = a.view_dir[3 * (int64_t)sample + 1]; dz = a.view_dir[3 * (int64_t)sample + 2];
+      } else {
+        int64_t r = sample / a.N;
+        int i = sample - (int)(r * a.N);
+        float z = a.z_in ? a.z_in[sample] : sample_z(a.near[r], a.far[r], a.tvals[i]);
+        dx = a.ray_d[3 * r]; dy = a.ray_d[3 * r + 1]; dz = a.ray_d[3 * r + 2];
+        px = xadd(a.ray_o[3 * r], xmul(dx, z)); py = xadd(a.ray_o[3 * r + 1], xmul(dy, z)); pz = xadd(a.ray_o[3 * r + 2], xmul(dz, z));
+      }
+      if (a.has_rot) {  // model/spacenet.py:254-258: xy <- (xy - c) @ rot + c
+        float qx = px - a.rot_center[0], qy = py - a.rot_center[1];
+        px = qx * a.rot[0] + qy * a.rot[2] + a.rot_center[0];
+        py = qx * a.rot[1] + qy * a.rot[3] + a.rot_center[1];
+      }
+      if (a.has_shift) { px += a.light_shift[0]; py += a.light_shift[1]; pz += a.light_shift[2]; }  // :260-263
+      float dn = xnorm3(v3(dx, dy, dz));
+      in[0] = nw.x; in[1] = nw.y; in[2] = nw.z; in[3] = px; in[4] = py; in[5] = pz;
+      in[6] = xdiv(dx, dn); in[7] = xdiv(dy, dn); in[8] = xdiv(dz, dn);
+    }
+    // LightingMLP (model/spacenet.py:165-188): 9 -> 128 -> 128 -> 1, ReLU, ReLU, ELU; color = (out+1)*essence
+    __syncthreads();
+    for (int j = 0; j < 128; ++j) {
+      float acc = b1[j];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc = fmaf(in[k], w1t[k * 128 + j], acc);
+      h1[j * SHADE_THREADS + threadIdx.x] = fmaxf(acc, 0.f);
+    }
+    float out = L.b3;
+    for (int jb = 0; jb < 128; jb += 16) {
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = b2[jb + j];
+      for (int k = 0; k < 128; ++k) {
+        float x = h1[k * SHADE_THREADS + threadIdx.x];
+        const float4* wr = reinterpret_cast<const float4*>(w2t + k * 128 + jb);
+        float4 wa = wr[0], wb = wr[1], wc = wr[2], wd = wr[3];
+        acc[0] = fmaf(x, wa.x, acc[0]); acc[1] = fmaf(x, wa.y, acc[1]); acc[2] = fmaf(x, wa.z, acc[2]); acc[3] = fmaf(x, wa.w, acc[3]);
+        acc[4] = fmaf(x, wb.x, acc[4]); acc[5] = fmaf(x, wb.y, acc[5]); acc[6] = fmaf(x, wb.z, acc[6]); acc[7] = fmaf(x, wb.w, acc[7]);
+        acc[8] = fmaf(x, wc.x, acc[8]); acc[9] = fmaf(x, wc.y, acc[9]); acc[10] = fmaf(x, wc.z, acc[10]); acc[11] = fmaf(x, wc.w, acc[11]);
+        acc[12] = fmaf(x, wd.x, acc[12]); acc[13] = fmaf(x, wd.y, acc[13]); acc[14] = fmaf(x, wd.z, acc[14]); acc[15] = fmaf(x, wd.w, acc[15]);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) out = fmaf(fmaxf(acc[j], 0.f), w3[jb + j], out);
+    }
+    float light = (out > 0.f ? out : expm1f(out)) + 1.0f;
+    if (live) a.raw[sample] = make_float4(light * ma.y, light * ma.z, light * ma.w, ma.x);
+  }
+}
+
+// density-only variant (Renderer.query_volume): raw.w = sigma
+__global__ void scatter_density_kernel(const float4* __restrict__ active, const float4* __restrict__ mlp_a, int64_t n, float* __restrict__ density) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) density[__float_as_int(active[t].w)] = mlp_a[t].x;
+}
+
+// utils/nerf_net_utils.py:5-56 raw2outputs (raw_noise_std = 0, white_bkgd = False).
+// One warp per ray; 32 samples per step with an in-register exclusive product scan for the
+// transmittance and a running carry across steps.
+struct CompositeArgs {
+  const float4* raw;       // (R,N) rgb+sigma
+  const float* ray_d;      // (R,3)
+  const float* near; const float* far; const float* tvals;  // z = near(1-t)+far t   (z_in == NULL)
+  const float* z_in;       // explicit (R,N) z
+  int64_t R; int N;
+  float* rgb; float* depth; float* acc; float* disp; float* weights; float* z_out;
+};
+
+__global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= a.R) return;
+  float nd = xnorm3(v3(a.ray_d[3 * r], a.ray_d[3 * r + 1], a.ray_d[3 * r + 2]));
+  float near = a.z_in ? 0.f : a.near[r], far = a.z_in ? 0.f : a.far[r];
+  float T = 1.0f;
+  float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+  for (int base = 0; base < a.N; base += 32) {
+    int i = base + lane;
+    bool live = i < a.N;
+    float z = 0.f, zn = 0.f;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      z = a.z_in ? a.z_in[r * a.N + i] : sample_z(near, far, a.tvals[i]);
+      if (i + 1 < a.N) zn = a.z_in ? a.z_in[r * a.N + i + 1] : sample_z(near, far, a.tvals[i + 1]);
+      c = a.raw[r * a.N + i];
+    }
+    float dist = (i + 1 < a.N) ? xsub(zn, z) : 1e10f;
+    dist = xmul(dist, nd);
+    float alpha = live ? xsub(1.0f, expf(-xmul(fmaxf(c.w, 0.f), dist))) : 0.f;
+    float t = xadd(xsub(1.0f, alpha), 1e-10f);
+    // inclusive product scan
+    float p = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float q = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) p *= q;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) excl = 1.0f;
+    float w = alpha * (T * excl);
+    T *= __shfl_sync(0xffffffffu, p, 31);
+    if (live) {
+      sr = fmaf(w, c.x, sr); sg = fmaf(w, c.y, sg); sb = fmaf(w, c.z, sb);
+      sd = fmaf(w, z, sd); sa += w;
+      if (a.weights) a.weights[r * a.N + i] = w;
+      if (a.z_out) a.z_out[r * a.N + i] = z;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o); sa += __shfl_xor_sync(0xffffffffu, sa, o);
+  }
+  if (lane == 0) {
+    a.rgb[3 * r] = sr; a.rgb[3 * r + 1] = sg; a.rgb[3 * r + 2] = sb;
+    a.depth[r] = sd; a.acc[r] = sa;
+    float q = xdiv(sd, sa);  // 0/0 = NaN when nothing was hit, as in the reference
+    a.disp[r] = (q != q) ? q : xdiv(1.0f, fmaxf(1e-10f, q));
+  }
+}
+
+// Hierarchical resampling (config 3).  The reference calls an undefined Renderer.resampling
+// (can_render.py:213); this implements the written spec in DESIGN.md "Config 3" =
+// oracle/oracle.py:sample_pdf: deterministic inverse-CDF sampling of the coarse weights
+// (NeRF sample_pdf, det=True) merged with the coarse z and sorted.  One warp per ray.
+__global__ void __launch_bounds__(128) resample_kernel(const float* __restrict__ z_in, const float* __restrict__ weights, int64_t R, int N,
+                                                       int n_imp, float* __restrict__ z_out) {
+  extern __shared__ float rs[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * 4 + warp;
+  if (r >= R) return;
+  int per = 2 * N + n_imp;
+  float* bins = rs + warp * per;   // N-1
+  float* cdf = bins + N;           // N-1
+  float* zn = cdf + N;             // n_imp
+  const float* z = z_in + r * N;
+  const float* w = weights + r * N;
+  float part = 0.f;
+  for (int j = lane; j < N - 1; j += 32) bins[j] = 0.5f * (z[j + 1] + z[j]);
+  for (int j = lane; j < N - 2; j += 32) part += w[j + 1] + 1e-5f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  __syncwarp();
+  if (lane == 0) {
+    float c = 0.f;
+    cdf[0] = 0.f;
+    for (int j = 0; j < N - 2; ++j) { c += (w[j + 1] + 1e-5f) / part; cdf[j + 1] = c; }
+  }
+  __syncwarp();
+  int len = N - 1;
+  for (int k = lane; k < n_imp; k += 32) {
+    float u = linspace01(k, n_imp);
+    int lo = 0, hi = len;  // first index with cdf > u
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    int below = max(lo - 1, 0), above = min(lo, len - 1);
+    float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
+    float den = c1 - c0;
+    if (den < 1e-5f) den = 1.0f;
+    zn[k] = b0 + (u - c0) / den * (b1 - b0);
+  }
+  __syncwarp();
+  float* out = z_out + r * (N + n_imp);
+  for (int i = lane; i < N; i += 32) {  // coarse z: rank = i + #(zn < z[i])
+    float v = z[i];
+    int lo = 0, hi = n_imp;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (zn[mid] < v) lo = mid + 1; else hi = mid; }
+    out[i + lo] = v;
+  }
+  for (int k = lane; k < n_imp; k += 32) {  // new z: rank = k + #(z <= zn[k])
+    float v = zn[k];
+    int lo = 0, hi = N;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (z[mid] <= v) lo = mid + 1; else hi = mid; }
+    out[k + lo] = v;
+  }
+}
+
+}  // namespace dsn

@@ -1,0 +1,155 @@
+/*
+ * dsnerf.h -- C ABI of libdsnerf.so, the B200 (sm_100a) volume-rendering path
+ * for Dual-Space NeRF.
+ *
+ * The reference (zyhbili/Dual-Space-NeRF) is pure Python: its "operator
+ * interface" for this path is the class can_render.Renderer
+ * (can_render.py:14-406).  It has no FFI, so these entry points are what a
+ * binding for that class has to call; each one names the reference code it
+ * replaces.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative dsnerf_status; the
+ *    message for the last failure on a context is dsnerf_last_error(ctx);
+ *    nothing throws or aborts;
+ *  - all arrays are fp32, contiguous, row-major; "dev" pointers are CUDA device
+ *    memory on the context's device, "host" pointers are ordinary host memory;
+ *  - the caller owns every I/O buffer; the context owns workspace and the
+ *    staged weights/meshes;
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*, 0 =
+ *    default stream) unless the name ends in _host; a context is bound to one
+ *    device and is not thread-safe: use one context per rank/GPU;
+ *  - near/far are never modified (the reference's in-place overwrite,
+ *    utils/pts_utils.py:52-53, is an accident of its implementation).
+ */
+#ifndef DSNERF_H_
+#define DSNERF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSNERF_ABI_VERSION 1
+
+typedef struct dsnerf_ctx dsnerf_ctx;
+
+typedef enum {
+  DSNERF_OK = 0,
+  DSNERF_ERR_INVALID = -1,  /* bad argument / call order */
+  DSNERF_ERR_CUDA = -2,     /* CUDA runtime error (message has the details) */
+  DSNERF_ERR_NO_DEVICE = -3,
+  DSNERF_ERR_STATE = -4     /* weights / mesh / frame not set yet */
+} dsnerf_status;
+
+/* dsnerf_render flags */
+#define DSNERF_SAMPLE_UNIFORM 0u   /* utils/pts_utils.py:3  uniform_sampling */
+#define DSNERF_SAMPLE_GG 1u        /* utils/pts_utils.py:18 geometry_guided_ray_marching */
+#define DSNERF_MLP_FP32_SIMT 2u    /* debug: evaluate the MLP with the fp32 SIMT kernel instead of tcgen05 */
+
+/* number of tensors in DualSpaceNeRF.state_dict() (model/spacenet.py), order in SURVEY.md 8b */
+#define DSNERF_NUM_WEIGHT_TENSORS 33
+
+typedef struct {
+  int64_t rays;               /* R of the last render */
+  int64_t samples;            /* R*N nominal samples */
+  int64_t evaluated_samples;  /* samples that were not transparent => went through the MLP */
+  int64_t nn_candidates;      /* centroid distance evaluations of the last render (0 unless profiling is on) */
+  double algorithmic_flop;    /* evaluated_samples * 1 804 544 */
+  int32_t kernel_launches;    /* kernels launched by the last render call */
+  int32_t reserved;
+} dsnerf_stats_t;
+
+int dsnerf_abi_version(void);
+
+/* Renderer.__init__ (can_render.py:15-23): one context per GPU. */
+int dsnerf_create(dsnerf_ctx** out, int device);
+void dsnerf_destroy(dsnerf_ctx* ctx);
+const char* dsnerf_last_error(const dsnerf_ctx* ctx);
+
+/* render.net.load_state_dict(ckpt["model"]) (validate.py:27): 33 HOST pointers in
+ * state_dict order (nerf.embedding.weight, nerf.stage1.0.weight, ... pose_mlp.4.bias);
+ * nn.Linear layout [out,in] row-major.  Splits/pads/transposes once into the
+ * device layouts the kernels use. */
+int dsnerf_set_weights(dsnerf_ctx* ctx, const float* const* host_tensors, int n_tensors);
+
+/* Renderer.load_body_model (can_render.py:382-406): faces (F,3) int32 and the
+ * canonical (X-pose) vertices (V,3), HOST pointers.  Builds the canonical-space
+ * nearest-centroid grid used by normal_local2world (model/spacenet.py:278-298). */
+int dsnerf_set_mesh(dsnerf_ctx* ctx, const int32_t* faces, int n_faces, const float* canonical_verts, int n_verts);
+
+/* Per-frame state read from the reference's batch dict + model switches:
+ *   posed_verts (V,3) host   batch["xyz"]                          (can_render.py:353)
+ *   poses (24,3) host        batch["poses"], joint 0 ignored       (model/spacenet.py:223)
+ *   frame                    batch["frame"], row of the 500x8 code table
+ *   zero_code != 0           render.net.nerf.w = 0                 (model/spacenet.py:126-129)
+ *   light_shift (3) or NULL  light_center - mean(batch["Th"])      (model/spacenet.py:260-263)
+ *   rot (2,2)+rot_center (2) or NULL   set_rot / set_rot_center    (model/spacenet.py:254-258)
+ * Computes the pose feature (pose_mlp), folds code+pose into the first layer's
+ * bias, uploads the posed mesh and rebuilds its nearest-centroid grid. */
+int dsnerf_set_frame(dsnerf_ctx* ctx, const float* posed_verts, const float* poses, int frame, int zero_code,
+                     const float* light_shift, const float* rot, const float* rot_center, void* stream);
+
+/* Renderer.render / batchify_rays_view (can_render.py:137-168, 172-245), eval mode:
+ * sample -> warp -> SpaceNet + density-gradient normal + lighting -> raw2outputs.
+ * DEVICE pointers: ray_o, ray_d (R,3); near, far (R); outputs rgb (R,3), depth,
+ * acc, disp (R); optional weights, z_vals (R,N) (NULL to skip). */
+int dsnerf_render(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                  int64_t n_rays, int n_samples, unsigned flags, float* rgb, float* depth, float* acc, float* disp,
+                  float* weights, float* z_vals, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies inputs to the device,
+ * renders, copies the outputs back and synchronises the stream.  This is the
+ * entry point Renderer.render_view (can_render.py:248-278) maps to, and what
+ * bench.py times as "e2e". */
+int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                       int64_t n_rays, int n_samples, unsigned flags, float* rgb, float* depth, float* acc,
+                       float* disp, float* weights, float* z_vals, void* stream);
+
+/* Second pass of a hierarchical render on caller-supplied, sorted z (R,N) (DEVICE).
+ * The reference's Renderer.resampling is undefined (can_render.py:213); see
+ * DESIGN.md "Config 3". */
+int dsnerf_render_z(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* z_vals, int64_t n_rays,
+                    int n_samples, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights,
+                    void* stream);
+
+/* Deterministic inverse-CDF resampling + merge (own spec, oracle/oracle.py:sample_pdf):
+ * z_in, weights (R,N) -> z_out (R, N + n_importance) sorted.  DEVICE pointers. */
+int dsnerf_resample(dsnerf_ctx* ctx, const float* z_in, const float* weights, int64_t n_rays, int n_samples,
+                    int n_importance, float* z_out, void* stream);
+
+/* utils/nerf_net_utils.py:5-56 raw2outputs (noise 0, white_bkgd False) as a
+ * stand-alone op.  raw (R,N,4) = rgb + density, z_vals (R,N), ray_d (R,3); DEVICE. */
+int dsnerf_composite(dsnerf_ctx* ctx, const float* raw, const float* z_vals, const float* ray_d, int64_t n_rays,
+                     int n_samples, float* rgb, float* depth, float* acc, float* disp, float* weights, void* stream);
+
+/* Renderer.w2l_without_lbs (can_render.py:333-379) as a stand-alone op on the
+ * current frame: pts (P,3) -> xyz_cano (P,3), transparent (P) uint8, idx (P) int32
+ * (nearest posed-triangle index; NULL to skip).  DEVICE pointers. */
+int dsnerf_warp_points(dsnerf_ctx* ctx, const float* pts, int64_t n_pts, float* xyz_cano, uint8_t* transparent,
+                       int32_t* idx, void* stream);
+
+/* Renderer.query_volume (can_render.py:280-296) / net(..., density_only=True)
+ * (model/spacenet.py:238-241): canonical points (P,3) -> density (P); entries with
+ * transparent[p] != 0 (may be NULL) are set to 0.  DEVICE pointers. */
+int dsnerf_query_density(dsnerf_ctx* ctx, const float* xyz_cano, const uint8_t* transparent, int64_t n_pts,
+                         float* density, unsigned flags, void* stream);
+
+/* DualSpaceNeRF.forward (model/spacenet.py:210-266) on explicit points:
+ * xyz_world, xyz_cano, view_dir (P,3) -> color (P,3), density (P).  DEVICE pointers. */
+int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz_cano, const float* view_dir,
+                       int64_t n_pts, float* color, float* density, unsigned flags, void* stream);
+
+/* Counters of the last render on this context (synchronises the stream it ran on). */
+int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
+
+/* CUDA-event timing of the MLP kernel inside render calls: enable, render, read
+ * back the accumulated milliseconds / launches since the last reset. */
+int dsnerf_profile(dsnerf_ctx* ctx, int enable);
+int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSNERF_H_ */

@@ -1,0 +1,169 @@
+"""GPU parity tests: the CUDA path (through the Renderer drop-in and the C ABI)
+against the committed reference goldens and the CPU oracle on identical inputs."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import common as C
+from dual_space_nerf_b200 import net as N
+from dual_space_nerf_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+import os
+
+MODES = {"tc": 2 if os.environ.get("DSNERF_TEST_FORCE_SIMT") else 0, "simt": 2}
+
+
+def make_cfg(n, mode="GG", fine=-1):
+    return SimpleNamespace(MODEL=SimpleNamespace(TYPE="nerf", COARSE_RAY_SAMPLING=n, FINE_RAY_SAMPLING=fine,
+                                                 sample_points_mode=mode, perturb=1.0, raw_noise_std=1.0),
+                           DATASETS=SimpleNamespace(SMPL_PATH=None))
+
+
+def make_renderer(sc, n, mode="GG", mlp="tc", net=None, fine=-1):
+    from dual_space_nerf_b200.renderer import Renderer
+
+    net = net or N.synthetic_net(0)
+    r = Renderer(net, None, make_cfg(n, mode, fine), torch.from_numpy(sc["canonical"]), device=0, faces=sc["faces"])
+    r.flags_extra = MODES[mlp]
+    r.eval()
+    return r
+
+
+def to_np(d):
+    return {k: v.detach().cpu().numpy() for k, v in d.items()}
+
+
+def oracle_run(sc, sd, n, rays=None, **kw):
+    from oracle import oracle as O
+
+    sel = slice(None) if rays is None else rays
+    st = {}
+    out = O.Oracle(sd, sc["canonical"], sc["faces"], n, **kw).render(
+        sc["ray_o"][sel], sc["ray_d"][sel], sc["near"][sel], sc["far"][sel], sc["posed"], sc["poses"], sc["frame"],
+        Th=sc["Th"], stages=st)
+    return out, st
+
+
+def kink_rays(st, n):
+    return (st["kink_margin"] < C.KINK_MARGIN).reshape(-1, n).any(1)
+
+
+@pytest.mark.parametrize("mlp", ["tc", "simt"])
+def test_render_view_config1_vs_reference_golden(mlp, scene64, state_dict):
+    """Config 1 (64x64, 32 samples) full frame against the reference's own render_view output."""
+    g = C.golden("render_64x64x32.npz")
+    r = make_renderer(scene64, 32, mlp=mlp)
+    out = r.render_view(S.to_batch(scene64, torch))
+    _, st = oracle_run(scene64, state_dict, 32)
+    got = {"color": out["coarse_color"].numpy().reshape(-1, 3), "depth_map": out["coarse_depth"].numpy().ravel(),
+           "acc_map": out["coarse_acc"].numpy().ravel(), "disp_map": out["coarse_disp"].numpy().ravel()}
+    ref = {"color": g["coarse_color"].reshape(-1, 3), "depth_map": g["coarse_depth"].ravel(),
+           "acc_map": g["coarse_acc"].ravel(), "disp_map": g["coarse_disp"].ravel()}
+    stats = C.check_rays(got, ref, kink_rays(st, 32), what=f"render_view[{mlp}]")
+    print(mlp, stats)
+    # discrete decisions are bit-identical to the oracle: same set of evaluated samples
+    assert r.ctx.stats()["evaluated_samples"] == int((~st["mask"]).sum())
+
+
+@pytest.mark.parametrize("mlp", ["tc", "simt"])
+def test_render_128x128x64_vs_reference_golden(mlp, state_dict):
+    g = C.golden("render_128x128x64.npz")
+    rays = g["rays"]
+    sc = S.make_scene(128, 128)
+    r = make_renderer(sc, 64, mlp=mlp)
+    out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    _, st = oracle_run(sc, state_dict, 64, rays)
+    stats = C.check_rays(out, g, kink_rays(st, 64), what=f"render 128[{mlp}]")
+    print(mlp, stats)
+    assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0  # GG near/far and sample placement are bit-exact
+    assert np.abs(out["weights"] - g["weights"]).max() < 1e-4
+
+
+def test_uniform_and_novel_pose_vs_reference_golden(scene64, state_dict):
+    g = C.golden("render_uniform.npz")
+    rays = g["rays"]
+    r = make_renderer(scene64, 16, mode="uniform")
+    out = to_np(r.render(S.to_batch(scene64, torch, rays=rays))["coarse"])
+    _, st = oracle_run(scene64, state_dict, 16, rays, mode="uniform")
+    C.check_rays(out, g, kink_rays(st, 16), what="uniform")
+    assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0
+
+    g = C.golden("render_novelpose.npz")
+    rays = g["rays"]
+    sc = S.make_scene(64, 64, pose_seed=3)
+    net = N.synthetic_net(0)
+    net.nerf.w = 0                                            # test.py:193
+    net.set_light_center(torch.from_numpy(S.LIGHT_CENTER_313))  # test.py:194-196
+    r = make_renderer(sc, 32, net=net)
+    out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    _, st = oracle_run(sc, state_dict, 32, rays, zero_code=True, light_center=S.LIGHT_CENTER_313)
+    C.check_rays(out, g, kink_rays(st, 32), what="novel pose")
+
+
+def test_stage_ops_bit_exact_vs_golden(scene64, state_dict):
+    """w2l_without_lbs through the C ABI: nearest-triangle index, mask and canonical point are bit-exact."""
+    g = C.golden("stages_64x64x32.npz")
+    r = make_renderer(scene64, 32)
+    pts = torch.from_numpy(g["pts"]).reshape(1, -1, 32, 3)
+    cano, tm, idx = r.w2l_without_lbs(pts, S.to_batch(scene64, torch), return_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    assert np.array_equal(tm.cpu().numpy().ravel(), g["mask"])
+    assert C.bits_equal(cano.cpu().numpy(), g["xyz_cano"]) == 0
+    # density-only query on the canonical points (Renderer.query_volume)
+    dens = r.query_volume(cano[None], torch.tensor([scene64["frame"]]), tm, S.to_batch(scene64, torch))
+    act = ~g["mask"]
+    assert np.abs(dens.cpu().numpy().ravel()[act] - g["density"][act]).max() < 5e-3  # |sigma| ~ 170
+    assert np.all(dens.cpu().numpy().ravel()[g["mask"]] == 0)
+
+
+def test_composite_op_vs_oracle():
+    from oracle import oracle as O
+    from dual_space_nerf_b200 import lib
+    import ctypes
+
+    rng = np.random.RandomState(0)
+    for R, Nn in ((1, 1), (7, 5), (300, 64), (33, 100)):
+        raw = rng.randn(R, Nn, 4).astype(np.float32)
+        raw[..., 3] *= 50
+        z = np.sort(rng.rand(R, Nn).astype(np.float32) + 2, -1)
+        d = rng.randn(R, 3).astype(np.float32)
+        if R > 5:
+            raw[3, :, 3] = -1.0  # nothing hit: acc == 0 -> disp NaN as in the reference
+        ref = O.raw2outputs(raw[..., :3], raw[..., 3], z, d)
+        ctx = lib.Context(0)
+        t = lambda a: torch.from_numpy(a).cuda()
+        traw, tz, td = t(raw), t(z), t(d)
+        rgb, dep, acc, dsp, w = (torch.empty(R, 3).cuda(), torch.empty(R).cuda(), torch.empty(R).cuda(), torch.empty(R).cuda(),
+                                 torch.empty(R, Nn).cuda())
+        p = lambda x: ctypes.c_void_p(x.data_ptr())
+        ctx.check(ctx.L.dsnerf_composite(ctx.h, p(traw), p(tz), p(td), R, Nn, p(rgb), p(dep), p(acc), p(dsp), p(w), None))
+        torch.cuda.synchronize()
+        assert np.abs(rgb.cpu().numpy() - ref["color"]).max() < 1e-5
+        assert np.abs(dep.cpu().numpy() - ref["depth_map"]).max() < 1e-5
+        assert np.abs(w.cpu().numpy() - ref["weights"]).max() < 1e-6
+        assert np.array_equal(np.isnan(dsp.cpu().numpy()), np.isnan(ref["disp_map"]))
+        ok = ~np.isnan(ref["disp_map"])
+        assert np.allclose(dsp.cpu().numpy()[ok], ref["disp_map"][ok], rtol=1e-5)
+        ctx.close()
+
+
+def test_edge_cases_and_errors(scene64):
+    from dual_space_nerf_b200 import lib
+
+    r = make_renderer(scene64, 32)
+    b = S.to_batch(scene64, torch, rays=np.arange(0))
+    out = r.render(b)["coarse"]  # empty ray batch
+    assert out["color"].shape == (0, 3)
+    b = S.to_batch(scene64, torch, rays=np.array([2080]))  # a single ray, ragged tile
+    out = r.render(b)["coarse"]
+    assert out["color"].shape == (1, 3) and torch.isfinite(out["color"]).all()
+    ctx = lib.Context(0)
+    with pytest.raises(lib.DsnerfError):  # call order is checked, errors are reported not aborted
+        ctx.check(ctx.L.dsnerf_render(ctx.h, None, None, None, None, 1, 8, 1, None, None, None, None, None, None, None))
+    r.train()
+    with pytest.raises(NotImplementedError):
+        r.render(S.to_batch(scene64, torch))

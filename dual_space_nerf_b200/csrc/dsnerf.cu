@@ -292,7 +292,7 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
                                                                     ctx->mlp_a.as<float4>(), ctx->mlp_g.as<float4>(), density_only);
     CKL("mlp_simt");
   } else {
-    if (int e = tc_launch(ctx->tw, ctx->bias0.as<float>(), ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
+    if (int e = tc_launch(ctx->tw, ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
                           ctx->mlp_g.as<float4>(), density_only, ctx->sm_count, st))
       return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc: ") + cudaGetErrorString((cudaError_t)e));
   }
@@ -566,6 +566,7 @@ int dsnerf_set_frame(dsnerf_ctx* ctx, const float* posed_verts, const float* pos
   }
   CK(cudaMemcpyAsync(ctx->posed.p, pv, vbytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->bias0.p, pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->tw.bias0_slot(), pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   int e = build_grid(ctx, ctx->g_posed, ctx->posed.as<float>(), pv, st);
   if (int e2 = pin_release(ctx, st)) return e2;
   if (e) return e;

@@ -40,8 +40,8 @@ struct DevBuf {
 struct MeshGrid {
   Grid g{};
   int ncell = 0;
-  DevBuf cent, counts, start, cursor, sorted, cdist;
-  void release() { cent.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); }
+  DevBuf cent, tri_n, counts, start, cursor, sorted, cdist, cidx;
+  void release() { cent.release(); tri_n.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); cidx.release(); }
 };
 
 // state_dict order
@@ -85,7 +85,7 @@ struct dsnerf_ctx {
   float rot[4] = {1, 0, 0, 1}, rot_center[2] = {0, 0};
   int has_rot = 0;
   // ---- workspace
-  DevBuf near2, far2, raw, active, mlp_a, mlp_g, tvals, counters, io;
+  DevBuf near2, far2, raw, active, active_tri, ray_mask, mlp_a, mlp_g, tvals, counters, io;
   int tvals_n = 0;
   void* pin = nullptr;
   size_t pin_cap = 0;
@@ -168,7 +168,7 @@ float transparency_radius(const float* verts, const int32_t* faces, int F) {
 
 // (Re)build the nearest-centroid grid of a mesh: centroids, counting sort by cell, cell-centre
 // distance table.  h_verts is the host copy (bbox and r_cap are computed on the host).
-int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float* h_verts, cudaStream_t st) {
+int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float* h_verts, int classify, cudaStream_t st) {
   const int F = ctx->F, V = ctx->V;
   float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
   for (int v = 0; v < V; ++v)
@@ -193,16 +193,20 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   g.r_cap = r_cap;
   mg.ncell = g.nx * g.ny * g.nz;
   CK(mg.cent.ensure(sizeof(float) * 3 * F));
+  CK(mg.tri_n.ensure(sizeof(float4) * F));
   CK(mg.counts.ensure(sizeof(int) * mg.ncell));
   CK(mg.start.ensure(sizeof(int) * (mg.ncell + 1)));
   CK(mg.cursor.ensure(sizeof(int) * mg.ncell));
   CK(mg.sorted.ensure(sizeof(float4) * F));
   CK(mg.cdist.ensure(sizeof(float) * mg.ncell));
+  CK(mg.cidx.ensure(sizeof(int) * mg.ncell));
   g.cell_start = mg.start.as<int>();
   g.sorted = mg.sorted.as<float4>();
   g.center_dist = mg.cdist.as<float>();
+  g.center_idx = mg.cidx.as<int>();
+  g.cent = mg.cent.as<float>();
   int fb = (F + 255) / 256;
-  centroid_kernel<<<fb, 256, 0, st>>>(d_verts, ctx->faces.as<int>(), F, mg.cent.as<float>());
+  centroid_kernel<<<fb, 256, 0, st>>>(d_verts, ctx->faces.as<int>(), F, mg.cent.as<float>(), mg.tri_n.as<float4>());
   CKL("centroid");
   CK(cudaMemsetAsync(mg.counts.p, 0, sizeof(int) * mg.ncell, st));
   grid_count_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.counts.as<int>());
@@ -211,7 +215,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CKL("grid_scan");
   grid_fill_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.cursor.as<int>(), mg.sorted.as<float4>());
   CKL("grid_fill");
-  grid_center_dist_kernel<<<(mg.ncell + 255) / 256, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.cdist.as<float>());
+  grid_center_dist_kernel<<<(mg.ncell + 255) / 256, 256, 0, st>>>(g, mg.cent.as<float>(), mg.tri_n.as<float4>(), F, classify, mg.cdist.as<float>(), mg.cidx.as<int>());
   CKL("grid_center_dist");
   return 0;
 }
@@ -252,6 +256,8 @@ int ensure_workspace(dsnerf_ctx* ctx, int64_t R, int N) {
   CK(ctx->far2.ensure(sizeof(float) * R));
   CK(ctx->raw.ensure(sizeof(float4) * P));
   CK(ctx->active.ensure(sizeof(float4) * (P + 128)));
+  CK(ctx->active_tri.ensure(sizeof(int) * (P + 128)));
+  CK(ctx->ray_mask.ensure(sizeof(unsigned) * (size_t)((P + 31) / 32 + 8)));
   CK(ctx->mlp_a.ensure(sizeof(float4) * (P + 128)));
   CK(ctx->mlp_g.ensure(sizeof(float4) * (P + 128)));
   CK(ctx->counters.ensure(sizeof(unsigned long long) * 4));
@@ -272,13 +278,13 @@ int ensure_tvals(dsnerf_ctx* ctx, int N, cudaStream_t st) {
 
 void profile_begin(dsnerf_ctx* ctx, cudaStream_t st, cudaEvent_t* a, cudaEvent_t* b) {
   *a = *b = nullptr;
-  if (!ctx->profile) return;
+  if (!(ctx->profile & 1)) return;
   cudaEventCreate(a);
   cudaEventCreate(b);
   cudaEventRecord(*a, st);
 }
 void profile_end(dsnerf_ctx* ctx, cudaStream_t st, cudaEvent_t a, cudaEvent_t b) {
-  if (!ctx->profile || !a) return;
+  if (!(ctx->profile & 1) || !a) return;
   cudaEventRecord(b, st);
   ctx->pending.emplace_back(a, b);
 }
@@ -362,21 +368,25 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   WarpArgs wa{};
   wa.ray_o = ray_o; wa.ray_d = ray_d; wa.near = near_use; wa.far = far_use; wa.z_in = z_in; wa.tvals = ctx->tvals.as<float>();
   wa.posed = ctx->posed.as<float>(); wa.canon = ctx->canon.as<float>(); wa.faces = ctx->faces.as<int>();
-  wa.R = R; wa.N = N; wa.raw = ctx->raw.as<float4>(); wa.active = ctx->active.as<float4>(); wa.counters = cnt;
-  wa.count_candidates = ctx->profile;
-  sample_warp_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(wa, ctx->g_posed.g);
+  wa.R = R; wa.N = N;
+  wa.active = ctx->active.as<float4>(); wa.active_tri = ctx->active_tri.as<int>(); wa.sample_mask = ctx->ray_mask.as<unsigned>();
+  wa.counters = cnt;
+  wa.count_candidates = (ctx->profile & 2) ? 1 : 0;
+  sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
   CKL("sample_warp");
   ++launches;
   if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
   ++launches;
   ShadeArgs sa = base_shade_args(ctx);
   sa.n_active = cnt;
+  sa.active_tri = ctx->active_tri.as<int>();
   sa.ray_o = ray_o; sa.ray_d = ray_d; sa.near = near_use; sa.far = far_use; sa.z_in = z_in; sa.tvals = ctx->tvals.as<float>();
   sa.N = N;
-  shade_kernel<<<ctx->sm_count, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
+  shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
   CKL("shade");
   ++launches;
   CompositeArgs ca{};
+  ca.sample_mask = ctx->ray_mask.as<unsigned>();
   ca.raw = ctx->raw.as<float4>(); ca.ray_d = ray_d; ca.near = near_use; ca.far = far_use; ca.tvals = ctx->tvals.as<float>(); ca.z_in = z_in;
   ca.R = R; ca.N = N; ca.rgb = rgb; ca.depth = depth; ca.acc = acc; ca.disp = disp; ca.weights = weights; ca.z_out = z_out;
   composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
@@ -427,7 +437,7 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->near2, &ctx->far2, &ctx->raw,
-                    &ctx->active, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io};
+                    &ctx->active, &ctx->active_tri, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io};
   for (DevBuf* b : bufs) b->release();
   ctx->g_canon.release();
   ctx->g_posed.release();
@@ -528,7 +538,7 @@ int dsnerf_set_mesh(dsnerf_ctx* ctx, const int32_t* faces, int n_faces, const fl
   CK(ctx->posed.ensure(sizeof(float) * 3 * n_verts));
   CK(cudaMemcpy(ctx->faces.p, faces, sizeof(int) * 3 * n_faces, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->canon.p, canonical_verts, sizeof(float) * 3 * n_verts, cudaMemcpyHostToDevice));
-  if (int e = build_grid(ctx, ctx->g_canon, ctx->canon.as<float>(), ctx->h_canon.data(), 0)) return e;
+  if (int e = build_grid(ctx, ctx->g_canon, ctx->canon.as<float>(), ctx->h_canon.data(), 0, 0)) return e;
   CK(cudaDeviceSynchronize());
   ctx->have_mesh = true;
   ctx->have_frame = false;
@@ -567,7 +577,7 @@ int dsnerf_set_frame(dsnerf_ctx* ctx, const float* posed_verts, const float* pos
   CK(cudaMemcpyAsync(ctx->posed.p, pv, vbytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->bias0.p, pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->tw.bias0_slot(), pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-  int e = build_grid(ctx, ctx->g_posed, ctx->posed.as<float>(), pv, st);
+  int e = build_grid(ctx, ctx->g_posed, ctx->posed.as<float>(), pv, 1, st);
   if (int e2 = pin_release(ctx, st)) return e2;
   if (e) return e;
   ctx->has_shift = light_shift != nullptr;
@@ -730,7 +740,7 @@ int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz
   sa.xyz_world = xyz_world;
   sa.view_dir = view_dir;
   sa.N = 1;
-  shade_kernel<<<ctx->sm_count, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
+  shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
   CKL("shade");
   scatter_points_kernel<<<blocks, 256, 0, st>>>(ctx->active.as<float4>(), ctx->raw.as<float4>(), cnt, color, density);
   CKL("scatter_points");
@@ -756,6 +766,7 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
     CK(cudaEventSynchronize(ctx->stats_ready));
     ctx->stats.evaluated_samples = (int64_t)ctx->h_counters[0];
     ctx->stats.nn_candidates = (int64_t)ctx->h_counters[1];
+    ctx->stats.reserved = (int32_t)std::min<unsigned long long>(ctx->h_counters[2], 0x7fffffffull);
     ctx->stats.algorithmic_flop = 1804544.0 * (double)ctx->stats.evaluated_samples;
   }
   *out = ctx->stats;
@@ -764,7 +775,7 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
 
 int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
   if (!ctx) return DSNERF_ERR_INVALID;
-  ctx->profile = enable ? 1 : 0;
+  ctx->profile = enable & 3;
   return 0;
 }
 

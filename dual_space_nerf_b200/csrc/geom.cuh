@@ -79,10 +79,13 @@ struct Grid {
   float r_cap;          // beyond this distance to the nearest centroid a point is provably transparent
   const int* __restrict__ cell_start;    // ncell+1
   const float4* __restrict__ sorted;     // (x,y,z,bits(idx)) sorted by cell
-  const float* __restrict__ center_dist; // per cell: distance from the cell centre to its nearest centroid
+  const float* __restrict__ cent;        // (F,3) centroids by index
+  const float* __restrict__ center_dist; // per cell: distance from the cell centre to its nearest centroid (huge = provably transparent)
+  const int* __restrict__ center_idx;    // per cell: index of that centroid (search seed)
 };
 
-__global__ void centroid_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int F, float* __restrict__ cent) {
+__global__ void centroid_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int F, float* __restrict__ cent,
+                                float4* __restrict__ tri_n) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   V3 a = ldv3(verts, faces[3 * f]), b = ldv3(verts, faces[3 * f + 1]), c = ldv3(verts, faces[3 * f + 2]);
@@ -90,6 +93,10 @@ __global__ void centroid_kernel(const float* __restrict__ verts, const int* __re
   cent[3 * f] = xdiv(xadd(xadd(a.x, b.x), c.x), 3.0f);
   cent[3 * f + 1] = xdiv(xadd(xadd(a.y, b.y), c.y), 3.0f);
   cent[3 * f + 2] = xdiv(xadd(xadd(a.z, b.z), c.z), 3.0f);
+  // unit normal, only used by the conservative cell classification below (NaN for degenerate triangles)
+  V3 n = xcross(xsub3(b, a), xsub3(c, a));
+  float nn = xnorm3(n);
+  tri_n[f] = make_float4(n.x / nn, n.y / nn, n.z / nn, 0.f);
 }
 
 __device__ __forceinline__ int grid_coord(float p, float o, float inv, int n) {
@@ -144,14 +151,21 @@ __global__ void grid_fill_kernel(Grid g, const float* __restrict__ cent, int F, 
   sorted[slot] = make_float4(x, y, z, __int_as_float(f));
 }
 
-// distance from every cell centre to its nearest centroid (brute force, tiled through smem)
-__global__ void grid_center_dist_kernel(Grid g, const float* __restrict__ cent, int F, float* __restrict__ out) {
-  __shared__ float sx[1024], sy[1024], sz[1024];
+// Per cell of the lookup table: distance dc from the cell centre to its nearest centroid, or
+// +huge when every point of the cell is PROVABLY transparent.  Proof: for p in the cell, its
+// nearest centroid c* satisfies |centre - c*| <= dc + 2*half_diag (candidate set), the signed
+// plane distance h* is 1-Lipschitz, so |h*(centre)| > 0.1 + half_diag for every candidate implies
+// |h*(p)| > 0.1 = max_dist of get_transparent_mask (utils/render_utils.py:103).  Brute force over
+// all centroids, tiled through shared memory: two sweeps (distance, then classification).
+__global__ void grid_center_dist_kernel(Grid g, const float* __restrict__ cent, const float4* __restrict__ tri_n, int F, int classify,
+                                        float* __restrict__ out, int* __restrict__ out_idx) {
+  __shared__ float sx[1024], sy[1024], sz[1024], snx[1024], sny[1024], snz[1024];
   int ncell = g.nx * g.ny * g.nz;
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
   float px = g.ox + (cx + 0.5f) * g.cell, py = g.oy + (cy + 0.5f) * g.cell, pz = g.oz + (cz + 0.5f) * g.cell;
   float best = 3.0e38f;
+  int besti = 0;
   for (int base = 0; base < F; base += 1024) {
     __syncthreads();
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
@@ -165,10 +179,42 @@ __global__ void grid_center_dist_kernel(Grid g, const float* __restrict__ cent, 
 #pragma unroll 8
     for (int i = 0; i < 1024; ++i) {
       float dx = px - sx[i], dy = py - sy[i], dz = pz - sz[i];
-      best = fminf(best, dx * dx + dy * dy + dz * dz);
+      float d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < best) { best = d2; besti = base + i; }
     }
   }
-  if (c < ncell) out[c] = sqrtf(best) * 1.00001f + 1e-7f;
+  float dc = sqrtf(best) * 1.00001f + 1e-7f;
+  const float h_thr = 0.1f + g.half_diag * 1.001f + 1e-4f;
+  // the centre's own nearest centroid is a candidate with |h| <= dc: only the band needs the second sweep
+  bool undecided = classify && (c < ncell) && (dc > h_thr) && (dc - g.half_diag <= g.r_cap);
+  bool search = (c < ncell) && (!classify || dc <= h_thr);
+  if (__syncthreads_or(undecided)) {
+    float thr = dc + 2.0f * g.half_diag * 1.001f + 1e-5f;
+    float thr2 = undecided ? thr * thr : -1.0f;
+    for (int base = 0; base < F; base += 1024) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        int f = base + i;
+        bool ok = f < F;
+        float4 n = ok ? tri_n[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        sx[i] = ok ? cent[3 * f] : 1.0e18f;
+        sy[i] = ok ? cent[3 * f + 1] : 1.0e18f;
+        sz[i] = ok ? cent[3 * f + 2] : 1.0e18f;
+        snx[i] = n.x; sny[i] = n.y; snz[i] = n.z;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int i = 0; i < 1024; ++i) {
+        float dx = px - sx[i], dy = py - sy[i], dz = pz - sz[i];
+        float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 <= thr2) {
+          float h = dx * snx[i] + dy * sny[i] + dz * snz[i];
+          if (!(fabsf(h) > h_thr)) search = true;  // NaN normal (degenerate triangle) keeps the cell searchable
+        }
+      }
+    }
+  }
+  if (c < ncell) { out[c] = search ? dc : 3.0e30f; out_idx[c] = besti; }
 }
 
 // Exact nearest centroid: squared L2 accumulated as d0*d0, fma(d1,d1,.), fma(d2,d2,.) and
@@ -177,18 +223,39 @@ __global__ void grid_center_dist_kernel(Grid g, const float* __restrict__ cent, 
 // g.r_cap from every centroid (then it is transparent whatever its nearest triangle is).
 // The search visits only grid rows that intersect the ball of the current best radius, which
 // starts from the cell-centre distance table, so it returns the same index as a full scan.
-__device__ __forceinline__ int nearest_centroid(const Grid& g, float px, float py, float pz, unsigned long long* cand_counter) {
+// `hint` (>= 0) is any centroid index expected to be close (the previous sample's answer along a
+// ray, or the posed-space triangle for the canonical search): its exact distance seeds the search
+// radius, which only prunes -- the result is still the exact argmin.
+__device__ __forceinline__ int nearest_centroid(const Grid& g, float px, float py, float pz, unsigned long long* cand_counter,
+                                                int hint = -1, const float* __restrict__ cent = nullptr) {
   float fx = (px - g.ox) * g.inv_cell, fy = (py - g.oy) * g.inv_cell, fz = (pz - g.oz) * g.inv_cell;
   // points outside the table region are farther than r_cap from the mesh by construction
   if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz)) return -1;
   int hx = (int)fx, hy = (int)fy, hz = (int)fz;
-  float dc = __ldg(g.center_dist + (hz * g.ny + hy) * g.nx + hx);
-  if (dc - g.half_diag > g.r_cap) return -1;
+  const int cell = (hz * g.ny + hy) * g.nx + hx;
+  float dc = __ldg(g.center_dist + cell);
+  if (hint < 0) {
+    if (dc - g.half_diag > g.r_cap) return -1;
+    // seed: the centroid nearest to the cell centre.  Its exact distance to p is at most dc + half_diag
+    // (the table bound) and usually much less, which shrinks the ball that has to be scanned.
+    hint = __ldg(g.center_idx + cell);
+    cent = g.cent;
+  } else if (dc > 1.0e29f) {
+    dc = g.r_cap;  // classified cell but the caller vouches for a nearby centroid: let the hint set the radius
+  }
   float rho = fminf(dc + g.half_diag, g.r_cap * 1.0001f + g.half_diag);
   float rho2 = rho * rho * 1.0001f;
   const float rho2_init = rho2;
   float best = 3.0e38f;
   int besti = -1;
+  if (hint >= 0) {
+    float dx = xsub(px, __ldg(cent + 3 * hint)), dy = xsub(py, __ldg(cent + 3 * hint + 1)), dz = xsub(pz, __ldg(cent + 3 * hint + 2));
+    float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+    best = d;
+    besti = hint;
+    rho2 = fminf(rho2, best * 1.0001f + 1e-12f);
+    rho = fminf(rho, sqrtf(rho2) * 1.0001f);
+  }
   unsigned long long ncand = 0;
   int z0 = max(0, (int)floorf((pz - rho - g.oz) * g.inv_cell)), z1 = min(g.nz - 1, (int)floorf((pz + rho - g.oz) * g.inv_cell));
   int y0 = max(0, (int)floorf((py - rho - g.oy) * g.inv_cell)), y1 = min(g.ny - 1, (int)floorf((py + rho - g.oy) * g.inv_cell));
@@ -297,55 +364,111 @@ __host__ __device__ inline float linspace01(int i, int n) {
 // utils/pts_utils.py:3-16 (eval): z = near*(1-t) + far*t
 __device__ __forceinline__ float sample_z(float near, float far, float t) { return xadd(xmul(near, xsub(1.0f, t)), xmul(far, t)); }
 
-// One thread per sample: place the sample, find its nearest posed triangle, project, mask,
-// re-emit on the canonical triangle (Renderer.w2l_without_lbs, can_render.py:333-379).
-// Non-transparent samples are appended to the active list; raw of the others is zeroed so that
-// the compositor gives them weight exactly 0 (can_render.py:118-120).
+// Renderer.w2l_without_lbs over all samples (can_render.py:333-379), one thread per sample.
+// Phase 1 places the sample and looks its cell up: ~80 % of the samples sit in cells that are far
+// from the mesh or provably transparent and stop there.  The rest are compacted into a per-block
+// queue so that phase 2 (exact nearest centroid -> project -> mask -> re-emit on the canonical
+// triangle) runs with full warps.  Non-transparent samples are appended to the active list; one
+// bit per sample tells the compositor which samples carry a raw value, so nothing is written for
+// transparent samples (their weight is exactly 0, can_render.py:118-120).
 struct WarpArgs {
   const float* ray_o; const float* ray_d; const float* near; const float* far;  // near/far after GG
-  const float* z_in;       // optional explicit z (R,N) (hierarchical second pass); NULL => linspace
-  const float* tvals;      // (N) linspace table
+  const float* z_in;       // optional explicit z (R,N); NULL => linspace
+  const float* tvals;      // (N)
   const float* posed; const float* canon; const int* faces;
   int64_t R; int N;
-  float4* raw;             // (R*N) rgb+sigma
   float4* active;          // (x_c, y_c, z_c, bits(sample id))
-  unsigned long long* counters;  // [0] = active count, [1] = candidate evaluations (optional)
+  int* active_tri;         // posed-space nearest triangle of each active sample
+  unsigned* sample_mask;   // ceil(R*N/32) words, bit s&31 of word s>>5
+  unsigned long long* counters;
   int count_candidates;
 };
 
-__global__ void __launch_bounds__(256) sample_warp_kernel(WarpArgs a, Grid g) {
-  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t P = a.R * a.N;
-  bool live = s < P;
-  bool act = false;
-  V3 xc = v3(0, 0, 0);
-  if (live) {
-    int64_t r = s / a.N;
-    int i = (int)(s - r * a.N);
-    float z = a.z_in ? a.z_in[s] : sample_z(a.near[r], a.far[r], a.tvals[i]);
-    float px = xadd(a.ray_o[3 * r], xmul(a.ray_d[3 * r], z));
-    float py = xadd(a.ray_o[3 * r + 1], xmul(a.ray_d[3 * r + 1], z));
-    float pz = xadd(a.ray_o[3 * r + 2], xmul(a.ray_d[3 * r + 2], z));
-    int idx = nearest_centroid(g, px, py, pz, a.count_candidates ? a.counters + 1 : nullptr);
-    if (idx >= 0) {
-      int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
-      float u, v, h;
-      project_point(v3(px, py, pz), ldv3(a.posed, i0), ldv3(a.posed, i1), ldv3(a.posed, i2), u, v, h);
-      if (!is_transparent(u, v, h)) {
-        xc = map_to_triangle(u, v, h, ldv3(a.canon, i0), ldv3(a.canon, i1), ldv3(a.canon, i2));
-        act = true;
+constexpr int WARP_THREADS = 256;
+
+__device__ __forceinline__ void sample_position(const WarpArgs& a, int64_t s, float& px, float& py, float& pz) {
+  int64_t r = s / a.N;
+  int i = (int)(s - r * a.N);
+  float z = a.z_in ? a.z_in[s] : sample_z(a.near[r], a.far[r], __ldg(a.tvals + i));
+  px = xadd(a.ray_o[3 * r], xmul(a.ray_d[3 * r], z));
+  py = xadd(a.ray_o[3 * r + 1], xmul(a.ray_d[3 * r + 1], z));
+  pz = xadd(a.ray_o[3 * r + 2], xmul(a.ray_d[3 * r + 2], z));
+}
+
+__global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, Grid g) {
+  __shared__ int queue[WARP_THREADS];
+  __shared__ int qn;
+  __shared__ unsigned char flag[WARP_THREADS];
+  const int64_t P = a.R * a.N;
+  const int64_t s0 = (int64_t)blockIdx.x * WARP_THREADS;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) qn = 0;
+  flag[threadIdx.x] = 0;
+  __syncthreads();
+  {
+    const int64_t s = s0 + threadIdx.x;
+    bool need = false;
+    if (s < P) {
+      float px, py, pz;
+      sample_position(a, s, px, py, pz);
+      float fx = (px - g.ox) * g.inv_cell, fy = (py - g.oy) * g.inv_cell, fz = (pz - g.oz) * g.inv_cell;
+      if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz) {
+        float dc = __ldg(g.center_dist + ((int)fz * g.ny + (int)fy) * g.nx + (int)fx);
+        need = !(dc - g.half_diag > g.r_cap);
       }
     }
-    if (!act) a.raw[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned m = __ballot_sync(0xffffffffu, need);
+    int base = 0;
+    if (m) {
+      int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(&qn, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) queue[base + __popc(m & ((1u << lane) - 1))] = threadIdx.x;
+    }
   }
-  // warp-aggregated append
-  unsigned m = __ballot_sync(0xffffffffu, act);
-  if (m) {
-    int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == (__ffs(m) - 1)) base = atomicAdd(a.counters, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (act) a.active[base + __popc(m & ((1u << lane) - 1))] = make_float4(xc.x, xc.y, xc.z, __int_as_float((int)s));
+  __syncthreads();
+  {
+    const int n = qn;
+    if (a.count_candidates && threadIdx.x == 0 && n) atomicAdd(a.counters + 2, (unsigned long long)n);
+    bool act = false;
+    V3 xc = v3(0, 0, 0);
+    int idx = -1, t = 0;
+    if (threadIdx.x < n) {
+      t = queue[threadIdx.x];
+      float px, py, pz;
+      sample_position(a, s0 + t, px, py, pz);
+      idx = nearest_centroid(g, px, py, pz, a.count_candidates ? a.counters + 1 : nullptr);
+      if (idx >= 0) {
+        int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
+        float u, v, h;
+        project_point(v3(px, py, pz), ldv3(a.posed, i0), ldv3(a.posed, i1), ldv3(a.posed, i2), u, v, h);
+        if (!is_transparent(u, v, h)) {
+          xc = map_to_triangle(u, v, h, ldv3(a.canon, i0), ldv3(a.canon, i1), ldv3(a.canon, i2));
+          act = true;
+        }
+      }
+    }
+    if ((threadIdx.x & ~31) < n) {  // warp-uniform: this warp holds queue entries
+      unsigned m = __ballot_sync(0xffffffffu, act);
+      if (m) {
+        int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(a.counters, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (act) {
+          unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+          a.active[slot] = make_float4(xc.x, xc.y, xc.z, __int_as_float((int)(s0 + t)));
+          a.active_tri[slot] = idx;
+          flag[t] = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    unsigned m = __ballot_sync(0xffffffffu, flag[threadIdx.x] != 0);
+    const int64_t s = s0 + threadIdx.x;
+    if (lane == 0 && s < P) a.sample_mask[s >> 5] = m;
   }
 }
 

@@ -128,6 +128,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// wait for outstanding tcgen05.ld; the registers are listed as in/out operands so that the
+// compiler cannot hoist a read of them above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -301,11 +321,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
           // ---------- forward layer: bias + ReLU, record mask bits, split to fp16 hi/lo -> next A operand
           const float* __restrict__ bias = P.bias + op * 256;
           uint32_t mbits[4];
+          uint32_t vbuf[2][32];
+          tmem_ld32_nowait(t_lane + TM_ACC + half * 128, vbuf[0]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int col0 = half * 128 + c * 32;
-            uint32_t v[32];
-            tmem_ld32(t_lane + TM_ACC + col0, v);
+            tmem_wait_ld(vbuf[c & 1]);
+            if (c + 1 < 4) tmem_ld32_nowait(t_lane + TM_ACC + col0 + 32, vbuf[(c + 1) & 1]);  // overlaps the math below
+            uint32_t (&v)[32] = vbuf[c & 1];
             uint32_t m = 0;
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -313,10 +336,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
               float h0 = fmaxf(__uint_as_float(v[i]) + b.x, 0.f), h1 = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
               float h2 = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), h3 = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
-              m |= (h0 > 0.f ? 1u : 0u) << i;
-              m |= (h1 > 0.f ? 1u : 0u) << (i + 1);
-              m |= (h2 > 0.f ? 1u : 0u) << (i + 2);
-              m |= (h3 > 0.f ? 1u : 0u) << (i + 3);
+              // ReLU bit = (h != 0): h >= +0, so bits(h) + 0x7fffffff carries into bit 31 iff h > 0; shifted in MSB-first
+              m = __funnelshift_l(__float_as_uint(h0) + 0x7fffffffu, m, 1);
+              m = __funnelshift_l(__float_as_uint(h1) + 0x7fffffffu, m, 1);
+              m = __funnelshift_l(__float_as_uint(h2) + 0x7fffffffu, m, 1);
+              m = __funnelshift_l(__float_as_uint(h3) + 0x7fffffffu, m, 1);
               if (op == 6) {
                 const float4 wd = __ldg(reinterpret_cast<const float4*>(P.w_dens + col0 + i));
                 sigma_part = fmaf(wd.x, h0, sigma_part); sigma_part = fmaf(wd.y, h1, sigma_part);
@@ -325,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
               split_h2(h0, h1, hi[i / 2], lo[i / 2]);
               split_h2(h2, h3, hi[i / 2 + 1], lo[i / 2 + 1]);
             }
-            mbits[c] = m;
+            mbits[c] = __brev(m);  // element i of the chunk -> bit i
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const uint32_t off = (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16;
@@ -344,11 +368,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
             uint32_t v[32];
             tmem_ld32(t_lane + TM_ACC + col0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float r = fmaxf(__uint_as_float(v[i]) + __ldg(P.b_rgb1 + col0 + i), 0.f);
-              e0 = fmaf(__ldg(P.w_rgb2 + col0 + i), r, e0);
-              e1 = fmaf(__ldg(P.w_rgb2 + 128 + col0 + i), r, e1);
-              e2 = fmaf(__ldg(P.w_rgb2 + 256 + col0 + i), r, e2);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(P.b_rgb1 + col0 + i));
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + col0 + i));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 128 + col0 + i));
+              const float4 w2 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 256 + col0 + i));
+              const float r0 = fmaxf(__uint_as_float(v[i]) + b.x, 0.f), r1 = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
+              const float r2 = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), r3 = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
+              e0 = fmaf(w0.x, r0, e0); e0 = fmaf(w0.y, r1, e0); e0 = fmaf(w0.z, r2, e0); e0 = fmaf(w0.w, r3, e0);
+              e1 = fmaf(w1.x, r0, e1); e1 = fmaf(w1.y, r1, e1); e1 = fmaf(w1.z, r2, e1); e1 = fmaf(w1.w, r3, e1);
+              e2 = fmaf(w2.x, r0, e2); e2 = fmaf(w2.y, r1, e2); e2 = fmaf(w2.z, r2, e2); e2 = fmaf(w2.w, r3, e2);
             }
           }
           float* x = xch + (row * 2 + half) * 8;
@@ -360,10 +389,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
             const int col0 = half * 128 + c * 32;
             uint32_t hi[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float g0 = ((mb[c] >> i) & 1u) ? __ldg(P.seed + col0 + i) : 0.f;
-              float g1 = ((mb[c] >> (i + 1)) & 1u) ? __ldg(P.seed + col0 + i + 1) : 0.f;
+            for (int i = 0; i < 32; i += 4) {
+              const float4 sd = __ldg(reinterpret_cast<const float4*>(P.seed + col0 + i));
+              float g0 = ((mb[c] >> i) & 1u) ? sd.x : 0.f, g1 = ((mb[c] >> (i + 1)) & 1u) ? sd.y : 0.f;
+              float g2 = ((mb[c] >> (i + 2)) & 1u) ? sd.z : 0.f, g3 = ((mb[c] >> (i + 3)) & 1u) ? sd.w : 0.f;
               hi[i / 2] = pack_h2(g0, g1);
+              hi[i / 2 + 1] = pack_h2(g2, g3);
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t)
@@ -375,11 +406,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
           const int mask_layer = 13 - op;  // op 8 -> layer 5 ... op 13 -> layer 0
           uint32_t mb[4];
           tmem_ld4(t_lane + TM_MASK + mask_layer * 8 + half * 4, mb);
+          uint32_t vbuf[2][32];
+          tmem_ld32_nowait(t_lane + TM_ACC + half * 128, vbuf[0]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int col0 = half * 128 + c * 32;
-            uint32_t v[32];
-            tmem_ld32(t_lane + TM_ACC + col0, v);
+            tmem_wait_ld(vbuf[c & 1]);
+            if (c + 1 < 4) tmem_ld32_nowait(t_lane + TM_ACC + col0 + 32, vbuf[(c + 1) & 1]);
+            uint32_t (&v)[32] = vbuf[c & 1];
             uint32_t hi[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {

@@ -15,6 +15,7 @@ struct LightWeights {
 
 struct ShadeArgs {
   const float4* active;   // (xyz_cano, bits(sample))
+  const int* active_tri;  // posed-space nearest triangle per active sample (search hint), may be NULL
   const float4* mlp_a;    // (sigma, essence)
   const float4* mlp_g;    // (d sigma / d xyz_cano, -)
   const unsigned long long* n_active;
@@ -29,8 +30,9 @@ struct ShadeArgs {
   float4* raw;            // (R*N) rgb + sigma, indexed by sample id
 };
 
-constexpr int SHADE_THREADS = 128;
-constexpr size_t SHADE_SMEM = (size_t)(9 * 128 + 128 + 128 * 128 + 128 + 128 + 128 * SHADE_THREADS) * sizeof(float);
+constexpr int SHADE_THREADS = 256;
+// shared memory: first layer as [128 units][12] (9 weights, bias, 2 pad), second layer transposed [128][128], b2, w3
+constexpr size_t SHADE_SMEM = (size_t)(128 * 12 + 128 * 128 + 128 + 128) * sizeof(float);
 
 // model/spacenet.py:278-298 normal_local2world.  The reference maps xyz_cano and xyz_cano+g onto
 // the posed triangle and normalises the difference; the map is affine in the point, so the
@@ -62,33 +64,32 @@ __device__ __forceinline__ V3 normal_to_world(V3 g, V3 c0, V3 c1, V3 c2, V3 m0, 
   return v3(r.x * in, r.y * in, r.z * in);
 }
 
-// One thread per active sample; the 128x128 lighting layer runs out of shared memory.
-__global__ void __launch_bounds__(SHADE_THREADS) shade_kernel(ShadeArgs a, LightWeights L, Grid gc) {
+// One thread per active sample.  The lighting layers run out of shared memory; the 128 hidden
+// units of the first layer are recomputed per 32-wide output chunk instead of being staged, which
+// keeps the block at ~71 KB of shared memory (3 blocks = 24 warps per SM).
+__global__ void __launch_bounds__(SHADE_THREADS, 3) shade_kernel(ShadeArgs a, LightWeights L, Grid gc) {
   extern __shared__ __align__(16) float sm[];
-  float* w1t = sm;                 // 9*128
-  float* b1 = w1t + 9 * 128;       // 128
-  float* w2t = b1 + 128;           // 128*128
+  float* w1p = sm;                 // [128][12]
+  float* w2t = w1p + 128 * 12;     // [128][128]
   float* b2 = w2t + 128 * 128;     // 128
   float* w3 = b2 + 128;            // 128
-  float* h1 = w3 + 128;            // [128 units][SHADE_THREADS samples]
-  for (int i = threadIdx.x; i < 9 * 128; i += SHADE_THREADS) w1t[i] = L.w1t[i];
+  for (int i = threadIdx.x; i < 128 * 12; i += SHADE_THREADS) {
+    int k = i / 12, j = i - k * 12;
+    w1p[i] = j < 9 ? L.w1t[j * 128 + k] : (j == 9 ? L.b1[k] : 0.f);
+  }
   for (int i = threadIdx.x; i < 128 * 128; i += SHADE_THREADS) w2t[i] = L.w2t[i];
-  for (int i = threadIdx.x; i < 128; i += SHADE_THREADS) { b1[i] = L.b1[i]; b2[i] = L.b2[i]; w3[i] = L.w3[i]; }
+  for (int i = threadIdx.x; i < 128; i += SHADE_THREADS) { b2[i] = L.b2[i]; w3[i] = L.w3[i]; }
   __syncthreads();
   int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
-  int64_t n_round = (n_active + SHADE_THREADS - 1) / SHADE_THREADS * SHADE_THREADS;
-  for (int64_t base = (int64_t)blockIdx.x * SHADE_THREADS; base < n_round; base += (int64_t)gridDim.x * SHADE_THREADS) {
-    int64_t t = base + threadIdx.x;
-    bool live = t < n_active;
-    float in[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float4 ma = make_float4(0, 0, 0, 0);
-    int sample = 0;
-    if (live) {
-      float4 ac = a.active[t];
-      ma = a.mlp_a[t];
-      float4 mg = a.mlp_g[t];
-      sample = __float_as_int(ac.w);
-      int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr);
+  for (int64_t t = (int64_t)blockIdx.x * SHADE_THREADS + threadIdx.x; t < n_active; t += (int64_t)gridDim.x * SHADE_THREADS) {
+    float in[9];
+    float4 ac = a.active[t];
+    float4 ma = a.mlp_a[t];
+    float4 mg = a.mlp_g[t];
+    int sample = __float_as_int(ac.w);
+    {
+      // the canonical point was emitted on canonical triangle active_tri[t]: its centroid is an excellent seed
+      int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr, a.active_tri ? a.active_tri[t] : -1, a.cent_canon);
       if (idx < 0) {  // cannot happen for warped points; keep the exact answer anyway
         float best = 3.0e38f;
         for (int f = 0; f < a.F; ++f) {
@@ -122,32 +123,34 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_kernel(ShadeArgs a, Light
       in[6] = xdiv(dx, dn); in[7] = xdiv(dy, dn); in[8] = xdiv(dz, dn);
     }
     // LightingMLP (model/spacenet.py:165-188): 9 -> 128 -> 128 -> 1, ReLU, ReLU, ELU; color = (out+1)*essence
-    __syncthreads();
-    for (int j = 0; j < 128; ++j) {
-      float acc = b1[j];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc = fmaf(in[k], w1t[k * 128 + j], acc);
-      h1[j * SHADE_THREADS + threadIdx.x] = fmaxf(acc, 0.f);
-    }
     float out = L.b3;
-    for (int jb = 0; jb < 128; jb += 16) {
-      float acc[16];
+#pragma unroll 1
+    for (int jb = 0; jb < 128; jb += 32) {
+      float acc[32];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = b2[jb + j];
+      for (int j = 0; j < 32; ++j) acc[j] = b2[jb + j];
+#pragma unroll 2
       for (int k = 0; k < 128; ++k) {
-        float x = h1[k * SHADE_THREADS + threadIdx.x];
+        const float4* w1 = reinterpret_cast<const float4*>(w1p + k * 12);
+        float4 wa = w1[0], wb = w1[1], wc = w1[2];
+        float h = wc.y;
+        h = fmaf(in[0], wa.x, h); h = fmaf(in[1], wa.y, h); h = fmaf(in[2], wa.z, h); h = fmaf(in[3], wa.w, h);
+        h = fmaf(in[4], wb.x, h); h = fmaf(in[5], wb.y, h); h = fmaf(in[6], wb.z, h); h = fmaf(in[7], wb.w, h);
+        h = fmaf(in[8], wc.x, h);
+        h = fmaxf(h, 0.f);
         const float4* wr = reinterpret_cast<const float4*>(w2t + k * 128 + jb);
-        float4 wa = wr[0], wb = wr[1], wc = wr[2], wd = wr[3];
-        acc[0] = fmaf(x, wa.x, acc[0]); acc[1] = fmaf(x, wa.y, acc[1]); acc[2] = fmaf(x, wa.z, acc[2]); acc[3] = fmaf(x, wa.w, acc[3]);
-        acc[4] = fmaf(x, wb.x, acc[4]); acc[5] = fmaf(x, wb.y, acc[5]); acc[6] = fmaf(x, wb.z, acc[6]); acc[7] = fmaf(x, wb.w, acc[7]);
-        acc[8] = fmaf(x, wc.x, acc[8]); acc[9] = fmaf(x, wc.y, acc[9]); acc[10] = fmaf(x, wc.z, acc[10]); acc[11] = fmaf(x, wc.w, acc[11]);
-        acc[12] = fmaf(x, wd.x, acc[12]); acc[13] = fmaf(x, wd.y, acc[13]); acc[14] = fmaf(x, wd.z, acc[14]); acc[15] = fmaf(x, wd.w, acc[15]);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 w = wr[j4];
+          acc[4 * j4] = fmaf(h, w.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(h, w.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(h, w.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(h, w.w, acc[4 * j4 + 3]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) out = fmaf(fmaxf(acc[j], 0.f), w3[jb + j], out);
+      for (int j = 0; j < 32; ++j) out = fmaf(fmaxf(acc[j], 0.f), w3[jb + j], out);
     }
     float light = (out > 0.f ? out : expm1f(out)) + 1.0f;
-    if (live) a.raw[sample] = make_float4(light * ma.y, light * ma.z, light * ma.w, ma.x);
+    a.raw[sample] = make_float4(light * ma.y, light * ma.z, light * ma.w, ma.x);
   }
 }
 
@@ -165,6 +168,7 @@ struct CompositeArgs {
   const float* ray_d;      // (R,3)
   const float* near; const float* far; const float* tvals;  // z = near(1-t)+far t   (z_in == NULL)
   const float* z_in;       // explicit (R,N) z
+  const unsigned* sample_mask; // bit (s & 31) of word s >> 5 set <=> raw[s] was written (s = r*N + i); NULL => all
   int64_t R; int N;
   float* rgb; float* depth; float* acc; float* disp; float* weights; float* z_out;
 };
@@ -185,7 +189,9 @@ __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
     if (live) {
       z = a.z_in ? a.z_in[r * a.N + i] : sample_z(near, far, a.tvals[i]);
       if (i + 1 < a.N) zn = a.z_in ? a.z_in[r * a.N + i + 1] : sample_z(near, far, a.tvals[i + 1]);
-      c = a.raw[r * a.N + i];
+      const int64_t sidx = r * a.N + i;
+      bool has = a.sample_mask ? ((a.sample_mask[sidx >> 5] >> (sidx & 31)) & 1u) : true;
+      if (has) c = a.raw[r * a.N + i];
     }
     float dist = (i + 1 < a.N) ? xsub(zn, z) : 1e10f;
     dist = xmul(dist, nd);

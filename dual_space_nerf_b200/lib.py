@@ -112,10 +112,12 @@ class Context:
     def stats(self):
         s = Stats()
         self.check(self.L.dsnerf_get_stats(self.h, ctypes.byref(s)))
-        return {k: getattr(s, k) for k, _ in Stats._fields_ if k != "reserved"}
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k != "reserved"}
+        d["searched_samples"] = s.reserved  # only counted with profile bit 2
+        return d
 
     def profile(self, enable):
-        self.check(self.L.dsnerf_profile(self.h, int(bool(enable))))
+        self.check(self.L.dsnerf_profile(self.h, int(enable)))
 
     def profile_read(self, reset=True):
         ms, n = ctypes.c_double(), ctypes.c_int64()

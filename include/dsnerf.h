@@ -58,7 +58,7 @@ typedef struct {
   int64_t nn_candidates;      /* centroid distance evaluations of the last render (0 unless profiling is on) */
   double algorithmic_flop;    /* evaluated_samples * 1 804 544 */
   int32_t kernel_launches;    /* kernels launched by the last render call */
-  int32_t reserved;
+  int32_t reserved;           /* with profile bit 2: samples that needed an exact nearest-centroid search */
 } dsnerf_stats_t;
 
 int dsnerf_abi_version(void);
@@ -144,8 +144,10 @@ int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz
 /* Counters of the last render on this context (synchronises the stream it ran on). */
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
 
-/* CUDA-event timing of the MLP kernel inside render calls: enable, render, read
- * back the accumulated milliseconds / launches since the last reset. */
+/* Profiling switches (bit mask): 1 = CUDA-event timing of the MLP kernel inside render calls
+ * (read back with dsnerf_profile_read: accumulated milliseconds / launches since the last
+ * reset); 2 = count nearest-centroid distance evaluations (dsnerf_stats_t.nn_candidates; slows
+ * the warp kernel, never enable it in a timed run). */
 int dsnerf_profile(dsnerf_ctx* ctx, int enable);
 int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int reset);
 

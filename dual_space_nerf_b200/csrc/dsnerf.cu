@@ -85,6 +85,7 @@ struct dsnerf_ctx {
   float rot[4] = {1, 0, 0, 1}, rot_center[2] = {0, 0};
   int has_rot = 0;
   // ---- workspace
+  DevBuf tc_timing;
   DevBuf near2, far2, raw, active, active_tri, ray_mask, mlp_a, mlp_g, tvals, counters, io;
   int tvals_n = 0;
   void* pin = nullptr;
@@ -298,7 +299,12 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
                                                                     ctx->mlp_a.as<float4>(), ctx->mlp_g.as<float4>(), density_only);
     CKL("mlp_simt");
   } else {
-    if (int e = tc_launch(ctx->tw, ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
+    long long* timing = nullptr;
+    if (ctx->profile & 4) {
+      if (ctx->tc_timing.ensure(sizeof(long long) * 64) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "timing buffer");
+      timing = ctx->tc_timing.as<long long>();
+    }
+    if (int e = tc_launch(ctx->tw, timing, ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
                           ctx->mlp_g.as<float4>(), density_only, ctx->sm_count, st))
       return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc: ") + cudaGetErrorString((cudaError_t)e));
   }
@@ -775,7 +781,14 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
 
 int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
   if (!ctx) return DSNERF_ERR_INVALID;
-  ctx->profile = enable & 3;
+  ctx->profile = enable & 7;
+  return 0;
+}
+
+int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out64) {
+  if (!ctx || !out64 || !ctx->tc_timing.p) return DSNERF_ERR_INVALID;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out64, ctx->tc_timing.p, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
   return 0;
 }
 

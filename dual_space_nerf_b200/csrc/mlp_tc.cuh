@@ -29,6 +29,7 @@ constexpr int TC_TILE = 128;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_STAGES = 4;
+constexpr int TC_CLUSTER = 2;
 constexpr uint32_t TC_STAGE_BYTES = 16384;
 // shared memory map (bytes)
 constexpr uint32_t SM_ACT_HI = 0;
@@ -79,6 +80,7 @@ struct TcParams {
   float4* out_a;
   float4* out_g;
   int density_only;
+  long long* timing;       // debug: clock64 stamps of CTA 0 / tile 0 (2 per op + 2), NULL in production
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -98,6 +100,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t mbar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(mbar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -171,7 +186,10 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
+// Launched as clusters of TC_CLUSTER CTAs: every weight slab is fetched from L2 once per cluster (each CTA
+// loads 1/TC_CLUSTER of it and multicasts it into all CTAs' rings).  Measured: without multicast the kernel is
+// bound by L2->SM weight streaming (~30 B/cycle/SM), see profiles/.
+__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + SM_BAR;             // [TC_STAGES]
@@ -182,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_CLUSTER); }
     mbar_init(bar_acc, 1);
     mbar_init(bar_a, TC_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -193,25 +211,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into / arrives on them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t cta_rank = cluster_ctarank();
+  const uint16_t mc_mask = (uint16_t)((1u << TC_CLUSTER) - 1);
 
   const int64_t n_active = P.n_active_ptr ? (int64_t)*P.n_active_ptr : P.n_active_host;
   const int64_t n_tiles = (n_active + TC_TILE - 1) / TC_TILE;
+  // every CTA runs the same number of iterations (the ring of a cluster advances in lockstep); tiles past the
+  // end are dummies (no live rows)
+  const int64_t n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int n_ops = P.density_only ? 7 : TC_NUM_OPS;
 
   if (warp == TC_EPI_WARPS + 1) {
     // =============================== weight loader (one thread) ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t it = 0; it < n_iter; ++it) {
         for (int op = 0; op < n_ops; ++op) {
           const TcOp o = c_tc_ops[op];
-          const uint8_t* src = P.wpack + o.src_off;
+          const uint32_t part = o.slab_bytes / TC_CLUSTER;
+          const uint8_t* src = P.wpack + o.src_off + cta_rank * part;
           for (int s = 0; s < o.n_slabs; ++s) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);  // every CTA of the cluster has consumed this slot
             mbar_expect_tx(bar_full + 8 * stage, o.slab_bytes);
-            bulk_g2s(sbase + SM_RING + stage * TC_STAGE_BYTES, src + (size_t)s * o.slab_bytes, o.slab_bytes, bar_full + 8 * stage);
+            bulk_g2s_mc(sbase + SM_RING + stage * TC_STAGE_BYTES + cta_rank * part, src + (size_t)s * o.slab_bytes, part,
+                        bar_full + 8 * stage, mc_mask);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -221,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
     // =============================== MMA issuer (one thread) ==================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t it = 0; it < n_iter; ++it) {
         for (int op = 0; op < n_ops; ++op) {
           const TcOp o = c_tc_ops[op];
           const uint32_t rows = o.n_main + o.n_extra;
@@ -263,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
                 tc_mma(tmem + TM_GPE, da_hi, db_x, idesc_extra, (uint32_t)(o.gpe_accum | (kk > 0)));
               }
             }
-            tc_commit(bar_empty + 8 * stage);  // frees the ring slot once these MMAs have read it
+            tc_commit_mc(bar_empty + 8 * stage, mc_mask);  // frees the slot in every CTA of the cluster once these MMAs have read it
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
           tc_commit(bar_acc);  // accumulator complete
@@ -276,11 +302,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t acc_phase = 0;
-    float* xch = reinterpret_cast<float*>(smem + SM_PE_HI);  // [128][2][8] floats, aliases the PE region (free after op 4)
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // [128][2][8] floats of cross-half partial sums.  Lives in the A-lo region, which is idle once the last
+    // 3-pass op (rgb head) has run; the density-only path ends earlier and uses the PE region (idle after op 4).
+    float* xch = reinterpret_cast<float*>(smem + (P.density_only ? SM_PE_HI : SM_ACT_LO));
+    float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((int64_t)blockIdx.x * TC_TILE + row < n_active) pt_next = P.active[(int64_t)blockIdx.x * TC_TILE + row];
+    for (int64_t it = 0; it < n_iter; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t base = tile * TC_TILE;
       const bool live = base + row < n_active;
-      float4 pt = live ? P.active[base + row] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 pt = pt_next;
+      {  // fetch the next tile's point now: its DRAM latency hides behind this tile
+        const int64_t nb = (tile + gridDim.x) * TC_TILE + row;
+        pt_next = nb < n_active ? P.active[nb] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       const float xs[3] = {pt.x, pt.y, pt.z};
       // ---- positional encoding (model/dimension_kernel.py:5-35) as the A operand of op 0 / tail of op 4
       {
@@ -308,6 +343,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
           }
         }
       }
+      const bool stamp = P.timing && blockIdx.x == 0 && it == 0 && threadIdx.x == 0;
+      if (stamp) P.timing[0] = clock64();
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_a);
@@ -317,6 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        if (stamp) P.timing[1 + 2 * op] = clock64();
         if (op <= 6) {
           // ---------- forward layer: bias + ReLU, record mask bits, split to fp16 hi/lo -> next A operand
           const float* __restrict__ bias = P.bias + op * 256;
@@ -434,23 +472,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
           auto gpe = [&](int c) -> float { return __uint_as_float(c < 32 ? g0[c] : g1[c - 32]); };
           float gx[3] = {0.f, 0.f, 0.f};
           if (half == 0) { gx[0] = gpe(0); gx[1] = gpe(1); gx[2] = gpe(2); }
+          // sin/cos of this thread's five octaves are still in the PE region (written by this very thread)
+          auto pe_val = [&](int col) -> float {
+            const uint32_t off = (uint32_t)(col >> 3) * A_CHUNK + row * 16 + (col & 7) * 2;
+            return __half2float(*reinterpret_cast<const __half*>(smem + SM_PE_HI + off)) +
+                   __half2float(*reinterpret_cast<const __half*>(smem + SM_PE_LO + off));
+          };
 #pragma unroll
           for (int kk = 0; kk < 5; ++kk) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              // columns are compile-time for each half: select after computing both candidates
               const int k0 = kk, k1 = kk + 5;
               const float gs = half ? gpe(3 + 6 * k1 + c) : gpe(3 + 6 * k0 + c);
               const float gc = half ? gpe(6 + 6 * k1 + c) : gpe(6 + 6 * k0 + c);
               const float f = half ? (float)(1 << k1) : (float)(1 << k0);
-              float sn, cs;
-              sincosf(xs[c] * f, &sn, &cs);
+              const int ks = half ? k1 : k0;
+              const float sn = pe_val(3 + 6 * ks + c), cs = pe_val(6 + 6 * ks + c);
               gx[c] = fmaf((gs * cs - gc * sn), f, gx[c]);
             }
           }
           float* x = xch + (row * 2 + half) * 8;
           x[4] = gx[0]; x[5] = gx[1]; x[6] = gx[2];
         }
+        if (stamp) P.timing[2 + 2 * op] = clock64();
         if (op == n_ops - 1) {
           // ---------- tile outputs
           if (P.density_only) {
@@ -480,6 +524,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still multicast into its ring or arrive on its barriers
   if (warp == TC_EPI_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
@@ -612,7 +657,7 @@ struct TcWeights {
 
 inline void tc_configure() { cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM); }
 
-inline int tc_launch(TcWeights& w, const float4* active, const unsigned long long* n_active_ptr, int64_t n_active_host,
+inline int tc_launch(TcWeights& w, long long* timing, const float4* active, const unsigned long long* n_active_ptr, int64_t n_active_host,
                      float4* out_a, float4* out_g, int density_only, int sm_count, cudaStream_t st) {
   TcParams p{};
   p.wpack = reinterpret_cast<const uint8_t*>(w.d_pack);
@@ -630,7 +675,8 @@ inline int tc_launch(TcWeights& w, const float4* active, const unsigned long lon
   p.out_a = out_a;
   p.out_g = out_g;
   p.density_only = density_only;
-  mlp_tc_kernel<<<sm_count, TC_THREADS, TC_SMEM, st>>>(p);
+  p.timing = timing;
+  mlp_tc_kernel<<<sm_count / TC_CLUSTER * TC_CLUSTER, TC_THREADS, TC_SMEM, st>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -149,6 +149,8 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
  * reset); 2 = count nearest-centroid distance evaluations (dsnerf_stats_t.nn_candidates; slows
  * the warp kernel, never enable it in a timed run). */
 int dsnerf_profile(dsnerf_ctx* ctx, int enable);
+/* debug (profile bit 4): clock64 stamps of the tensor-core kernel's first tile, 64 values */
+int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out64);
 int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int reset);
 
 #ifdef __cplusplus

@@ -1,0 +1,26 @@
+"""Manual GPU probe: per-op clock64 stamps of the tcgen05 kernel's first tile (not a pytest file)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from types import SimpleNamespace
+from dual_space_nerf_b200 import net as N, scene as S
+from dual_space_nerf_b200.renderer import Renderer
+sc = S.make_scene(256, 256)
+cfg = SimpleNamespace(MODEL=SimpleNamespace(TYPE="nerf", COARSE_RAY_SAMPLING=64, FINE_RAY_SAMPLING=-1, sample_points_mode="GG", perturb=1.0, raw_noise_std=1.0), DATASETS=SimpleNamespace(SMPL_PATH=None))
+r = Renderer(N.synthetic_net(0), None, cfg, torch.from_numpy(sc["canonical"]), device=0, faces=sc["faces"])
+r.eval()
+for _ in range(3): r.render(S.to_batch(sc, torch))
+r.ctx.profile(4)
+r.render(S.to_batch(sc, torch)); torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 64)()
+r.ctx.check(r.ctx.L.dsnerf_debug_tc_timing(r.ctx.h, buf))
+t = np.array(buf[:32], dtype=np.int64)
+names = ["L0","L1","L2","L3","L4","L5","L6","rgb1","bW6","bW5","bW4","bW3","bW2","bW1","bW0"]
+print("op      mma+sync  epilogue (cycles)")
+tot_m = tot_e = 0
+for op in range(15):
+    prev = t[0] if op == 0 else t[2 * op]
+    m = t[1 + 2 * op] - prev; e = t[2 + 2 * op] - t[1 + 2 * op]
+    tot_m += m; tot_e += e
+    print(f"{names[op]:6s} {m:9d} {e:9d}")
+print("total", tot_m, tot_e, "tile", t[30] - t[0])

@@ -301,7 +301,7 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
   } else {
     long long* timing = nullptr;
     if (ctx->profile & 4) {
-      if (ctx->tc_timing.ensure(sizeof(long long) * 64) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "timing buffer");
+      if (ctx->tc_timing.ensure(sizeof(long long) * 128) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "timing buffer");
       timing = ctx->tc_timing.as<long long>();
     }
     if (int e = tc_launch(ctx->tw, timing, ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
@@ -788,7 +788,7 @@ int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
 int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out64) {
   if (!ctx || !out64 || !ctx->tc_timing.p) return DSNERF_ERR_INVALID;
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out64, ctx->tc_timing.p, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out64, ctx->tc_timing.p, sizeof(long long) * 128, cudaMemcpyDeviceToHost));
   return 0;
 }
 

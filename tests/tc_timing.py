@@ -12,15 +12,17 @@ r.eval()
 for _ in range(3): r.render(S.to_batch(sc, torch))
 r.ctx.profile(4)
 r.render(S.to_batch(sc, torch)); torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 64)()
+buf = (ctypes.c_longlong * 128)()
 r.ctx.check(r.ctx.L.dsnerf_debug_tc_timing(r.ctx.h, buf))
-t = np.array(buf[:32], dtype=np.int64)
+t = np.array(buf[:128], dtype=np.int64)
 names = ["L0","L1","L2","L3","L4","L5","L6","rgb1","bW6","bW5","bW4","bW3","bW2","bW1","bW0"]
-print("op      mma+sync  epilogue (cycles)")
-tot_m = tot_e = 0
+print("op      wait0->start0  epi0   gap  epi1   (cycles; start = accumulator half ready)")
+prev = t[0]
 for op in range(15):
-    prev = t[0] if op == 0 else t[2 * op]
-    m = t[1 + 2 * op] - prev; e = t[2 + 2 * op] - t[1 + 2 * op]
-    tot_m += m; tot_e += e
-    print(f"{names[op]:6s} {m:9d} {e:9d}")
-print("total", tot_m, tot_e, "tile", t[30] - t[0])
+    s0, e0, s1, e1 = t[1 + 4 * op], t[2 + 4 * op], t[3 + 4 * op], t[4 + 4 * op]
+    print(f"{names[op]:6s} {s0 - prev:8d} {e0 - s0:8d} {s1 - e0:8d} {e1 - s1:8d}")
+    prev = e1
+print("tile total", t[62] - t[0])
+print("MMA thread per op: wait_full  wait_a  total_issue_loop")
+for op in range(15):
+    print(f"{names[op]:6s} {t[64+3*op]:9d} {t[65+3*op]:9d} {t[66+3*op]:9d}")

@@ -40,8 +40,8 @@ struct DevBuf {
 struct MeshGrid {
   Grid g{};
   int ncell = 0;
-  DevBuf cent, tri_n, counts, start, cursor, sorted, cdist, cidx;
-  void release() { cent.release(); tri_n.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); cidx.release(); }
+  DevBuf cent, tri_n, counts, start, cursor, sorted, cdist, cidx, rowmask, dc0, idx0;
+  void release() { cent.release(); tri_n.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); cidx.release(); rowmask.release(); dc0.release(); idx0.release(); }
 };
 
 // state_dict order
@@ -177,12 +177,13 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   for (int k = 0; k < 3; ++k)
     if (!(lo[k] <= hi[k]) || !std::isfinite(lo[k]) || !std::isfinite(hi[k])) return fail(ctx, DSNERF_ERR_INVALID, "mesh vertices are not finite");
   float r_cap = transparency_radius(h_verts, ctx->h_faces.data(), F);
+  // enumeration cell: 4 cm, grown until the lattice has at most 64 cells along x (row occupancy words) and ~3M cells
   float cell = 0.04f;
   double ext[3];
   for (;;) {
     double n = 1;
     for (int k = 0; k < 3; ++k) { ext[k] = (double)hi[k] - lo[k] + 2.0 * (r_cap + 2.0 * cell); n *= ceil(ext[k] / cell); }
-    if (n <= 3.0e6) break;
+    if (n <= 3.0e6 && ceil(ext[0] / cell) <= 64) break;
     cell *= 1.26f;
   }
   Grid& g = mg.g;
@@ -190,19 +191,28 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   g.inv_cell = 1.0f / cell;
   g.ox = lo[0] - (r_cap + 2 * cell); g.oy = lo[1] - (r_cap + 2 * cell); g.oz = lo[2] - (r_cap + 2 * cell);
   g.nx = (int)ceil(ext[0] / cell); g.ny = (int)ceil(ext[1] / cell); g.nz = (int)ceil(ext[2] / cell);
-  g.half_diag = cell * 0.8660254f * 1.0001f;
+  g.tinv = 2.0f / cell;
+  g.tnx = 2 * g.nx; g.tny = 2 * g.ny; g.tnz = 2 * g.nz;
+  g.thalf_diag = 0.5f * cell * 0.8660254f * 1.0001f;
   g.r_cap = r_cap;
   mg.ncell = g.nx * g.ny * g.nz;
+  const int nrow = g.ny * g.nz, ntab = 8 * mg.ncell;
+  const float cell0 = 2.0f * cell;  // level-0 lattice: 4 table cells per edge
+  const int n0x = (g.nx + 1) / 2, n0y = (g.ny + 1) / 2, n0z = (g.nz + 1) / 2, n0 = n0x * n0y * n0z;
   CK(mg.cent.ensure(sizeof(float) * 3 * F));
   CK(mg.tri_n.ensure(sizeof(float4) * F));
   CK(mg.counts.ensure(sizeof(int) * mg.ncell));
   CK(mg.start.ensure(sizeof(int) * (mg.ncell + 1)));
   CK(mg.cursor.ensure(sizeof(int) * mg.ncell));
   CK(mg.sorted.ensure(sizeof(float4) * F));
-  CK(mg.cdist.ensure(sizeof(float) * mg.ncell));
-  CK(mg.cidx.ensure(sizeof(int) * mg.ncell));
+  CK(mg.rowmask.ensure(sizeof(unsigned long long) * nrow));
+  CK(mg.cdist.ensure(sizeof(float) * ntab));
+  CK(mg.cidx.ensure(sizeof(int) * ntab));
+  CK(mg.dc0.ensure(sizeof(float) * n0));
+  CK(mg.idx0.ensure(sizeof(int) * n0));
   g.cell_start = mg.start.as<int>();
   g.sorted = mg.sorted.as<float4>();
+  g.row_mask = mg.rowmask.as<unsigned long long>();
   g.center_dist = mg.cdist.as<float>();
   g.center_idx = mg.cidx.as<int>();
   g.cent = mg.cent.as<float>();
@@ -210,14 +220,19 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   centroid_kernel<<<fb, 256, 0, st>>>(d_verts, ctx->faces.as<int>(), F, mg.cent.as<float>(), mg.tri_n.as<float4>());
   CKL("centroid");
   CK(cudaMemsetAsync(mg.counts.p, 0, sizeof(int) * mg.ncell, st));
-  grid_count_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.counts.as<int>());
+  CK(cudaMemsetAsync(mg.rowmask.p, 0, sizeof(unsigned long long) * nrow, st));
+  grid_count_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.counts.as<int>(), mg.rowmask.as<unsigned long long>());
   CKL("grid_count");
   grid_scan_kernel<<<1, 1024, 0, st>>>(mg.counts.as<int>(), mg.ncell, mg.start.as<int>(), mg.cursor.as<int>());
   CKL("grid_scan");
   grid_fill_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.cursor.as<int>(), mg.sorted.as<float4>());
   CKL("grid_fill");
-  grid_center_dist_kernel<<<(mg.ncell + 255) / 256, 256, 0, st>>>(g, mg.cent.as<float>(), mg.tri_n.as<float4>(), F, classify, mg.cdist.as<float>(), mg.cidx.as<int>());
-  CKL("grid_center_dist");
+  table_coarse_kernel<<<(n0 + 255) / 256, 256, 0, st>>>(g.ox, g.oy, g.oz, cell0, n0x, n0y, n0z, mg.cent.as<float>(), F, mg.dc0.as<float>(),
+                                                        mg.idx0.as<int>());
+  CKL("table_coarse");
+  table_fine_kernel<<<(ntab + 127) / 128, 128, 0, st>>>(g, mg.tri_n.as<float4>(), cell0, n0x, n0y, n0z, mg.dc0.as<float>(), mg.idx0.as<int>(),
+                                                        classify, mg.cdist.as<float>(), mg.cidx.as<int>());
+  CKL("table_fine");
   return 0;
 }
 
@@ -360,12 +375,15 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   const float* near_use = near;
   const float* far_use = far;
   if (!z_in && (flags & DSNERF_SAMPLE_GG)) {
-    CK(ctx->vq.ensure(sizeof(float4) * ctx->V));
-    gg_prep_kernel<<<(ctx->V + 255) / 256, 256, 0, st>>>(ctx->posed.as<float>(), ctx->V, ray_o, ctx->vq.as<float4>());
+    CK(ctx->vq.ensure(sizeof(float4) * ctx->V + 32));
+    unsigned* qbox = reinterpret_cast<unsigned*>(ctx->vq.as<float4>() + ctx->V);
+    CK(cudaMemsetAsync(qbox, 0xff, 12, st));
+    CK(cudaMemsetAsync(qbox + 3, 0, 12, st));
+    gg_prep_kernel<<<(ctx->V + 255) / 256, 256, 0, st>>>(ctx->posed.as<float>(), ctx->V, ray_o, ctx->vq.as<float4>(), qbox);
     CKL("gg_prep");
     float gamma2 = (float)(0.05 * 0.05);  // python double 0.05**2 rounded to fp32 (pts_utils.py:36)
     gg_bounds_kernel<<<(unsigned)((R + GG_THREADS - 1) / GG_THREADS), GG_THREADS, 0, st>>>(
-        ctx->vq.as<float4>(), ctx->V, ray_d, near, far, R, gamma2, ctx->near2.as<float>(), ctx->far2.as<float>());
+        ctx->vq.as<float4>(), ctx->V, qbox, ray_d, near, far, R, gamma2, 0.05f, ctx->near2.as<float>(), ctx->far2.as<float>());
     CKL("gg_bounds");
     launches += 2;
     near_use = ctx->near2.as<float>();

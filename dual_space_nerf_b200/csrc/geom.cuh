@@ -70,18 +70,24 @@ __device__ __forceinline__ V3 map_to_triangle(float u, float v, float h, V3 c0, 
 
 // ---------------------------------------------------------------------------------------------
 // Uniform grid over triangle centroids (one per mesh: posed = per frame, canonical = static).
-// Cells are x-fastest, so a run of cells along x is one contiguous run of sorted centroids.
+// Enumeration grid: cells are x-fastest, so a run of cells along x is one contiguous run of sorted
+// centroids; one 64-bit occupancy word per (z,y) row lets the scan skip empty rows and trim ranges.
+// Lookup table: twice as fine as the enumeration grid; per cell the distance from the cell centre
+// to its nearest centroid (or "provably transparent") and that centroid's index (search seed).
 struct Grid {
-  float ox, oy, oz;     // origin of cell (0,0,0)
-  float cell, inv_cell; // edge length
-  int nx, ny, nz;
-  float half_diag;      // cell * sqrt(3)/2 (rounded up)
+  float ox, oy, oz;     // origin of cell (0,0,0) of both lattices
+  float cell, inv_cell; // enumeration cell edge
+  int nx, ny, nz;       // enumeration cells (nx <= 64)
+  float tinv;           // 1 / table cell edge (= 2 / cell)
+  int tnx, tny, tnz;    // table cells (2nx, 2ny, 2nz)
+  float thalf_diag;     // table cell half diagonal (rounded up)
   float r_cap;          // beyond this distance to the nearest centroid a point is provably transparent
-  const int* __restrict__ cell_start;    // ncell+1
-  const float4* __restrict__ sorted;     // (x,y,z,bits(idx)) sorted by cell
-  const float* __restrict__ cent;        // (F,3) centroids by index
-  const float* __restrict__ center_dist; // per cell: distance from the cell centre to its nearest centroid (huge = provably transparent)
-  const int* __restrict__ center_idx;    // per cell: index of that centroid (search seed)
+  const int* __restrict__ cell_start;              // ncell+1
+  const float4* __restrict__ sorted;               // (x,y,z,bits(idx)) sorted by cell
+  const unsigned long long* __restrict__ row_mask; // (nz*ny) occupancy bits along x
+  const float* __restrict__ cent;                  // (F,3) centroids by index
+  const float* __restrict__ center_dist;           // table: distance centre -> nearest centroid (huge = provably transparent)
+  const int* __restrict__ center_idx;              // table: index of that centroid
 };
 
 __global__ void centroid_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int F, float* __restrict__ cent,
@@ -104,13 +110,14 @@ __device__ __forceinline__ int grid_coord(float p, float o, float inv, int n) {
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
-__global__ void grid_count_kernel(Grid g, const float* __restrict__ cent, int F, int* __restrict__ counts) {
+__global__ void grid_count_kernel(Grid g, const float* __restrict__ cent, int F, int* __restrict__ counts, unsigned long long* __restrict__ row_mask) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   int cx = grid_coord(cent[3 * f], g.ox, g.inv_cell, g.nx);
   int cy = grid_coord(cent[3 * f + 1], g.oy, g.inv_cell, g.ny);
   int cz = grid_coord(cent[3 * f + 2], g.oz, g.inv_cell, g.nz);
   atomicAdd(&counts[(cz * g.ny + cy) * g.nx + cx], 1);
+  atomicOr(&row_mask[cz * g.ny + cy], 1ull << cx);
 }
 
 // single-block exclusive scan: counts[ncell] -> start[ncell+1]; also copies start into cursor
@@ -151,19 +158,49 @@ __global__ void grid_fill_kernel(Grid g, const float* __restrict__ cent, int F, 
   sorted[slot] = make_float4(x, y, z, __int_as_float(f));
 }
 
-// Per cell of the lookup table: distance dc from the cell centre to its nearest centroid, or
-// +huge when every point of the cell is PROVABLY transparent.  Proof: for p in the cell, its
-// nearest centroid c* satisfies |centre - c*| <= dc + 2*half_diag (candidate set), the signed
-// plane distance h* is 1-Lipschitz, so |h*(centre)| > 0.1 + half_diag for every candidate implies
-// |h*(p)| > 0.1 = max_dist of get_transparent_mask (utils/render_utils.py:103).  Brute force over
-// all centroids, tiled through shared memory: two sweeps (distance, then classification).
-__global__ void grid_center_dist_kernel(Grid g, const float* __restrict__ cent, const float4* __restrict__ tri_n, int F, int classify,
-                                        float* __restrict__ out, int* __restrict__ out_idx) {
-  __shared__ float sx[1024], sy[1024], sz[1024], snx[1024], sny[1024], snz[1024];
-  int ncell = g.nx * g.ny * g.nz;
+// Visit every centroid stored in a grid cell that intersects the ball (p, sqrt(rho2)).  rho2 may shrink while
+// the scan runs (the visitor holds a reference); the initial extent comes from rho.  All bounds are rounded
+// outwards, so no cell touching the ball is skipped.
+template <class Visit>
+__device__ __forceinline__ void scan_ball(const Grid& g, float px, float py, float pz, float rho, const float& rho2, Visit&& visit) {
+  int z0 = max(0, (int)floorf((pz - rho - g.oz) * g.inv_cell)), z1 = min(g.nz - 1, (int)floorf((pz + rho - g.oz) * g.inv_cell));
+  int y0 = max(0, (int)floorf((py - rho - g.oy) * g.inv_cell)), y1 = min(g.ny - 1, (int)floorf((py + rho - g.oy) * g.inv_cell));
+  for (int cz = z0; cz <= z1; ++cz) {
+    float zl = g.oz + cz * g.cell;
+    float dz = fmaxf(0.f, fmaxf(zl - pz, pz - (zl + g.cell)));
+    float dz2 = dz * dz * 0.9999f;
+    if (dz2 > rho2) continue;
+    for (int cy = y0; cy <= y1; ++cy) {
+      unsigned long long m = __ldg(g.row_mask + cz * g.ny + cy);
+      if (!m) continue;
+      float yl = g.oy + cy * g.cell;
+      float dy = fmaxf(0.f, fmaxf(yl - py, py - (yl + g.cell)));
+      float rem = rho2 - dz2 - dy * dy * 0.9999f;
+      if (rem < 0.f) continue;
+      float rx = sqrtf(rem) * 1.0001f + 1e-6f;
+      int x0 = max(0, (int)floorf((px - rx - g.ox) * g.inv_cell)), x1 = min(g.nx - 1, (int)floorf((px + rx - g.ox) * g.inv_cell));
+      if (x0 > x1) continue;
+      m &= (x1 - x0 >= 63 ? ~0ull : ((1ull << (x1 - x0 + 1)) - 1ull)) << x0;
+      if (!m) continue;
+      x0 = __ffsll((long long)m) - 1;  // trim to the occupied cells of the range
+      x1 = 63 - __clzll((long long)m);
+      int row = (cz * g.ny + cy) * g.nx;
+      int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+      for (int j = b; j < e; ++j) visit(__ldg(g.sorted + j));
+    }
+  }
+}
+
+// ---- lookup-table construction ---------------------------------------------------------------
+// Level 0: brute force (tiled through shared memory) on a lattice 4x coarser than the table: nearest centroid of
+// every coarse cell centre.  Only seeds level 1.
+__global__ void table_coarse_kernel(float ox, float oy, float oz, float cell0, int n0x, int n0y, int n0z, const float* __restrict__ cent, int F,
+                                    float* __restrict__ dc0, int* __restrict__ idx0) {
+  __shared__ float sx[1024], sy[1024], sz[1024];
+  int n = n0x * n0y * n0z;
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
-  float px = g.ox + (cx + 0.5f) * g.cell, py = g.oy + (cy + 0.5f) * g.cell, pz = g.oz + (cz + 0.5f) * g.cell;
+  int cx = c % n0x, cy = (c / n0x) % n0y, cz = c / (n0x * n0y);
+  float px = ox + (cx + 0.5f) * cell0, py = oy + (cy + 0.5f) * cell0, pz = oz + (cz + 0.5f) * cell0;
   float best = 3.0e38f;
   int besti = 0;
   for (int base = 0; base < F; base += 1024) {
@@ -183,116 +220,102 @@ __global__ void grid_center_dist_kernel(Grid g, const float* __restrict__ cent, 
       if (d2 < best) { best = d2; besti = base + i; }
     }
   }
+  if (c < n) { dc0[c] = sqrtf(best); idx0[c] = besti; }
+}
+
+// Level 1: the table itself.  Per table cell: distance dc from the centre to its nearest centroid (found through the
+// enumeration grid, seeded by level 0) and that centroid's index; +huge when every point of the cell is PROVABLY
+// transparent.  Proof: for p in the cell, its nearest centroid c* satisfies |centre - c*| <= dc + 2*half_diag
+// (candidate set), the signed plane distance h is 1-Lipschitz, so |h*(centre)| > 0.1 + half_diag for every
+// candidate implies |h*(p)| > 0.1 = max_dist of get_transparent_mask (utils/render_utils.py:103).
+__global__ void table_fine_kernel(Grid g, const float4* __restrict__ tri_n, float cell0, int n0x, int n0y, int n0z, const float* __restrict__ dc0,
+                                  const int* __restrict__ idx0, int classify, float* __restrict__ out, int* __restrict__ out_idx) {
+  int n = g.tnx * g.tny * g.tnz;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  int cx = c % g.tnx, cy = (c / g.tnx) % g.tny, cz = c / (g.tnx * g.tny);
+  const float tcell = 1.0f / g.tinv;
+  float px = g.ox + (cx + 0.5f) * tcell, py = g.oy + (cy + 0.5f) * tcell, pz = g.oz + (cz + 0.5f) * tcell;
+  int c0 = (min(cz / 4, n0z - 1) * n0y + min(cy / 4, n0y - 1)) * n0x + min(cx / 4, n0x - 1);
+  float d0 = dc0[c0];
+  int seed = idx0[c0];
+  const float hd0 = cell0 * 0.8660254f * 1.001f;
+  if (d0 - hd0 - g.thalf_diag > g.r_cap) { out[c] = 3.0e30f; out_idx[c] = seed; return; }
+  float sx = px - g.cent[3 * seed], sy = py - g.cent[3 * seed + 1], sz = pz - g.cent[3 * seed + 2];
+  float best = sx * sx + sy * sy + sz * sz;
+  int besti = seed;
+  float rho2 = best * 1.0001f + 1e-12f;
+  scan_ball(g, px, py, pz, sqrtf(rho2) * 1.0001f, rho2, [&](float4 q) {
+    float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+    float d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 < best) { best = d2; besti = __float_as_int(q.w); rho2 = best * 1.0001f + 1e-12f; }
+  });
   float dc = sqrtf(best) * 1.00001f + 1e-7f;
-  const float h_thr = 0.1f + g.half_diag * 1.001f + 1e-4f;
-  // the centre's own nearest centroid is a candidate with |h| <= dc: only the band needs the second sweep
-  bool undecided = classify && (c < ncell) && (dc > h_thr) && (dc - g.half_diag <= g.r_cap);
-  bool search = (c < ncell) && (!classify || dc <= h_thr);
-  if (__syncthreads_or(undecided)) {
-    float thr = dc + 2.0f * g.half_diag * 1.001f + 1e-5f;
-    float thr2 = undecided ? thr * thr : -1.0f;
-    for (int base = 0; base < F; base += 1024) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-        int f = base + i;
-        bool ok = f < F;
-        float4 n = ok ? tri_n[f] : make_float4(0.f, 0.f, 0.f, 0.f);
-        sx[i] = ok ? cent[3 * f] : 1.0e18f;
-        sy[i] = ok ? cent[3 * f + 1] : 1.0e18f;
-        sz[i] = ok ? cent[3 * f + 2] : 1.0e18f;
-        snx[i] = n.x; sny[i] = n.y; snz[i] = n.z;
+  out_idx[c] = besti;
+  if (dc - g.thalf_diag > g.r_cap) { out[c] = 3.0e30f; return; }
+  const float h_thr = 0.1f + g.thalf_diag * 1.001f + 1e-4f;
+  bool search = !classify || dc <= h_thr;  // the nearest centroid itself is a candidate with |h| <= dc
+  if (!search) {
+    float thr = dc + 2.0f * g.thalf_diag * 1.001f + 1e-5f;
+    float thr2 = thr * thr;
+    scan_ball(g, px, py, pz, thr * 1.0001f, thr2, [&](float4 q) {
+      float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+      if (dx * dx + dy * dy + dz * dz <= thr2) {
+        float4 nq = __ldg(tri_n + __float_as_int(q.w));
+        float h = dx * nq.x + dy * nq.y + dz * nq.z;
+        if (!(fabsf(h) > h_thr)) search = true;  // NaN normal (degenerate triangle) keeps the cell searchable
       }
-      __syncthreads();
-#pragma unroll 4
-      for (int i = 0; i < 1024; ++i) {
-        float dx = px - sx[i], dy = py - sy[i], dz = pz - sz[i];
-        float d2 = dx * dx + dy * dy + dz * dz;
-        if (d2 <= thr2) {
-          float h = dx * snx[i] + dy * sny[i] + dz * snz[i];
-          if (!(fabsf(h) > h_thr)) search = true;  // NaN normal (degenerate triangle) keeps the cell searchable
-        }
-      }
-    }
+    });
   }
-  if (c < ncell) { out[c] = search ? dc : 3.0e30f; out_idx[c] = besti; }
+  out[c] = search ? dc : 3.0e30f;
 }
 
 // Exact nearest centroid: squared L2 accumulated as d0*d0, fma(d1,d1,.), fma(d2,d2,.) and
 // strict '<' with lowest index on ties -- the arithmetic of pytorch3d 0.4.0 knn_points(K=1)
 // as called at utils/render_utils.py:95.  Returns -1 when the point is provably farther than
-// g.r_cap from every centroid (then it is transparent whatever its nearest triangle is).
-// The search visits only grid rows that intersect the ball of the current best radius, which
-// starts from the cell-centre distance table, so it returns the same index as a full scan.
-// `hint` (>= 0) is any centroid index expected to be close (the previous sample's answer along a
-// ray, or the posed-space triangle for the canonical search): its exact distance seeds the search
-// radius, which only prunes -- the result is still the exact argmin.
+// g.r_cap from every centroid or sits in a provably transparent cell.  The scan visits only
+// grid rows that intersect the ball of the current best radius, which starts at the exact
+// distance to a seed centroid, so it returns the same index as a full scan.
+// `hint` (>= 0) is a caller-supplied seed (the posed-space triangle for the canonical search);
+// without it the seed is the table's centroid nearest to the cell centre.
 __device__ __forceinline__ int nearest_centroid(const Grid& g, float px, float py, float pz, unsigned long long* cand_counter,
-                                                int hint = -1, const float* __restrict__ cent = nullptr) {
-  float fx = (px - g.ox) * g.inv_cell, fy = (py - g.oy) * g.inv_cell, fz = (pz - g.oz) * g.inv_cell;
+                                                int hint = -1) {
+  float fx = (px - g.ox) * g.tinv, fy = (py - g.oy) * g.tinv, fz = (pz - g.oz) * g.tinv;
   // points outside the table region are farther than r_cap from the mesh by construction
-  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz)) return -1;
-  int hx = (int)fx, hy = (int)fy, hz = (int)fz;
-  const int cell = (hz * g.ny + hy) * g.nx + hx;
+  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.tnx && fy < (float)g.tny && fz < (float)g.tnz)) return -1;
+  const int cell = ((int)fz * g.tny + (int)fy) * g.tnx + (int)fx;
   float dc = __ldg(g.center_dist + cell);
   if (hint < 0) {
-    if (dc - g.half_diag > g.r_cap) return -1;
-    // seed: the centroid nearest to the cell centre.  Its exact distance to p is at most dc + half_diag
-    // (the table bound) and usually much less, which shrinks the ball that has to be scanned.
+    if (dc - g.thalf_diag > g.r_cap) return -1;
     hint = __ldg(g.center_idx + cell);
-    cent = g.cent;
   } else if (dc > 1.0e29f) {
-    dc = g.r_cap;  // classified cell but the caller vouches for a nearby centroid: let the hint set the radius
+    dc = g.r_cap;  // classified cell, but the caller vouches for a nearby centroid: let the hint set the radius
   }
-  float rho = fminf(dc + g.half_diag, g.r_cap * 1.0001f + g.half_diag);
-  float rho2 = rho * rho * 1.0001f;
-  const float rho2_init = rho2;
-  float best = 3.0e38f;
-  int besti = -1;
-  if (hint >= 0) {
-    float dx = xsub(px, __ldg(cent + 3 * hint)), dy = xsub(py, __ldg(cent + 3 * hint + 1)), dz = xsub(pz, __ldg(cent + 3 * hint + 2));
-    float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
-    best = d;
-    besti = hint;
-    rho2 = fminf(rho2, best * 1.0001f + 1e-12f);
-    rho = fminf(rho, sqrtf(rho2) * 1.0001f);
+  // true nearest distance <= dc + half_diag; a candidate beyond that bound means the point is farther than r_cap anyway
+  const float bound = fminf(dc + g.thalf_diag, g.r_cap * 1.0001f + g.thalf_diag);
+  const float rho2_init = bound * bound * 1.0001f;
+  float best, rho2;
+  int besti = hint;
+  {
+    float dx = xsub(px, __ldg(g.cent + 3 * hint)), dy = xsub(py, __ldg(g.cent + 3 * hint + 1)), dz = xsub(pz, __ldg(g.cent + 3 * hint + 2));
+    best = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+    rho2 = fminf(rho2_init, best * 1.0001f + 1e-12f);
   }
-  unsigned long long ncand = 0;
-  int z0 = max(0, (int)floorf((pz - rho - g.oz) * g.inv_cell)), z1 = min(g.nz - 1, (int)floorf((pz + rho - g.oz) * g.inv_cell));
-  int y0 = max(0, (int)floorf((py - rho - g.oy) * g.inv_cell)), y1 = min(g.ny - 1, (int)floorf((py + rho - g.oy) * g.inv_cell));
-  for (int cz = z0; cz <= z1; ++cz) {
-    float zl = g.oz + cz * g.cell;
-    float dz = fmaxf(0.f, fmaxf(zl - pz, pz - (zl + g.cell)));
-    float dz2 = dz * dz * 0.9999f;
-    if (dz2 > rho2) continue;
-    for (int cy = y0; cy <= y1; ++cy) {
-      float yl = g.oy + cy * g.cell;
-      float dy = fmaxf(0.f, fmaxf(yl - py, py - (yl + g.cell)));
-      float rem = rho2 - dz2 - dy * dy * 0.9999f;
-      if (rem < 0.f) continue;
-      float rx = sqrtf(rem) * 1.0001f + 1e-6f;
-      int x0 = max(0, (int)floorf((px - rx - g.ox) * g.inv_cell)), x1 = min(g.nx - 1, (int)floorf((px + rx - g.ox) * g.inv_cell));
-      if (x0 > x1) continue;
-      int row = (cz * g.ny + cy) * g.nx;
-      int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
-      ncand += (unsigned)(e - b);
-      for (int j = b; j < e; ++j) {
-        float4 c = __ldg(g.sorted + j);
-        float dx = xsub(px, c.x), dy2 = xsub(py, c.y), dzz = xsub(pz, c.z);
-        float d = xmul(dx, dx);
-        d = xfma(dy2, dy2, d);
-        d = xfma(dzz, dzz, d);
-        int id = __float_as_int(c.w);
-        if (d < best || (d == best && id < besti)) {
-          best = d;
-          besti = id;
-          rho2 = fminf(rho2, best * 1.0001f + 1e-12f);
-        }
-      }
+  unsigned ncand = 0;
+  scan_ball(g, px, py, pz, sqrtf(rho2) * 1.0001f, rho2, [&](float4 c) {
+    float dx = xsub(px, c.x), dy = xsub(py, c.y), dz = xsub(pz, c.z);
+    float d = xmul(dx, dx);
+    d = xfma(dy, dy, d);
+    d = xfma(dz, dz, d);
+    int id = __float_as_int(c.w);
+    ++ncand;
+    if (d < best || (d == best && id < besti)) {
+      best = d;
+      besti = id;
+      rho2 = fminf(rho2, best * 1.0001f + 1e-12f);
     }
-  }
-  if (cand_counter && ncand) atomicAdd(cand_counter, ncand);
-  // a candidate beyond the initial radius came from a partially covered cell: the true nearest
-  // may sit in an unvisited one, but it is farther than r_cap either way
+  });
+  if (cand_counter && ncand) atomicAdd(cand_counter, (unsigned long long)ncand);
   if (best > rho2_init) besti = -1;
   return besti;
 }
@@ -300,21 +323,42 @@ __device__ __forceinline__ int nearest_centroid(const Grid& g, float px, float p
 // ---------------------------------------------------------------------------------------------
 // geometry_guided_ray_marching, utils/pts_utils.py:18-53 (near/far only).
 // vq = (vertex - o0, |vertex - o0|^2) per vertex, prepared by gg_prep_kernel.
-__global__ void gg_prep_kernel(const float* __restrict__ xyz, int V, const float* __restrict__ ray_o, float4* __restrict__ vq) {
+__device__ __forceinline__ unsigned f2key(float f) { unsigned b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+__device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
+
+// qbox: 6 order-preserving keys, [0..2] = min (initialised to 0xff..), [3..5] = max (initialised to 0) of q
+__global__ void gg_prep_kernel(const float* __restrict__ xyz, int V, const float* __restrict__ ray_o, float4* __restrict__ vq,
+                               unsigned* __restrict__ qbox) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
   // the reference uses ray_o[:, 0:1] -- the FIRST ray's origin -- for every ray (pts_utils.py:31,33)
-  float qx = xsub(xyz[3 * v], ray_o[0]), qy = xsub(xyz[3 * v + 1], ray_o[1]), qz = xsub(xyz[3 * v + 2], ray_o[2]);
-  float qq = xadd(xadd(xmul(qx, qx), xmul(qy, qy)), xmul(qz, qz));
-  vq[v] = make_float4(qx, qy, qz, qq);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  bool live = v < V;
+  if (live) {
+    qx = xsub(xyz[3 * v], ray_o[0]); qy = xsub(xyz[3 * v + 1], ray_o[1]); qz = xsub(xyz[3 * v + 2], ray_o[2]);
+    float qq = xadd(xadd(xmul(qx, qx), xmul(qy, qy)), xmul(qz, qz));
+    vq[v] = make_float4(qx, qy, qz, qq);
+  }
+  float lo[3] = {live ? qx : 3e38f, live ? qy : 3e38f, live ? qz : 3e38f};
+  float hi[3] = {live ? qx : -3e38f, live ? qy : -3e38f, live ? qz : -3e38f};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { atomicMin(qbox + k, f2key(lo[k])); atomicMax(qbox + 3 + k, f2key(hi[k])); }
 }
 
 constexpr int GG_THREADS = 256;
 constexpr int GG_VCHUNK = 2048;  // vertices staged per smem tile (32 KB)
 
-__global__ void __launch_bounds__(GG_THREADS) gg_bounds_kernel(const float4* __restrict__ vq, int V, const float* __restrict__ ray_d,
-                                                               const float* __restrict__ near_in, const float* __restrict__ far_in,
-                                                               int64_t R, float gamma2, float* __restrict__ near_out, float* __restrict__ far_out) {
+__global__ void __launch_bounds__(GG_THREADS) gg_bounds_kernel(const float4* __restrict__ vq, int V, const unsigned* __restrict__ qbox,
+                                                               const float* __restrict__ ray_d, const float* __restrict__ near_in,
+                                                               const float* __restrict__ far_in, int64_t R, float gamma2, float gamma,
+                                                               float* __restrict__ near_out, float* __restrict__ far_out) {
   __shared__ float4 sv[GG_VCHUNK];
   int64_t r = (int64_t)blockIdx.x * GG_THREADS + threadIdx.x;
   bool live = r < R;
@@ -322,23 +366,48 @@ __global__ void __launch_bounds__(GG_THREADS) gg_bounds_kernel(const float4* __r
   if (live) { dx = ray_d[3 * r]; dy = ray_d[3 * r + 1]; dz = ray_d[3 * r + 2]; }
   float norm = xnorm3(v3(dx, dy, dz));
   float ux = xdiv(dx, norm), uy = xdiv(dy, norm), uz = xdiv(dz, norm);
+  // cull: a vertex can be within gamma of the ray's LINE (the test below has no t >= 0 restriction) only if the line
+  // meets the vertex box inflated by gamma (+ rounding slack); rays of whole blocks far from the body skip the scan
+  bool maybe = false;
+  if (live) {
+    const float pad = gamma * 1.001f + 1e-4f;
+    float t0 = -3e38f, t1 = 3e38f;
+    const float u[3] = {ux, uy, uz};
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float lo = key2f(qbox[k]) - pad, hi = key2f(qbox[3 + k]) + pad;
+      if (fabsf(u[k]) < 1e-12f) {
+        ok = ok && (lo <= 0.f && 0.f <= hi);
+      } else {
+        float a = lo / u[k], b = hi / u[k];
+        t0 = fmaxf(t0, fminf(a, b));
+        t1 = fminf(t1, fmaxf(a, b));
+      }
+    }
+    maybe = ok && (t0 <= t1 * (1.0f + 1e-5f) + 1e-5f);
+  }
   float zmin = 99999.0f, zmax = -99999.0f;
   bool any = false;
-  for (int base = 0; base < V; base += GG_VCHUNK) {
-    int n = min(GG_VCHUNK, V - base);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += GG_THREADS) sv[i] = vq[base + i];
-    __syncthreads();
+  if (__syncthreads_or(maybe)) {
+    for (int base = 0; base < V; base += GG_VCHUNK) {
+      int n = min(GG_VCHUNK, V - base);
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += GG_THREADS) sv[i] = vq[base + i];
+      __syncthreads();
+      if (maybe) {
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-      float4 q = sv[i];
-      float z0 = xadd(xadd(xmul(q.x, ux), xmul(q.y, uy)), xmul(q.z, uz));
-      float tmp = xsub(q.w, xmul(z0, z0));
-      if (tmp < gamma2) {
-        float del = xsqrt(xsub(gamma2, tmp));
-        zmin = fminf(zmin, xsub(z0, del));
-        zmax = fmaxf(zmax, xadd(z0, del));
-        any = true;
+        for (int i = 0; i < n; ++i) {
+          float4 q = sv[i];
+          float z0 = xadd(xadd(xmul(q.x, ux), xmul(q.y, uy)), xmul(q.z, uz));
+          float tmp = xsub(q.w, xmul(z0, z0));
+          if (tmp < gamma2) {
+            float del = xsqrt(xsub(gamma2, tmp));
+            zmin = fminf(zmin, xsub(z0, del));
+            zmax = fmaxf(zmax, xadd(z0, del));
+            any = true;
+          }
+        }
       }
     }
   }
@@ -411,10 +480,10 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
     if (s < P) {
       float px, py, pz;
       sample_position(a, s, px, py, pz);
-      float fx = (px - g.ox) * g.inv_cell, fy = (py - g.oy) * g.inv_cell, fz = (pz - g.oz) * g.inv_cell;
-      if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz) {
-        float dc = __ldg(g.center_dist + ((int)fz * g.ny + (int)fy) * g.nx + (int)fx);
-        need = !(dc - g.half_diag > g.r_cap);
+      float fx = (px - g.ox) * g.tinv, fy = (py - g.oy) * g.tinv, fz = (pz - g.oz) * g.tinv;
+      if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.tnx && fy < (float)g.tny && fz < (float)g.tnz) {
+        float dc = __ldg(g.center_dist + ((int)fz * g.tny + (int)fy) * g.tnx + (int)fx);
+        need = !(dc - g.thalf_diag > g.r_cap);
       }
     }
     unsigned m = __ballot_sync(0xffffffffu, need);

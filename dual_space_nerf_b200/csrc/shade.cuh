@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 3) shade_kernel(ShadeArgs a, Li
     int sample = __float_as_int(ac.w);
     {
       // the canonical point was emitted on canonical triangle active_tri[t]: its centroid is an excellent seed
-      int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr, a.active_tri ? a.active_tri[t] : -1, a.cent_canon);
+      int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr, a.active_tri ? a.active_tri[t] : -1);
       if (idx < 0) {  // cannot happen for warped points; keep the exact answer anyway
         float best = 3.0e38f;
         for (int f = 0; f < a.F; ++f) {

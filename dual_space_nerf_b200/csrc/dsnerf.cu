@@ -15,6 +15,7 @@
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
 #include "shade.cuh"
+#include "light_tc.cuh"
 
 using namespace dsn;
 
@@ -71,6 +72,7 @@ struct dsnerf_ctx {
   SimtWeights sw{};
   LightWeights lw{};
   TcWeights tw;      // fp16 hi/lo tensor-core layouts
+  DevBuf light_w2;   // lighting layer 2 as a packed fp16 B operand
   // ---- mesh
   bool have_mesh = false;
   int F = 0, V = 0;
@@ -335,6 +337,17 @@ int check_ready(dsnerf_ctx* ctx, bool need_frame) {
   return 0;
 }
 
+int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStream_t st) {
+  if (flags & DSNERF_MLP_FP32_SIMT) {
+    shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
+    CKL("shade");
+  } else {
+    light_tc_kernel<<<ctx->sm_count * 3, LT_THREADS, LT_SMEM, st>>>(sa, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
+    CKL("light_tc");
+  }
+  return 0;
+}
+
 ShadeArgs base_shade_args(dsnerf_ctx* ctx) {
   ShadeArgs s{};
   s.active = ctx->active.as<float4>();
@@ -406,8 +419,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   sa.active_tri = ctx->active_tri.as<int>();
   sa.ray_o = ray_o; sa.ray_d = ray_d; sa.near = near_use; sa.far = far_use; sa.z_in = z_in; sa.tvals = ctx->tvals.as<float>();
   sa.N = N;
-  shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
-  CKL("shade");
+  if (int e = launch_shade(ctx, sa, flags, st)) return e;
   ++launches;
   CompositeArgs ca{};
   ca.sample_mask = ctx->ray_mask.as<unsigned>();
@@ -449,6 +461,7 @@ int dsnerf_create(dsnerf_ctx** out, int device) {
   memset(ctx->h_counters, 0, sizeof(unsigned long long) * 4);
   cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMT_SMEM);
   cudaFuncSetAttribute(shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHADE_SMEM);
+  cudaFuncSetAttribute(light_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM);
   tc_configure();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { delete ctx; return DSNERF_ERR_CUDA; }
@@ -460,7 +473,7 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->near2, &ctx->far2, &ctx->raw,
+  DevBuf* bufs[] = {&ctx->light_w2, &ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->near2, &ctx->far2, &ctx->raw,
                     &ctx->active, &ctx->active_tri, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io};
   for (DevBuf* b : bufs) b->release();
   ctx->g_canon.release();
@@ -541,6 +554,12 @@ int dsnerf_set_weights(dsnerf_ctx* ctx, const float* const* t, int n_tensors) {
                             ctx->hw[T_S2_4_B], ctx->hw[T_DENS_W], ctx->hw[T_DENS_B][0], ctx->hw[T_RGB1_W], ctx->hw[T_RGB1_B],
                             ctx->hw[T_RGB3_W], ctx->hw[T_RGB3_B]))
     return fail(ctx, DSNERF_ERR_CUDA, std::string("staging tensor-core weights: ") + cudaGetErrorString((cudaError_t)e));
+  {
+    std::vector<__half> w2p;
+    light_pack_w2(ctx->hw[T_L2_W], w2p);
+    CK(ctx->light_w2.ensure(w2p.size() * sizeof(__half)));
+    CK(cudaMemcpy(ctx->light_w2.p, w2p.data(), w2p.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   ctx->have_weights = true;
   ctx->have_frame = false;  // the folded bias depends on the weights
   return 0;
@@ -764,8 +783,7 @@ int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz
   sa.xyz_world = xyz_world;
   sa.view_dir = view_dir;
   sa.N = 1;
-  shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
-  CKL("shade");
+  if (int e = launch_shade(ctx, sa, flags, st)) return e;
   scatter_points_kernel<<<blocks, 256, 0, st>>>(ctx->active.as<float4>(), ctx->raw.as<float4>(), cnt, color, density);
   CKL("scatter_points");
   return 0;

@@ -1,0 +1,158 @@
+// Shading on the tensor cores: normal_local2world + LightingMLP (model/spacenet.py:165-188, 278-298).
+//
+// Tile = 128 active samples per CTA iteration, one thread per sample (4 warps):
+//   A. exact nearest canonical centroid, world normal, world position, view direction (shade_inputs), then the
+//      9 -> 128 first layer in fp32 registers; ReLU output is written as the fp16 A operand (K-major core matrices);
+//   B. one elected lane issues 8 tcgen05.mma (M = 128, N = 128, K = 16; A and B from shared memory): the 128 x 128
+//      second layer.  Its weights are packed on the host into the B-operand image and fetched once per CTA with
+//      cp.async.bulk, so they stay resident in shared memory for every tile of the CTA;
+//   C. tcgen05.ld of the thread's accumulator row, bias + ReLU + 128 -> 1 dot + ELU in fp32, colour = (out+1)*essence.
+// ~71 KB of shared memory and 128 TMEM columns per CTA: three CTAs share an SM, so phases A/C of one CTA overlap the
+// MMAs of another.  Only the middle layer is rounded to fp16 (single pass): the lighting term is smooth and enters the
+// colour linearly (measured effect on |d rgb| is ~1e-5); the fp32 SIMT kernel in shade.cuh remains as
+// the verification path.
+#pragma once
+#include "mlp_tc.cuh"
+#include "shade.cuh"
+
+namespace dsn {
+
+constexpr int LT_THREADS = 128;
+constexpr uint32_t LT_SM_W2 = 0;                    // B operand: [16 k-chunks][128 rows][8] fp16 = 32 KB
+constexpr uint32_t LT_SM_A = 32768;                 // A operand: [16 k-chunks][128 rows][8] fp16 = 32 KB
+constexpr uint32_t LT_SM_W1 = 65536;                // fp32 [128][12]: 9 weights, bias, 2 pad
+constexpr uint32_t LT_SM_B2 = LT_SM_W1 + 128 * 12 * 4;
+constexpr uint32_t LT_SM_W3 = LT_SM_B2 + 512;
+constexpr uint32_t LT_SM_BAR = LT_SM_W3 + 512;      // 2 mbarriers + tmem slot
+constexpr uint32_t LT_SMEM = LT_SM_BAR + 64;
+constexpr uint32_t LT_TMEM_COLS = 128;
+
+__global__ void __launch_bounds__(LT_THREADS, 3) light_tc_kernel(ShadeArgs a, LightWeights L, const uint8_t* __restrict__ w2_packed, Grid gc) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_w = sbase + LT_SM_BAR, bar_mma = bar_w + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + LT_SM_BAR + 16);
+  float* w1p = reinterpret_cast<float*>(smem + LT_SM_W1);
+  float* b2 = reinterpret_cast<float*>(smem + LT_SM_B2);
+  float* w3 = reinterpret_cast<float*>(smem + LT_SM_W3);
+  const int warp = threadIdx.x >> 5;
+  const int row = threadIdx.x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 128 * 12; i += LT_THREADS) {
+    int k = i / 12, j = i - k * 12;
+    w1p[i] = j < 9 ? L.w1t[j * 128 + k] : (j == 9 ? L.b1[k] : 0.f);
+  }
+  for (int i = threadIdx.x; i < 128; i += LT_THREADS) { b2[i] = L.b2[i]; w3[i] = L.w3[i]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) {  // second-layer weights: one bulk copy, resident for the whole kernel
+    mbar_expect_tx(bar_w, 32768);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sbase + LT_SM_W2), "l"(w2_packed), "r"(32768u), "r"(bar_w) : "memory");
+  }
+  const int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
+  const int64_t n_tiles = (n_active + LT_THREADS - 1) / LT_THREADS;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t mma_phase = 0;
+  bool w_ready = false;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t t = tile * LT_THREADS + row;
+    const bool live = t < n_active;
+    float in[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float4 ma = make_float4(0.f, 0.f, 0.f, 0.f);
+    int sample = 0;
+    if (live) shade_inputs(a, gc, t, in, sample, ma);
+    // ---- first layer (fp32) -> fp16 A operand
+#pragma unroll 2
+    for (int kc = 0; kc < 16; ++kc) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        float hv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4* w1 = reinterpret_cast<const float4*>(w1p + (kc * 8 + e + u) * 12);
+          const float4 wa = w1[0], wb = w1[1], wc = w1[2];
+          float h = wc.y;
+          h = fmaf(in[0], wa.x, h); h = fmaf(in[1], wa.y, h); h = fmaf(in[2], wa.z, h); h = fmaf(in[3], wa.w, h);
+          h = fmaf(in[4], wb.x, h); h = fmaf(in[5], wb.y, h); h = fmaf(in[6], wb.z, h); h = fmaf(in[7], wb.w, h);
+          h = fmaf(in[8], wc.x, h);
+          hv[u] = fmaxf(h, 0.f);
+        }
+        pk[e / 2] = pack_h2(hv[0], hv[1]);
+      }
+      *reinterpret_cast<uint4*>(smem + LT_SM_A + (uint32_t)kc * (LT_THREADS * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    // ---- second layer on the tensor core
+    if (warp == 0) {
+      if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t DHI = (128u >> 4) | (1u << 14);
+        constexpr uint32_t LBO = ((LT_THREADS * 16) >> 4) << 16;
+        constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a0 = LBO | ((sbase + LT_SM_A) >> 4), b0 = LBO | ((sbase + LT_SM_W2) >> 4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t step = (uint32_t)k * ((2 * LT_THREADS * 16) >> 4);
+          tc_mma_ss(tmem, ((uint64_t)DHI << 32) | (a0 + step), ((uint64_t)DHI << 32) | (b0 + step), IDESC, k > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    // ---- third layer + ELU (fp32)
+    float out = L.b3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(b2 + c * 32 + i);
+        const float4 ww = *reinterpret_cast<const float4*>(w3 + c * 32 + i);
+        out = fmaf(fmaxf(__uint_as_float(v[i]) + bb.x, 0.f), ww.x, out);
+        out = fmaf(fmaxf(__uint_as_float(v[i + 1]) + bb.y, 0.f), ww.y, out);
+        out = fmaf(fmaxf(__uint_as_float(v[i + 2]) + bb.z, 0.f), ww.z, out);
+        out = fmaf(fmaxf(__uint_as_float(v[i + 3]) + bb.w, 0.f), ww.w, out);
+      }
+    }
+    const float light = (out > 0.f ? out : expm1f(out)) + 1.0f;
+    if (live) a.raw[sample] = make_float4(light * ma.y, light * ma.z, light * ma.w, ma.x);
+    tc_fence_before();
+    __syncthreads();  // accumulator and A operand are reused by the next tile
+    tc_fence_after();
+  }
+  if (warp == 0 && !w_ready) mbar_wait(bar_w, 0);  // never leave with the bulk copy in flight
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(LT_TMEM_COLS) : "memory");
+  }
+}
+
+// host: pack lights_encoding.2.weight [out=128][in=128] as the B operand image (B[n][k] = W[n][k])
+inline void light_pack_w2(const std::vector<float>& w2, std::vector<__half>& out) {
+  out.assign((size_t)128 * 128, __float2half_rn(0.f));
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 128; ++k) out[((size_t)(k / 8) * 128 + n) * 8 + (k % 8)] = __float2half_rn(w2[(size_t)n * 128 + k]);
+}
+
+}  // namespace dsn

@@ -64,9 +64,52 @@ __device__ __forceinline__ V3 normal_to_world(V3 g, V3 c0, V3 c1, V3 c2, V3 m0, 
   return v3(r.x * in, r.y * in, r.z * in);
 }
 
-// One thread per active sample.  The lighting layers run out of shared memory; the 128 hidden
-// units of the first layer are recomputed per 32-wide output chunk instead of being staged, which
-// keeps the block at ~71 KB of shared memory (3 blocks = 24 warps per SM).
+// Inputs of the lighting MLP for active sample t: world normal (normal_local2world, model/spacenet.py:278-298, incl. the
+// exact nearest canonical centroid), world position (with the optional rot / light_center shift, :254-263) and the
+// normalised view direction (:179-181).
+__device__ __forceinline__ void shade_inputs(const ShadeArgs& a, const Grid& gc, int64_t t, float (&in)[9], int& sample, float4& ma) {
+  float4 ac = a.active[t];
+  ma = a.mlp_a[t];
+  float4 mg = a.mlp_g[t];
+  sample = __float_as_int(ac.w);
+  // the canonical point was emitted on canonical triangle active_tri[t]: its centroid is an excellent seed
+  int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr, a.active_tri ? a.active_tri[t] : -1);
+  if (idx < 0) {  // cannot happen for warped points; keep the exact answer anyway
+    float best = 3.0e38f;
+    for (int f = 0; f < a.F; ++f) {
+      float dx = xsub(ac.x, a.cent_canon[3 * f]), dy = xsub(ac.y, a.cent_canon[3 * f + 1]), dz = xsub(ac.z, a.cent_canon[3 * f + 2]);
+      float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+      if (d < best) { best = d; idx = f; }
+    }
+  }
+  int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
+  V3 nw = normal_to_world(v3(mg.x, mg.y, mg.z), ldv3(a.canon, i0), ldv3(a.canon, i1), ldv3(a.canon, i2),
+                          ldv3(a.posed, i0), ldv3(a.posed, i1), ldv3(a.posed, i2));
+  float px, py, pz, dx, dy, dz;
+  if (a.xyz_world) {
+    px = a.xyz_world[3 * (int64_t)sample]; py = a.xyz_world[3 * (int64_t)sample + 1]; pz = a.xyz_world[3 * (int64_t)sample + 2];
+    dx = a.view_dir[3 * (int64_t)sample]; dy = a.view_dir[3 * (int64_t)sample + 1]; dz = a.view_dir[3 * (int64_t)sample + 2];
+  } else {
+    int64_t r = sample / a.N;
+    int i = sample - (int)(r * a.N);
+    float z = a.z_in ? a.z_in[sample] : sample_z(a.near[r], a.far[r], a.tvals[i]);
+    dx = a.ray_d[3 * r]; dy = a.ray_d[3 * r + 1]; dz = a.ray_d[3 * r + 2];
+    px = xadd(a.ray_o[3 * r], xmul(dx, z)); py = xadd(a.ray_o[3 * r + 1], xmul(dy, z)); pz = xadd(a.ray_o[3 * r + 2], xmul(dz, z));
+  }
+  if (a.has_rot) {  // model/spacenet.py:254-258: xy <- (xy - c) @ rot + c
+    float qx = px - a.rot_center[0], qy = py - a.rot_center[1];
+    px = qx * a.rot[0] + qy * a.rot[2] + a.rot_center[0];
+    py = qx * a.rot[1] + qy * a.rot[3] + a.rot_center[1];
+  }
+  if (a.has_shift) { px += a.light_shift[0]; py += a.light_shift[1]; pz += a.light_shift[2]; }  // :260-263
+  float dn = xnorm3(v3(dx, dy, dz));
+  in[0] = nw.x; in[1] = nw.y; in[2] = nw.z; in[3] = px; in[4] = py; in[5] = pz;
+  in[6] = xdiv(dx, dn); in[7] = xdiv(dy, dn); in[8] = xdiv(dz, dn);
+}
+
+// fp32 SIMT shading (verification path, flag DSNERF_MLP_FP32_SIMT).  One thread per active sample; the lighting
+// layers run out of shared memory; the 128 hidden units of the first layer are recomputed per 32-wide output chunk
+// instead of being staged, which keeps the block at ~71 KB of shared memory (3 blocks = 24 warps per SM).
 __global__ void __launch_bounds__(SHADE_THREADS, 3) shade_kernel(ShadeArgs a, LightWeights L, Grid gc) {
   extern __shared__ __align__(16) float sm[];
   float* w1p = sm;                 // [128][12]
@@ -83,45 +126,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, 3) shade_kernel(ShadeArgs a, Li
   int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
   for (int64_t t = (int64_t)blockIdx.x * SHADE_THREADS + threadIdx.x; t < n_active; t += (int64_t)gridDim.x * SHADE_THREADS) {
     float in[9];
-    float4 ac = a.active[t];
-    float4 ma = a.mlp_a[t];
-    float4 mg = a.mlp_g[t];
-    int sample = __float_as_int(ac.w);
-    {
-      // the canonical point was emitted on canonical triangle active_tri[t]: its centroid is an excellent seed
-      int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr, a.active_tri ? a.active_tri[t] : -1);
-      if (idx < 0) {  // cannot happen for warped points; keep the exact answer anyway
-        float best = 3.0e38f;
-        for (int f = 0; f < a.F; ++f) {
-          float dx = xsub(ac.x, a.cent_canon[3 * f]), dy = xsub(ac.y, a.cent_canon[3 * f + 1]), dz = xsub(ac.z, a.cent_canon[3 * f + 2]);
-          float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
-          if (d < best) { best = d; idx = f; }
-        }
-      }
-      int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
-      V3 nw = normal_to_world(v3(mg.x, mg.y, mg.z), ldv3(a.canon, i0), ldv3(a.canon, i1), ldv3(a.canon, i2),
-                              ldv3(a.posed, i0), ldv3(a.posed, i1), ldv3(a.posed, i2));
-      float px, py, pz, dx, dy, dz;
-      if (a.xyz_world) {
-        px = a.xyz_world[3 * (int64_t)sample]; py = a.xyz_world[3 * (int64_t)sample + 1]; pz = a.xyz_world[3 * (int64_t)sample + 2];
-        dx = a.view_dir[3 * (int64_t)sample]; dy = a.view_dir[3 * (int64_t)sample + 1]; dz = a.view_dir[3 * (int64_t)sample + 2];
-      } else {
-        int64_t r = sample / a.N;
-        int i = sample - (int)(r * a.N);
-        float z = a.z_in ? a.z_in[sample] : sample_z(a.near[r], a.far[r], a.tvals[i]);
-        dx = a.ray_d[3 * r]; dy = a.ray_d[3 * r + 1]; dz = a.ray_d[3 * r + 2];
-        px = xadd(a.ray_o[3 * r], xmul(dx, z)); py = xadd(a.ray_o[3 * r + 1], xmul(dy, z)); pz = xadd(a.ray_o[3 * r + 2], xmul(dz, z));
-      }
-      if (a.has_rot) {  // model/spacenet.py:254-258: xy <- (xy - c) @ rot + c
-        float qx = px - a.rot_center[0], qy = py - a.rot_center[1];
-        px = qx * a.rot[0] + qy * a.rot[2] + a.rot_center[0];
-        py = qx * a.rot[1] + qy * a.rot[3] + a.rot_center[1];
-      }
-      if (a.has_shift) { px += a.light_shift[0]; py += a.light_shift[1]; pz += a.light_shift[2]; }  // :260-263
-      float dn = xnorm3(v3(dx, dy, dz));
-      in[0] = nw.x; in[1] = nw.y; in[2] = nw.z; in[3] = px; in[4] = py; in[5] = pz;
-      in[6] = xdiv(dx, dn); in[7] = xdiv(dy, dn); in[8] = xdiv(dz, dn);
-    }
+    float4 ma;
+    int sample;
+    shade_inputs(a, gc, t, in, sample, ma);
     // LightingMLP (model/spacenet.py:165-188): 9 -> 128 -> 128 -> 1, ReLU, ReLU, ELU; color = (out+1)*essence
     float out = L.b3;
 #pragma unroll 1

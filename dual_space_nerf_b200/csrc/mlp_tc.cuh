@@ -13,21 +13,21 @@
 //     fp16 range (the normal is scale invariant).
 //
 // Pipeline (one CTA = one SM, 10 warps)
-//   * every layer is computed as two N-halves of 128 columns into two TMEM accumulators, so the
-//     epilogue of one half (8 warps: tcgen05.ld -> bias/ReLU/mask/split -> next A operand) overlaps the
-//     MMAs of the other half and the first K-half of the next layer;
-//   * the A operand ping-pongs between two buffers: fp16 hi parts in shared memory (K-major,
-//     no-swizzle core matrices), fp16 lo parts in TMEM (the third MMA of a k-step reads A from TMEM),
-//     so a layer's output never overwrites the operand its own MMAs are still reading;
-//   * weights are pre-packed on the host into the exact shared-memory image, in consumption order, and
-//     streamed by one elected lane with cp.async.bulk (TMA engine) into a 4x16 KB mbarrier ring.  The kernel
-//     is cluster-ready (TC_CLUSTER = 2: each CTA fetches half of every slab and multicasts it to both, so
-//     every weight byte leaves L2 once per cluster); measured on B200 the ring is latency- not
-//     bandwidth-bound, so the default is TC_CLUSTER = 1 (no lockstep between CTAs);
-//   * one elected lane of a converged warp issues all tcgen05.mma (slab-templated, descriptors are
-//     "base + immediate"); tcgen05.commit releases ring slots and publishes finished accumulator halves.
-//   Measured (profiles/): an SS MMA (A from shared memory) occupies the tensor pipe for >= 128 cycles
-//   whatever N is (A-tile read, 4 KB at 32 B/cycle), a TS MMA (A from TMEM) for N/2 cycles.
+//   * measured on B200 (profiles/): an MMA whose A operand comes from shared memory occupies the tensor pipe for
+//     >= 128 cycles whatever N is (the 128 x 16 A tile is read at 32 B/cycle), so every MMA here is N = 256
+//     (128 cycles = the ideal rate); an earlier version with two N = 128 halves ran 1.7-2x slower per layer;
+//   * the A operand (fp16 hi + lo, K-major no-swizzle core matrices, 128 KB) is rewritten in place by the
+//     epilogue; two 256-column TMEM accumulators alternate between layers, so the epilogue of layer l (8 warps:
+//     tcgen05.ld -> bias/ReLU/mask bits/hi-lo split -> st.shared) overlaps the MMAs of layer l+1: the epilogue
+//     publishes its first 128 columns early and the next layer's first 8 k-steps start on them;
+//   * weights are pre-packed on the host into the exact shared-memory image, in consumption order, and streamed
+//     by one elected lane with cp.async.bulk (TMA engine) into a 4x16 KB mbarrier ring (cluster-ready: with
+//     TC_CLUSTER = 2 each CTA fetches half of every slab and multicasts it; the ring is latency- not
+//     bandwidth-bound on B200, so the default is 1);
+//   * one elected lane of a converged warp issues all tcgen05.mma (slab-templated: descriptors are
+//     "base + immediate"); tcgen05.commit releases ring slots and publishes finished accumulators;
+//   * ReLU bits live in registers (28 words per thread), d sigma / d PE of layer 4 is parked in the idle A-lo
+//     region during the backward chain, cross-thread partial sums go through 8 TMEM cells per row.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -44,8 +44,8 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_CLUSTER = 1;
 constexpr uint32_t TC_STAGE_BYTES = 16384;
 // shared memory map (bytes)
-constexpr uint32_t SM_A0 = 0;            // A operand (fp16 hi), buffer 0: [K/8 = 32 chunks][128 rows][8]
-constexpr uint32_t SM_A1 = 65536;        // buffer 1
+constexpr uint32_t SM_A_HI = 0;          // A operand, fp16 hi: [K/8 = 32 chunks][128 rows][8]
+constexpr uint32_t SM_A_LO = 65536;      // A operand, fp16 lo (forward only); backward: fp32 stash of layer 4's d sigma / d PE
 constexpr uint32_t SM_PE_HI = 131072;    // positional encoding hi, 8 chunks
 constexpr uint32_t SM_PE_LO = 147456;    // positional encoding lo
 constexpr uint32_t SM_RING = 163840;
@@ -53,28 +53,23 @@ constexpr uint32_t SM_BAR = SM_RING + TC_STAGES * TC_STAGE_BYTES;  // 229376
 constexpr uint32_t TC_SMEM = SM_BAR + 128;
 constexpr uint32_t A_CHUNK = TC_TILE * 16;  // bytes between consecutive 8-wide K chunks of an A operand
 // tensor memory map (32-bit columns)
-constexpr uint32_t TM_ACC0 = 0;     // accumulator, output columns   0..127
-constexpr uint32_t TM_ACC1 = 128;   // accumulator, output columns 128..255
-constexpr uint32_t TM_LO0 = 256;    // A operand lo (fp16 pairs), buffer 0: K = 256 -> 128 columns
-constexpr uint32_t TM_LO1 = 384;    // buffer 1
-constexpr uint32_t TM_GPE = 256;    // d sigma / d PE (64 columns); aliases TM_LO0, which is idle in the backward chain
-constexpr uint32_t TM_XCH = 0;      // 8 columns of cross-thread partial sums at the very end of a tile (aliases TM_ACC0)
+constexpr uint32_t TM_ACC = 256;    // accumulator b (= op & 1) starts at column b * TM_ACC
+constexpr uint32_t TM_XCH = 256;    // 8 columns of cross-thread partial sums at the very end of a tile (accumulator 1 is idle then)
 constexpr uint32_t TM_COLS = 512;
 
 constexpr int TC_NUM_OPS = 15;
 enum { A_ACT = 0, A_PE = 1, A_ACT_PE = 2 };
 
+enum { K_FWD = 0, K_RGB = 1, K_BWD = 2, K_BW4 = 3, K_BW0 = 4 };
+
 struct TcOp {
-  uint32_t src_off[2];     // byte offset of the first slab of each N-half in the packed weight blob
-  uint32_t slab_bytes[2];  // bytes per slab (<= TC_STAGE_BYTES, multiple of 32)
-  uint16_t n_slabs[2];     // 0 => this op has no MMAs in that half
-  uint16_t ksteps[2];      // k-steps (of 16) per slab
-  uint16_t rows[2];        // B rows per k-chunk in the slab (LBO = rows * 16 bytes)
-  uint16_t n_mma[2];       // N of the main MMA of the half
-  uint8_t passes;          // 3 = hi/lo split, 1 = hi only
-  uint8_t a_src;           // A_ACT, A_PE, A_ACT_PE (k-steps >= 16 come from the PE region)
-  uint8_t extra_h1;        // half 1 also issues an N=64 MMA (rows 128..191 of its slabs) into TM_GPE
-  uint8_t main_to_gpe;     // half-0 main MMA accumulates into TM_GPE instead of TM_ACC0
+  uint32_t src_off;     // byte offset of the op's first slab in the packed weight blob
+  uint32_t slab_bytes;  // bytes per slab (<= TC_STAGE_BYTES, multiple of 32)
+  uint16_t n_slabs;
+  uint16_t ksteps;      // k-steps (of 16) per slab
+  uint8_t kind;         // K_FWD (N=256, 3-pass), K_RGB (N=128, 3-pass), K_BWD (N=256), K_BW4 (N=256 + 64 extra), K_BW0 (N=64)
+  uint8_t a_src;        // A_ACT, A_PE, A_ACT_PE (k-steps >= 16 come from the PE region)
+  uint8_t pad[2];
 };
 
 __constant__ TcOp c_tc_ops[TC_NUM_OPS];
@@ -231,12 +226,10 @@ struct ReluBits {
 
 // Issue all MMAs of one weight slab (KSTEPS k-steps) and release its ring slot.  Shapes are template
 // parameters so that every descriptor is "slab base + immediate": the issuing lane spends a couple of
-// uniform-datapath adds per tcgen05.mma instead of rebuilding 64-bit descriptors (with N = 128 an MMA
-// occupies the tensor pipe for only 64 cycles, so the issue loop has to be that tight).
-//   a_word / b_word: low 32 bits of the A-hi / B-hi shared-memory descriptors at the slab's first k-step
-//   a_third: PE slabs -> low word of the A-lo smem descriptor; activation slabs -> TMEM address of A-lo
-template <int ROWS, int KSTEPS, bool THREE, bool THIRD_FROM_TMEM, int NMMA, bool EXTRA>
-__device__ __forceinline__ void issue_slab(uint32_t d_main, uint32_t d_extra, uint32_t a_word, uint32_t a_third, uint32_t b_word,
+// uniform-datapath adds per tcgen05.mma instead of rebuilding 64-bit descriptors.
+//   a_word / a_lo_word / b_word: low 32 bits of the A-hi / A-lo / B-hi shared-memory descriptors at the slab's first k-step
+template <int ROWS, int KSTEPS, bool THREE, int NMMA, bool EXTRA>
+__device__ __forceinline__ void issue_slab(uint32_t d_main, uint32_t d_extra, uint32_t a_word, uint32_t a_lo_word, uint32_t b_word,
                                            uint32_t first_acc, uint32_t empty_bar, uint16_t mc_mask) {
   constexpr uint32_t DHI = (128u >> 4) | (1u << 14);             // descriptor bits 32..63: SBO = 128 B, version 1
   constexpr uint32_t A_STEP = (2 * A_CHUNK) >> 4;                // one k-step along K in the A operand
@@ -252,12 +245,12 @@ __device__ __forceinline__ void issue_slab(uint32_t d_main, uint32_t d_extra, ui
       tc_mma_ss(d_main, da, db, IDESC, j == 0 ? first_acc : 1u);
       if (THREE) {
         const uint64_t dbl = ((uint64_t)DHI << 32) | (b_word + j * B_STEP + B_LO);
+        const uint64_t dal = ((uint64_t)DHI << 32) | (a_lo_word + j * A_STEP);
         tc_mma_ss(d_main, da, dbl, IDESC, 1u);
-        if (THIRD_FROM_TMEM) tc_mma_ts(d_main, a_third + j * 8, db, IDESC, 1u);
-        else tc_mma_ss(d_main, ((uint64_t)DHI << 32) | (a_third + j * A_STEP), db, IDESC, 1u);
+        tc_mma_ss(d_main, dal, db, IDESC, 1u);
       }
       if (EXTRA) {
-        const uint64_t dbx = ((uint64_t)DHI << 32) | (b_word + j * B_STEP + ((128 * 16) >> 4));
+        const uint64_t dbx = ((uint64_t)DHI << 32) | (b_word + j * B_STEP + ((256 * 16) >> 4));
         tc_mma_ss(d_extra, da, dbx, IDESC_X, j == 0 ? first_acc : 1u);
       }
     }
@@ -272,14 +265,15 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + SM_BAR;             // [TC_STAGES]   weights landed
   const uint32_t bar_empty = bar_full + 8 * TC_STAGES;  // [TC_STAGES]   ring slot consumed by every CTA of the cluster
-  const uint32_t bar_acc = bar_empty + 8 * TC_STAGES;   // [2]           accumulator half complete (MMA -> epilogue)
-  const uint32_t bar_a = bar_acc + 16;                  // [2]           epilogue of accumulator half done (epilogue -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * (2 * TC_STAGES + 4));
+  const uint32_t bar_acc = bar_empty + 8 * TC_STAGES;   //               accumulator complete (MMA -> epilogue)
+  const uint32_t bar_a = bar_acc + 8;                   // [4]           epilogue done with column quarter q (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * (2 * TC_STAGES + 6));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_CLUSTER); }
-    for (int h = 0; h < 2; ++h) { mbar_init(bar_acc + 8 * h, 1); mbar_init(bar_a + 8 * h, TC_EPI_WARPS * 32); }
+    mbar_init(bar_acc, 1);
+    for (int q4 = 0; q4 < 4; ++q4) mbar_init(bar_a + 8 * q4, TC_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS) {
@@ -307,19 +301,17 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
       for (int64_t it = 0; it < n_iter; ++it) {
         for (int op = 0; op < n_ops; ++op) {
           const TcOp o = c_tc_ops[op];
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t part = o.slab_bytes[h] / TC_CLUSTER;
-            const uint8_t* src = P.wpack + o.src_off[h] + cta_rank * part;
-            for (int s = 0; s < o.n_slabs[h]; ++s) {
-              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              if (elect_one()) {
-                mbar_expect_tx(bar_full + 8 * stage, o.slab_bytes[h]);
-                bulk_g2s_mc(sbase + SM_RING + stage * TC_STAGE_BYTES + cta_rank * part, src + (size_t)s * o.slab_bytes[h], part,
-                            bar_full + 8 * stage, mc_mask);
-              }
-              __syncwarp();
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          const uint32_t part = o.slab_bytes / TC_CLUSTER;
+          const uint8_t* src = P.wpack + o.src_off + cta_rank * part;
+          for (int s = 0; s < o.n_slabs; ++s) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(bar_full + 8 * stage, o.slab_bytes);
+              bulk_g2s_mc(sbase + SM_RING + stage * TC_STAGE_BYTES + cta_rank * part, src + (size_t)s * o.slab_bytes, part,
+                          bar_full + 8 * stage, mc_mask);
             }
+            __syncwarp();
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -334,60 +326,46 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
           const TcOp o = c_tc_ops[op];
           const bool mstamp = P.timing && blockIdx.x == 0 && it == 0 && lane == 0;
           long long w_full = 0, w_a = 0, t_op0 = mstamp ? clock64() : 0;
-          const uint32_t abuf = (uint32_t)(op + 1) & 1u;  // A buffer read by this op (its producer wrote buffer (op-1)&1)
-          const uint32_t a_hi_base = sbase + (abuf ? SM_A1 : SM_A0);
-          const uint32_t a_lo_tm = tmem + (abuf ? TM_LO1 : TM_LO0);
-          bool waited1 = false;
-          for (int h = 0; h < 2; ++h) {
-            if (h == 0) {
-              long long t0 = mstamp ? clock64() : 0;
-              mbar_wait(bar_a, a_phase);  // producer's half 0 done: A columns 0..127 written, accumulator half 0 free
-              if (o.a_src == A_PE || o.n_slabs[0] == 0) { mbar_wait(bar_a + 8, a_phase); waited1 = true; }
-              tc_fence_after();
-              if (mstamp) w_a += clock64() - t0;
+          const uint32_t d_main = tmem + (uint32_t)(op & 1) * TM_ACC;
+          const uint32_t d_extra = tmem + (uint32_t)((op & 1) ^ 1) * TM_ACC;
+          // the producer's epilogue publishes its 256 output columns in four quarters of 64 (= 4 k-steps of this op's A operand)
+          int waited = 0;
+          auto need_quarters = [&](int nq) {
+            if (waited >= nq) return;
+            long long t0 = mstamp ? clock64() : 0;
+            while (waited < nq) { mbar_wait(bar_a + 8 * waited, a_phase); ++waited; }
+            tc_fence_after();
+            if (mstamp) w_a += clock64() - t0;
+          };
+          need_quarters(o.a_src == A_PE ? 4 : 1);
+          const uint32_t rows = o.kind == K_FWD || o.kind == K_BWD ? 256u : (o.kind == K_RGB ? 128u : (o.kind == K_BW4 ? 320u : 64u));
+          const uint32_t b_lbo = ((rows * 16) >> 4) << 16;
+          uint32_t kk = 0;
+          for (int s = 0; s < o.n_slabs; ++s, kk += o.ksteps) {
+            if (kk < 16) need_quarters(min(4, (int)((kk + o.ksteps - 1) >> 2) + 1));
+            long long t1 = mstamp ? clock64() : 0;
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            if (mstamp) w_full += clock64() - t1;
+            const uint32_t b_word = b_lbo | ((sbase + SM_RING + stage * TC_STAGE_BYTES) >> 4);
+            const uint32_t ebar = bar_empty + 8 * stage;
+            const bool from_pe = (o.a_src == A_PE) || (o.a_src == A_ACT_PE && kk >= 16);
+            const uint32_t pc = (o.a_src == A_PE ? kk : kk - 16) * 2;
+            const uint32_t a_word = A_LBO | ((from_pe ? sbase + SM_PE_HI + pc * A_CHUNK : sbase + SM_A_HI + kk * 2 * A_CHUNK) >> 4);
+            const uint32_t a_lo_word = A_LBO | ((from_pe ? sbase + SM_PE_LO + pc * A_CHUNK : sbase + SM_A_LO + kk * 2 * A_CHUNK) >> 4);
+            const uint32_t first_acc = (uint32_t)(kk > 0);
+            switch (o.kind) {
+              case K_FWD: issue_slab<256, 1, true, 256, false>(d_main, 0u, a_word, a_lo_word, b_word, first_acc, ebar, mc_mask); break;
+              case K_RGB: issue_slab<128, 2, true, 128, false>(d_main, 0u, a_word, a_lo_word, b_word, first_acc, ebar, mc_mask); break;
+              case K_BWD: issue_slab<256, 2, false, 256, false>(d_main, 0u, a_word, 0u, b_word, first_acc, ebar, mc_mask); break;
+              case K_BW4: issue_slab<320, 1, false, 256, true>(d_main, d_extra, a_word, 0u, b_word, first_acc, ebar, mc_mask); break;
+              default: issue_slab<64, 8, false, 64, false>(d_main, 0u, a_word, 0u, b_word, first_acc, ebar, mc_mask); break;
             }
-            const uint32_t rows = o.rows[h], ks = o.ksteps[h];
-            const uint32_t b_lbo = ((rows * 16) >> 4) << 16;
-            const uint32_t d_main = tmem + ((h == 0 && o.main_to_gpe) ? TM_GPE : (h ? TM_ACC1 : TM_ACC0));
-            const bool to_gpe = (h == 0 && o.main_to_gpe);
-            uint32_t kk = 0;
-            for (int s = 0; s < o.n_slabs[h]; ++s, kk += ks) {
-              if (!waited1 && kk >= 8) {  // second K-half of the A operand comes from the producer's half 1
-                long long t0 = mstamp ? clock64() : 0;
-                mbar_wait(bar_a + 8, a_phase);
-                tc_fence_after();
-                waited1 = true;
-                if (mstamp) w_a += clock64() - t0;
-              }
-              long long t1 = mstamp ? clock64() : 0;
-              mbar_wait(bar_full + 8 * stage, phase);
-              tc_fence_after();
-              if (mstamp) w_full += clock64() - t1;
-              const uint32_t b_word = b_lbo | ((sbase + SM_RING + stage * TC_STAGE_BYTES) >> 4);
-              const uint32_t ebar = bar_empty + 8 * stage;
-              const bool from_pe = (o.a_src == A_PE) || (o.a_src == A_ACT_PE && kk >= 16);
-              const uint32_t first_acc = to_gpe ? 1u : (uint32_t)(kk > 0);
-              if (o.passes == 3) {
-                if (from_pe) {
-                  const uint32_t pc = (o.a_src == A_PE ? kk : kk - 16) * 2;
-                  issue_slab<128, 2, true, false, 128, false>(d_main, 0u, A_LBO | ((sbase + SM_PE_HI + pc * A_CHUNK) >> 4),
-                                                              A_LBO | ((sbase + SM_PE_LO + pc * A_CHUNK) >> 4), b_word, first_acc, ebar, mc_mask);
-                } else {
-                  issue_slab<128, 2, true, true, 128, false>(d_main, 0u, A_LBO | ((a_hi_base + kk * 2 * A_CHUNK) >> 4), a_lo_tm + kk * 8, b_word,
-                                                             first_acc, ebar, mc_mask);
-                }
-              } else {
-                const uint32_t a_word = A_LBO | ((a_hi_base + kk * 2 * A_CHUNK) >> 4);
-                if (rows == 128) issue_slab<128, 4, false, false, 128, false>(d_main, 0u, a_word, 0u, b_word, first_acc, ebar, mc_mask);
-                else if (rows == 192) issue_slab<192, 2, false, false, 128, true>(d_main, tmem + TM_GPE, a_word, 0u, b_word, first_acc, ebar, mc_mask);
-                else issue_slab<64, 8, false, false, 64, false>(d_main, 0u, a_word, 0u, b_word, first_acc, ebar, mc_mask);
-              }
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-            }
-            if (h == 0 && !waited1) { mbar_wait(bar_a + 8, a_phase); tc_fence_after(); waited1 = true; }
-            if (elect_one()) tc_commit(bar_acc + 8 * h);  // accumulator half h complete (immediately if the op has no MMAs there)
-            __syncwarp();
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
+          need_quarters(4);
+          if (elect_one()) tc_commit(bar_acc);  // accumulator (and the extra columns of K_BW4) complete
+          __syncwarp();
           a_phase ^= 1;
           if (mstamp) { P.timing[64 + 3 * op] = w_full; P.timing[65 + 3 * op] = w_a; P.timing[66 + 3 * op] = clock64() - t_op0; }
         }
@@ -395,8 +373,8 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
     }
   } else {
     // =============================== epilogue warps ===========================================
-    // warp w: TMEM lane quarter q = w % 4 (rows 32q..32q+31), column sub-block sub = w / 4: of every 128-column
-    // accumulator half this thread handles columns [64*sub, 64*sub + 64) of its row.
+    // warp w: TMEM lane quarter q = w % 4 (rows 32q..32q+31), column sub-block sub = w / 4: of every 64-column
+    // accumulator quarter this thread handles columns [32*sub, 32*sub + 32) of its row.
     const int q = warp & 3, sub = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
@@ -448,143 +426,129 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
       if (stamp) P.timing[0] = clock64();
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(bar_a);
-      mbar_arrive(bar_a + 8);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) mbar_arrive(bar_a + 8 * q4);
 
       float sigma_part = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
+      float* stash = reinterpret_cast<float*>(smem + SM_A_LO);  // [64 PE columns][128 rows] fp32, backward chain only
       for (int op = 0; op < n_ops; ++op) {
-        const uint32_t w_hi = (op & 1) ? SM_A1 : SM_A0;             // buffer this op's epilogue writes (read by op + 1)
-        const uint32_t w_lo_tm = t_lane + ((op & 1) ? TM_LO1 : TM_LO0);
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const uint32_t t_accb = t_lane + (uint32_t)(op & 1) * TM_ACC;
+        if (op == 10) {
+          // layer 4 backward also produced d sigma / d PE (64 columns) in the idle accumulator: park this thread's 32 of them
+          uint32_t v[32];
+          tmem_ld32(t_lane + (uint32_t)((op & 1) ^ 1) * TM_ACC + sub * 32, v);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar_acc + 8 * h, acc_phase);
-          tc_fence_after();
-          if (stamp) P.timing[1 + 4 * op + 2 * h] = clock64();
-          const uint32_t t_acc = t_lane + (h ? TM_ACC1 : TM_ACC0) + sub * 64;
-          const int colbase = h * 128 + sub * 64;  // first of this thread's 64 output columns in this half
+          for (int i = 0; i < 32; ++i) stash[(sub * 32 + i) * TC_TILE + row] = __uint_as_float(v[i]);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (stamp && (q4 & 1) == 0) P.timing[1 + 4 * op + q4] = clock64();
+          const int col0 = q4 * 64 + sub * 32;  // this thread's 32 output columns of the quarter
           if (op <= 6) {
-            // ---------- forward layer: bias + ReLU, record ReLU bits, split to fp16 hi (smem) / lo (TMEM) = next A operand
+            // ---------- forward layer: bias + ReLU, record ReLU bits, split to fp16 hi / lo = next A operand (in place)
             const float* __restrict__ bias = P.bias + op * 256;
-            uint32_t lo[32];
+            uint32_t v[32];
+            tmem_ld32(t_accb + col0, v);
+            uint32_t m = 0;
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int col0 = colbase + c * 32;
-              uint32_t v[32];
-              tmem_ld32(t_acc + c * 32, v);
-              uint32_t m = 0;
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+              float h0 = fmaxf(__uint_as_float(v[i]) + b.x, 0.f), h1 = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
+              float h2 = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), h3 = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
+              // ReLU bit = (h != 0): h >= +0, so bits(h) + 0x7fffffff carries into bit 31 iff h > 0; shifted in MSB-first
+              m = __funnelshift_l(__float_as_uint(h0) + 0x7fffffffu, m, 1);
+              m = __funnelshift_l(__float_as_uint(h1) + 0x7fffffffu, m, 1);
+              m = __funnelshift_l(__float_as_uint(h2) + 0x7fffffffu, m, 1);
+              m = __funnelshift_l(__float_as_uint(h3) + 0x7fffffffu, m, 1);
+              if (op == 6) {
+                const float4 wd = __ldg(reinterpret_cast<const float4*>(P.w_dens + col0 + i));
+                sigma_part = fmaf(wd.x, h0, sigma_part); sigma_part = fmaf(wd.y, h1, sigma_part);
+                sigma_part = fmaf(wd.z, h2, sigma_part); sigma_part = fmaf(wd.w, h3, sigma_part);
+              }
+              split_h2(h0, h1, hi[i / 2], lo[i / 2]);
+              split_h2(h2, h3, hi[i / 2 + 1], lo[i / 2 + 1]);
+            }
+            relu.put(op, q4, __brev(m));  // element i of the chunk -> bit i
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t off = (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16;
+              *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
+              *reinterpret_cast<uint4*>(smem + SM_A_LO + off) = make_uint4(lo[4 * t], lo[4 * t + 1], lo[4 * t + 2], lo[4 * t + 3]);
+            }
+          } else if (op == 7) {
+            // ---------- rgb head: relu(acc[0:128] + b) -> Linear(128,3) partials (model/spacenet.py:75-80) ...
+            if (q4 < 2) {
+              uint32_t vr[32];
+              tmem_ld32(t_accb + col0, vr);
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(P.b_rgb1 + col0 + i));
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + col0 + i));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 128 + col0 + i));
+                const float4 w2 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 256 + col0 + i));
+                const float r0 = fmaxf(__uint_as_float(vr[i]) + b.x, 0.f), r1 = fmaxf(__uint_as_float(vr[i + 1]) + b.y, 0.f);
+                const float r2 = fmaxf(__uint_as_float(vr[i + 2]) + b.z, 0.f), r3 = fmaxf(__uint_as_float(vr[i + 3]) + b.w, 0.f);
+                e0 = fmaf(w0.x, r0, e0); e0 = fmaf(w0.y, r1, e0); e0 = fmaf(w0.z, r2, e0); e0 = fmaf(w0.w, r3, e0);
+                e1 = fmaf(w1.x, r0, e1); e1 = fmaf(w1.y, r1, e1); e1 = fmaf(w1.z, r2, e1); e1 = fmaf(w1.w, r3, e1);
+                e2 = fmaf(w2.x, r0, e2); e2 = fmaf(w2.y, r1, e2); e2 = fmaf(w2.z, r2, e2); e2 = fmaf(w2.w, r3, e2);
+              }
+            }
+            // ... and the seed of the backward chain (the rgb head's MMAs have read the A operand): G6 = (w_dens / scale) * relu'(a6)
+            {
+              const uint32_t mb = relu.w[6][q4];
               uint32_t hi[16];
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
-                float h0 = fmaxf(__uint_as_float(v[i]) + b.x, 0.f), h1 = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
-                float h2 = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), h3 = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
-                // ReLU bit = (h != 0): h >= +0, so bits(h) + 0x7fffffff carries into bit 31 iff h > 0; shifted in MSB-first
-                m = __funnelshift_l(__float_as_uint(h0) + 0x7fffffffu, m, 1);
-                m = __funnelshift_l(__float_as_uint(h1) + 0x7fffffffu, m, 1);
-                m = __funnelshift_l(__float_as_uint(h2) + 0x7fffffffu, m, 1);
-                m = __funnelshift_l(__float_as_uint(h3) + 0x7fffffffu, m, 1);
-                if (op == 6) {
-                  const float4 wd = __ldg(reinterpret_cast<const float4*>(P.w_dens + col0 + i));
-                  sigma_part = fmaf(wd.x, h0, sigma_part); sigma_part = fmaf(wd.y, h1, sigma_part);
-                  sigma_part = fmaf(wd.z, h2, sigma_part); sigma_part = fmaf(wd.w, h3, sigma_part);
-                }
-                split_h2(h0, h1, hi[i / 2], lo[c * 16 + i / 2]);
-                split_h2(h2, h3, hi[i / 2 + 1], lo[c * 16 + i / 2 + 1]);
+                const float4 sd = __ldg(reinterpret_cast<const float4*>(P.seed + col0 + i));
+                float g0 = ((mb >> i) & 1u) ? sd.x : 0.f, g1 = ((mb >> (i + 1)) & 1u) ? sd.y : 0.f;
+                float g2 = ((mb >> (i + 2)) & 1u) ? sd.z : 0.f, g3 = ((mb >> (i + 3)) & 1u) ? sd.w : 0.f;
+                hi[i / 2] = pack_h2(g0, g1);
+                hi[i / 2 + 1] = pack_h2(g2, g3);
               }
-              relu.put(op, h * 2 + c, __brev(m));  // element i of the chunk -> bit i
 #pragma unroll
               for (int t = 0; t < 4; ++t)
-                *reinterpret_cast<uint4*>(smem + w_hi + (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16) =
+                *reinterpret_cast<uint4*>(smem + SM_A_HI + (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16) =
                     make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
-            }
-            tmem_st32(w_lo_tm + colbase / 2, lo);  // 64 columns of lo = 32 TMEM cells of this lane
-            if (op == 6 && h == 1 && !P.density_only) {
-              // every MMA that read buffer 1 (layer 6's A operand) has completed: seed the backward chain there,
-              // G6 = (w_dens / scale) * relu'(a6), for this thread's 64 columns of both halves
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                  const int col0 = hh * 128 + sub * 64 + c * 32;
-                  const uint32_t mb = relu.w[6][hh * 2 + c];
-                  uint32_t hi[16];
-#pragma unroll
-                  for (int i = 0; i < 32; i += 4) {
-                    const float4 sd = __ldg(reinterpret_cast<const float4*>(P.seed + col0 + i));
-                    float g0 = ((mb >> i) & 1u) ? sd.x : 0.f, g1 = ((mb >> (i + 1)) & 1u) ? sd.y : 0.f;
-                    float g2 = ((mb >> (i + 2)) & 1u) ? sd.z : 0.f, g3 = ((mb >> (i + 3)) & 1u) ? sd.w : 0.f;
-                    hi[i / 2] = pack_h2(g0, g1);
-                    hi[i / 2 + 1] = pack_h2(g2, g3);
-                  }
-#pragma unroll
-                  for (int t = 0; t < 4; ++t)
-                    *reinterpret_cast<uint4*>(smem + SM_A1 + (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16) =
-                        make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
-                }
-            }
-            tmem_wait_st();
-          } else if (op == 7) {
-            // ---------- rgb head (accumulator half 0 only): relu(acc + b) -> Linear(128,3) partials (model/spacenet.py:75-80)
-            if (h == 0) {
-#pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                const int col0 = sub * 64 + c * 32;
-                uint32_t v[32];
-                tmem_ld32(t_acc + c * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(P.b_rgb1 + col0 + i));
-                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + col0 + i));
-                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 128 + col0 + i));
-                  const float4 w2 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 256 + col0 + i));
-                  const float r0 = fmaxf(__uint_as_float(v[i]) + b.x, 0.f), r1 = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
-                  const float r2 = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), r3 = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
-                  e0 = fmaf(w0.x, r0, e0); e0 = fmaf(w0.y, r1, e0); e0 = fmaf(w0.z, r2, e0); e0 = fmaf(w0.w, r3, e0);
-                  e1 = fmaf(w1.x, r0, e1); e1 = fmaf(w1.y, r1, e1); e1 = fmaf(w1.z, r2, e1); e1 = fmaf(w1.w, r3, e1);
-                  e2 = fmaf(w2.x, r0, e2); e2 = fmaf(w2.y, r1, e2); e2 = fmaf(w2.z, r2, e2); e2 = fmaf(w2.w, r3, e2);
-                }
-              }
             }
           } else if (op <= 13) {
             // ---------- backward layer: G_{l-1} = (G_l W_l) * relu'(a_{l-1}), fp16 single pass, hi only
-            const int mask_layer = 13 - op;  // op 8 -> layer 5 ... op 13 -> layer 0
+            const uint32_t mb = relu.get(13 - op, q4);  // op 8 -> layer 5 ... op 13 -> layer 0
+            uint32_t v[32];
+            tmem_ld32(t_accb + col0, v);
+            uint32_t hi[16];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int col0 = colbase + c * 32;
-              const uint32_t mb = relu.get(mask_layer, h * 2 + c);
-              uint32_t v[32];
-              tmem_ld32(t_acc + c * 32, v);
-              uint32_t hi[16];
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                float g0 = ((mb >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
-                float g1 = ((mb >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
-                hi[i / 2] = pack_h2(g0, g1);
-              }
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                *reinterpret_cast<uint4*>(smem + w_hi + (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16) =
-                    make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
+            for (int i = 0; i < 32; i += 2) {
+              float g0 = ((mb >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+              float g1 = ((mb >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
+              hi[i / 2] = pack_h2(g0, g1);
             }
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              *reinterpret_cast<uint4*>(smem + SM_A_HI + (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16) =
+                  make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
           }
-          if (stamp) P.timing[2 + 4 * op + 2 * h] = clock64();
+          if (stamp && (q4 & 1) == 1) P.timing[1 + 4 * op + q4] = clock64();
           if (op != n_ops - 1) {
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_a + 8 * h);
+            mbar_arrive(bar_a + 8 * q4);
           }
         }
-        acc_phase ^= 1;
       }
       // ---------- tile outputs: both accumulator halves of the last op are complete
       {
         float gx[3] = {0.f, 0.f, 0.f};
         if (!P.density_only) {
           // d sigma / d PE (64 columns) -> chain rule through the encoding; this thread owns octaves 5*sub .. 5*sub+4
+          // layer-0 part: accumulator 0 (op 14), columns 0..63; layer-4 part: the stash written at op 10
           uint32_t g0[32], g1[32];
-          tmem_ld32(t_lane + TM_GPE, g0);
-          tmem_ld32(t_lane + TM_GPE + 32, g1);
-          auto gpe = [&](int c) -> float { return __uint_as_float(c < 32 ? g0[c] : g1[c - 32]); };
+          tmem_ld32(t_lane, g0);
+          tmem_ld32(t_lane + 32, g1);
+          auto gpe = [&](int c) -> float { return __uint_as_float(c < 32 ? g0[c] : g1[c - 32]) + stash[c * TC_TILE + row]; };
           // sin/cos are still in the PE region (written by this very thread)
           auto pe_val = [&](int col) -> float {
             const uint32_t off = (uint32_t)(col >> 3) * A_CHUNK + row * 16 + (col & 7) * 2;
@@ -633,7 +597,7 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
           tc_fence_before();
         }
         if (stamp) P.timing[62] = clock64();
-        epi_bar();  // nobody overwrites the PE region / TM_GPE / TM_XCH of this tile before everyone is done with them
+        epi_bar();  // nobody overwrites the PE region / stash / TM_XCH of this tile before everyone is done with them
       }
     }
   }
@@ -664,20 +628,21 @@ struct TcWeights {
     d_f32 = nullptr;
   }
 
-  // One N-half of an op: B[n][k] (rows x K) packed as slabs of `ksteps` k-steps:
+  // B[n][k] (rows x K) packed as slabs of `ksteps` k-steps:
   //   [hi: (2*ksteps chunks) x rows x 8 halves][lo: same]   -- exactly the image the UMMA descriptors address
-  static void pack_half(std::vector<__half>& blob, TcOp& op, int h, int rows, int n_mma, int K, int ksteps, bool with_lo,
-                        const std::vector<float>& B) {
+  static void pack_op(std::vector<__half>& blob, TcOp& op, int kind, int a_src, int rows, int K, int ksteps, bool with_lo,
+                      const std::vector<float>& B) {
     const int n_slabs = K / (16 * ksteps);
     const size_t part = (size_t)ksteps * 2 * rows * 8;  // halves per hi (or lo) part
     const size_t slab = part * (with_lo ? 2 : 1);
     while (blob.size() % 64) blob.push_back(__float2half_rn(0.f));  // 128-byte aligned slabs
-    op.src_off[h] = (uint32_t)(blob.size() * sizeof(__half));
-    op.slab_bytes[h] = (uint32_t)(slab * sizeof(__half));
-    op.n_slabs[h] = (uint16_t)n_slabs;
-    op.ksteps[h] = (uint16_t)ksteps;
-    op.rows[h] = (uint16_t)rows;
-    op.n_mma[h] = (uint16_t)n_mma;
+    op.src_off = (uint32_t)(blob.size() * sizeof(__half));
+    op.slab_bytes = (uint32_t)(slab * sizeof(__half));
+    op.n_slabs = (uint16_t)n_slabs;
+    op.ksteps = (uint16_t)ksteps;
+    op.kind = (uint8_t)kind;
+    op.a_src = (uint8_t)a_src;
+    op.pad[0] = op.pad[1] = 0;
     const size_t base = blob.size();
     blob.resize(base + slab * n_slabs);
     for (int n = 0; n < rows; ++n)
@@ -690,9 +655,6 @@ struct TcWeights {
         if (with_lo) blob[off + part] = __float2half_rn(w - __half2float(hh));
       }
   }
-  static void no_half(TcOp& op, int h) {
-    op.src_off[h] = 0; op.slab_bytes[h] = 0; op.n_slabs[h] = 0; op.ksteps[h] = 1; op.rows[h] = 128; op.n_mma[h] = 128;
-  }
 
   int stage(const std::vector<float>& w0, const std::vector<float>& w1, const std::vector<float>& w2, const std::vector<float>& w3,
             const std::vector<float>& w4, const std::vector<float>& w5, const std::vector<float>& w6, const std::vector<float>& b1,
@@ -703,60 +665,42 @@ struct TcWeights {
     std::vector<__half> blob;
     std::vector<float> B;
     int oi = 0;
-    auto set = [&](TcOp& o, int passes, int a_src, int extra_h1, int to_gpe) {
-      o.passes = (uint8_t)passes; o.a_src = (uint8_t)a_src; o.extra_h1 = (uint8_t)extra_h1; o.main_to_gpe = (uint8_t)to_gpe;
-    };
-    // forward layers 0..6: two N-halves of 128 output columns, 3-pass (hi + lo)
+    // forward layers 0..6: N = 256, 3-pass (hi + lo), one k-step per 16 KB slab
     for (int l = 0; l < 7; ++l) {
       const int in_dim = l == 0 ? 87 : (l == 4 ? 319 : 256);
       const int K = l == 0 ? 64 : (l == 4 ? 320 : 256);
-      for (int h = 0; h < 2; ++h) {
-        B.assign((size_t)128 * K, 0.f);
-        for (int n = 0; n < 128; ++n)
-          for (int k = 0; k < (l == 0 ? 63 : in_dim); ++k)
-            B[(size_t)n * K + k] = (*W[l])[(size_t)(h * 128 + n) * in_dim + (l == 0 ? 8 + k : k)];
-        pack_half(blob, ops[oi], h, 128, 128, K, 2, true, B);
-      }
-      set(ops[oi], 3, l == 0 ? A_PE : (l == 4 ? A_ACT_PE : A_ACT), 0, 0);
-      ++oi;
+      B.assign((size_t)256 * K, 0.f);
+      for (int n = 0; n < 256; ++n)
+        for (int k = 0; k < (l == 0 ? 63 : in_dim); ++k) B[(size_t)n * K + k] = (*W[l])[(size_t)n * in_dim + (l == 0 ? 8 + k : k)];
+      pack_op(blob, ops[oi++], K_FWD, l == 0 ? A_PE : (l == 4 ? A_ACT_PE : A_ACT), 256, K, 1, true, B);
     }
-    // rgb head first layer: 256 -> 128, accumulator half 0 only
+    // rgb head first layer: 256 -> 128
     B.assign((size_t)128 * 256, 0.f);
     for (int n = 0; n < 128; ++n)
       for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = wr1[(size_t)n * 256 + k];
-    pack_half(blob, ops[oi], 0, 128, 128, 256, 2, true, B);
-    no_half(ops[oi], 1);
-    set(ops[oi], 3, A_ACT, 0, 0);
-    ++oi;
+    pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 256, 2, true, B);
     // backward through layers 6..1: B[n][k] = W[k][n] (n = input index, k = output index), 1-pass
     for (int l = 6; l >= 1; --l) {
-      const int in_dim = l == 4 ? 319 : 256;
-      for (int h = 0; h < 2; ++h) {
-        const bool extra = (l == 4 && h == 1);
-        const int rows = extra ? 192 : 128;
-        B.assign((size_t)rows * 256, 0.f);
-        for (int n = 0; n < rows; ++n) {
-          const int src_n = n < 128 ? h * 128 + n : 256 + (n - 128);  // extra rows: the 63 PE input columns of layer 4 (+1 pad)
-          if (src_n >= in_dim) continue;
-          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = (*W[l])[(size_t)k * in_dim + src_n];
-        }
-        pack_half(blob, ops[oi], h, rows, 128, 256, extra ? 2 : 4, false, B);
+      if (l == 4) {  // 256 hidden inputs + 63 PE inputs (+1 pad): rows 256..319 feed the extra N = 64 MMA
+        B.assign((size_t)320 * 256, 0.f);
+        for (int n = 0; n < 319; ++n)
+          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = w4[(size_t)k * 319 + n];
+        pack_op(blob, ops[oi++], K_BW4, A_ACT, 320, 256, 1, false, B);
+      } else {
+        B.assign((size_t)256 * 256, 0.f);
+        for (int n = 0; n < 256; ++n)
+          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = (*W[l])[(size_t)k * 256 + n];
+        pack_op(blob, ops[oi++], K_BWD, A_ACT, 256, 256, 2, false, B);
       }
-      set(ops[oi], 1, A_ACT, l == 4 ? 1 : 0, 0);
-      ++oi;
     }
-    // layer 0 backward, PE columns only (N = 64), accumulated onto the layer-4 PE gradient in TM_GPE
+    // layer 0 backward, PE columns only (N = 64); added to the stashed layer-4 PE gradient in the tile's last stage
     B.assign((size_t)64 * 256, 0.f);
     for (int n = 0; n < 63; ++n)
       for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = w0[(size_t)k * 87 + 8 + n];
-    pack_half(blob, ops[oi], 0, 64, 64, 256, 8, false, B);
-    no_half(ops[oi], 1);
-    set(ops[oi], 1, A_ACT, 0, 1);
-    ++oi;
+    pack_op(blob, ops[oi++], K_BW0, A_ACT, 64, 256, 8, false, B);
     if (oi != TC_NUM_OPS) return (int)cudaErrorUnknown;
     for (int i = 0; i < TC_NUM_OPS; ++i)
-      for (int h = 0; h < 2; ++h)
-        if (ops[i].slab_bytes[h] > TC_STAGE_BYTES || (ops[i].slab_bytes[h] & 31) || (ops[i].src_off[h] & 15)) return (int)cudaErrorInvalidValue;
+      if (ops[i].slab_bytes > TC_STAGE_BYTES || (ops[i].slab_bytes & 31) || (ops[i].src_off & 15)) return (int)cudaErrorInvalidValue;
     release();
     cudaError_t e = cudaMalloc(&d_pack, blob.size() * sizeof(__half));
     if (e != cudaSuccess) return (int)e;

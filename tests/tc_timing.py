@@ -16,12 +16,12 @@ buf = (ctypes.c_longlong * 128)()
 r.ctx.check(r.ctx.L.dsnerf_debug_tc_timing(r.ctx.h, buf))
 t = np.array(buf[:128], dtype=np.int64)
 names = ["L0","L1","L2","L3","L4","L5","L6","rgb1","bW6","bW5","bW4","bW3","bW2","bW1","bW0"]
-print("op      wait0->start0  epi0   gap  epi1   (cycles; start = accumulator half ready)")
+print("op     accwait  q0+q1  q2+q3 (cycles)")
 prev = t[0]
 for op in range(15):
-    s0, e0, s1, e1 = t[1 + 4 * op], t[2 + 4 * op], t[3 + 4 * op], t[4 + 4 * op]
-    print(f"{names[op]:6s} {s0 - prev:8d} {e0 - s0:8d} {s1 - e0:8d} {e1 - s1:8d}")
-    prev = e1
+    a0, a1, a2, a3 = t[1 + 4 * op], t[2 + 4 * op], t[3 + 4 * op], t[4 + 4 * op]
+    print(f"{names[op]:6s} {a0 - prev:8d} {a1 - a0:8d} {a3 - a2:8d}")
+    prev = a3
 print("tile total", t[62] - t[0])
 print("MMA thread per op: wait_full  wait_a  total_issue_loop")
 for op in range(15):

@@ -41,8 +41,8 @@ struct DevBuf {
 struct MeshGrid {
   Grid g{};
   int ncell = 0;
-  DevBuf cent, tri_n, counts, start, cursor, sorted, cdist, cidx, rowmask, dc0, idx0;
-  void release() { cent.release(); tri_n.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); cidx.release(); rowmask.release(); dc0.release(); idx0.release(); }
+  DevBuf cent, tri_n, counts, start, cursor, sorted, cdist, cidx, rowmask, dc0, idx0, dc1, idx1;
+  void release() { cent.release(); tri_n.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); cidx.release(); rowmask.release(); dc0.release(); idx0.release(); dc1.release(); idx1.release(); }
 };
 
 // state_dict order
@@ -212,6 +212,8 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CK(mg.cidx.ensure(sizeof(int) * ntab));
   CK(mg.dc0.ensure(sizeof(float) * n0));
   CK(mg.idx0.ensure(sizeof(int) * n0));
+  CK(mg.dc1.ensure(sizeof(float) * mg.ncell));
+  CK(mg.idx1.ensure(sizeof(int) * mg.ncell));
   g.cell_start = mg.start.as<int>();
   g.sorted = mg.sorted.as<float4>();
   g.row_mask = mg.rowmask.as<unsigned long long>();
@@ -229,12 +231,18 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CKL("grid_scan");
   grid_fill_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.cursor.as<int>(), mg.sorted.as<float4>());
   CKL("grid_fill");
-  table_coarse_kernel<<<(n0 + 255) / 256, 256, 0, st>>>(g.ox, g.oy, g.oz, cell0, n0x, n0y, n0z, mg.cent.as<float>(), F, mg.dc0.as<float>(),
-                                                        mg.idx0.as<int>());
+  table_coarse_kernel<<<(n0 + 255) / 256, 256, 0, st>>>(g.ox, g.oy, g.oz, cell0, n0x, n0y, n0z, mg.cent.as<float>(), mg.tri_n.as<float4>(), F,
+                                                        classify, r_cap, mg.dc0.as<float>(), mg.idx0.as<int>());
   CKL("table_coarse");
-  table_fine_kernel<<<(ntab + 127) / 128, 128, 0, st>>>(g, mg.tri_n.as<float4>(), cell0, n0x, n0y, n0z, mg.dc0.as<float>(), mg.idx0.as<int>(),
-                                                        classify, mg.cdist.as<float>(), mg.cidx.as<int>());
-  CKL("table_fine");
+  // level 1 (enumeration-cell resolution) seeded by level 0, then the lookup table (level 2) seeded by level 1
+  TableLevel l1{cell, cell * 0.8660254f * 1.0001f, g.nx, g.ny, g.nz};
+  table_level_kernel<<<(mg.ncell + TABLE_THREADS - 1) / TABLE_THREADS, TABLE_THREADS, 0, st>>>(g, l1, mg.tri_n.as<float4>(), n0x, n0y, n0z, mg.dc0.as<float>(), mg.idx0.as<int>(),
+                                                           classify, mg.dc1.as<float>(), mg.idx1.as<int>());
+  CKL("table_level1");
+  TableLevel l2{0.5f * cell, g.thalf_diag, g.tnx, g.tny, g.tnz};
+  table_level_kernel<<<(ntab + TABLE_THREADS - 1) / TABLE_THREADS, TABLE_THREADS, 0, st>>>(g, l2, mg.tri_n.as<float4>(), g.nx, g.ny, g.nz, mg.dc1.as<float>(), mg.idx1.as<int>(),
+                                                       classify, mg.cdist.as<float>(), mg.cidx.as<int>());
+  CKL("table_level2");
   return 0;
 }
 

@@ -194,9 +194,10 @@ __device__ __forceinline__ void scan_ball(const Grid& g, float px, float py, flo
 // ---- lookup-table construction ---------------------------------------------------------------
 // Level 0: brute force (tiled through shared memory) on a lattice 4x coarser than the table: nearest centroid of
 // every coarse cell centre.  Only seeds level 1.
-__global__ void table_coarse_kernel(float ox, float oy, float oz, float cell0, int n0x, int n0y, int n0z, const float* __restrict__ cent, int F,
-                                    float* __restrict__ dc0, int* __restrict__ idx0) {
-  __shared__ float sx[1024], sy[1024], sz[1024];
+__global__ void table_coarse_kernel(float ox, float oy, float oz, float cell0, int n0x, int n0y, int n0z, const float* __restrict__ cent,
+                                    const float4* __restrict__ tri_n, int F, int classify, float r_cap, float* __restrict__ dc0,
+                                    int* __restrict__ idx0) {
+  __shared__ float sx[1024], sy[1024], sz[1024], snx[1024], sny[1024], snz[1024];
   int n = n0x * n0y * n0z;
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   int cx = c % n0x, cy = (c / n0x) % n0y, cz = c / (n0x * n0y);
@@ -220,27 +221,91 @@ __global__ void table_coarse_kernel(float ox, float oy, float oz, float cell0, i
       if (d2 < best) { best = d2; besti = base + i; }
     }
   }
-  if (c < n) { dc0[c] = sqrtf(best); idx0[c] = besti; }
+  float dc = sqrtf(best) * 1.00001f + 1e-7f;
+  // Same transparency proof as for the table cells, one level up: a certified coarse cell certifies every table cell inside
+  // it, which spares the far band (the most expensive scans) in table_fine_kernel.
+  const float hd0 = cell0 * 0.8660254f * 1.001f;
+  const float h_thr = 0.1f + hd0 + 1e-4f;
+  bool undecided = classify && (c < n) && (dc > h_thr) && (dc - hd0 <= r_cap);
+  bool search = (c < n) && (!classify || dc <= h_thr);
+  if (__syncthreads_or(undecided)) {
+    float thr = dc + 2.0f * hd0 + 1e-5f;
+    float thr2 = undecided ? thr * thr : -1.0f;
+    for (int base = 0; base < F; base += 1024) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        int f = base + i;
+        bool ok = f < F;
+        float4 nq = ok ? tri_n[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        sx[i] = ok ? cent[3 * f] : 1.0e18f;
+        sy[i] = ok ? cent[3 * f + 1] : 1.0e18f;
+        sz[i] = ok ? cent[3 * f + 2] : 1.0e18f;
+        snx[i] = nq.x; sny[i] = nq.y; snz[i] = nq.z;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int i = 0; i < 1024; ++i) {
+        float dx = px - sx[i], dy = py - sy[i], dz = pz - sz[i];
+        if (dx * dx + dy * dy + dz * dz <= thr2) {
+          float h = dx * snx[i] + dy * sny[i] + dz * snz[i];
+          if (!(fabsf(h) > h_thr)) search = true;
+        }
+      }
+    }
+  }
+  // +huge marks a far or certified (provably transparent) coarse cell
+  if (c < n) { dc0[c] = (search && dc - hd0 <= r_cap) ? dc : 3.0e30f; idx0[c] = besti; }
 }
 
-// Level 1: the table itself.  Per table cell: distance dc from the centre to its nearest centroid (found through the
-// enumeration grid, seeded by level 0) and that centroid's index; +huge when every point of the cell is PROVABLY
-// transparent.  Proof: for p in the cell, its nearest centroid c* satisfies |centre - c*| <= dc + 2*half_diag
-// (candidate set), the signed plane distance h is 1-Lipschitz, so |h*(centre)| > 0.1 + half_diag for every
-// candidate implies |h*(p)| > 0.1 = max_dist of get_transparent_mask (utils/render_utils.py:103).
-__global__ void table_fine_kernel(Grid g, const float4* __restrict__ tri_n, float cell0, int n0x, int n0y, int n0z, const float* __restrict__ dc0,
-                                  const int* __restrict__ idx0, int classify, float* __restrict__ out, int* __restrict__ out_idx) {
-  int n = g.tnx * g.tny * g.tnz;
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  int cx = c % g.tnx, cy = (c / g.tnx) % g.tny, cz = c / (g.tnx * g.tny);
-  const float tcell = 1.0f / g.tinv;
-  float px = g.ox + (cx + 0.5f) * tcell, py = g.oy + (cy + 0.5f) * tcell, pz = g.oz + (cz + 0.5f) * tcell;
-  int c0 = (min(cz / 4, n0z - 1) * n0y + min(cy / 4, n0y - 1)) * n0x + min(cx / 4, n0x - 1);
-  float d0 = dc0[c0];
-  int seed = idx0[c0];
-  const float hd0 = cell0 * 0.8660254f * 1.001f;
-  if (d0 - hd0 - g.thalf_diag > g.r_cap) { out[c] = 3.0e30f; out_idx[c] = seed; return; }
+// Finer levels, each seeded by its parent (cells twice as large): per cell the distance dc from the centre to its
+// nearest centroid (found through the enumeration grid) and that centroid's index; +huge when every point of the cell is
+// farther than r_cap from all centroids or PROVABLY transparent.  Proof: for p in the cell, its nearest centroid c*
+// satisfies |centre - c*| <= dc + 2*half_diag (candidate set), the signed plane distance h is 1-Lipschitz, so
+// |h*(centre)| > 0.1 + half_diag for every candidate implies |h*(p)| > 0.1 = max_dist of get_transparent_mask
+// (utils/render_utils.py:103).  A far/certified parent settles all its children.  The last level is the lookup table.
+struct TableLevel {
+  float cell, half_diag;
+  int nx, ny, nz;
+};
+
+constexpr int TABLE_THREADS = 256;
+
+__global__ void __launch_bounds__(TABLE_THREADS) table_level_kernel(Grid g, TableLevel lv, const float4* __restrict__ tri_n, int pnx, int pny, int pnz,
+                                                                    const float* __restrict__ p_dc, const int* __restrict__ p_idx, int classify,
+                                                                    float* __restrict__ out, int* __restrict__ out_idx) {
+  // Most cells are settled by their parent (far / certified); the others are compacted into a per-block queue so that the
+  // scans below run with full warps.
+  __shared__ int queue[TABLE_THREADS];
+  __shared__ int qn;
+  const int n = lv.nx * lv.ny * lv.nz;
+  const int c0 = blockIdx.x * TABLE_THREADS;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) qn = 0;
+  __syncthreads();
+  {
+    int c = c0 + threadIdx.x;
+    bool need = false;
+    if (c < n) {
+      int cx = c % lv.nx, cy = (c / lv.nx) % lv.ny, cz = c / (lv.nx * lv.ny);
+      int pc = (min(cz / 2, pnz - 1) * pny + min(cy / 2, pny - 1)) * pnx + min(cx / 2, pnx - 1);
+      if (p_dc[pc] > 1.0e29f) { out[c] = 3.0e30f; out_idx[c] = p_idx[pc]; }
+      else need = true;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m) {
+      int leader = __ffs(m) - 1, base = 0;
+      if (lane == leader) base = atomicAdd(&qn, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) queue[base + __popc(m & ((1u << lane) - 1))] = threadIdx.x;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= qn) return;
+  const int c = c0 + queue[threadIdx.x];
+  int cx = c % lv.nx, cy = (c / lv.nx) % lv.ny, cz = c / (lv.nx * lv.ny);
+  float px = g.ox + (cx + 0.5f) * lv.cell, py = g.oy + (cy + 0.5f) * lv.cell, pz = g.oz + (cz + 0.5f) * lv.cell;
+  int pc = (min(cz / 2, pnz - 1) * pny + min(cy / 2, pny - 1)) * pnx + min(cx / 2, pnx - 1);
+  int seed = p_idx[pc];
   float sx = px - g.cent[3 * seed], sy = py - g.cent[3 * seed + 1], sz = pz - g.cent[3 * seed + 2];
   float best = sx * sx + sy * sy + sz * sz;
   int besti = seed;
@@ -252,18 +317,19 @@ __global__ void table_fine_kernel(Grid g, const float4* __restrict__ tri_n, floa
   });
   float dc = sqrtf(best) * 1.00001f + 1e-7f;
   out_idx[c] = besti;
-  if (dc - g.thalf_diag > g.r_cap) { out[c] = 3.0e30f; return; }
-  const float h_thr = 0.1f + g.thalf_diag * 1.001f + 1e-4f;
+  if (dc - lv.half_diag > g.r_cap) { out[c] = 3.0e30f; return; }
+  const float h_thr = 0.1f + lv.half_diag * 1.001f + 1e-4f;
   bool search = !classify || dc <= h_thr;  // the nearest centroid itself is a candidate with |h| <= dc
   if (!search) {
-    float thr = dc + 2.0f * g.thalf_diag * 1.001f + 1e-5f;
+    float thr = dc + 2.0f * lv.half_diag * 1.001f + 1e-5f;
     float thr2 = thr * thr;
-    scan_ball(g, px, py, pz, thr * 1.0001f, thr2, [&](float4 q) {
+    float live2 = thr2;  // set negative to cut the scan short once the cell is known to need searching
+    scan_ball(g, px, py, pz, thr * 1.0001f, live2, [&](float4 q) {
       float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
       if (dx * dx + dy * dy + dz * dz <= thr2) {
         float4 nq = __ldg(tri_n + __float_as_int(q.w));
         float h = dx * nq.x + dy * nq.y + dz * nq.z;
-        if (!(fabsf(h) > h_thr)) search = true;  // NaN normal (degenerate triangle) keeps the cell searchable
+        if (!(fabsf(h) > h_thr)) { search = true; live2 = -1.0f; }  // NaN normal (degenerate triangle) keeps the cell searchable
       }
     });
   }
@@ -467,34 +533,38 @@ __device__ __forceinline__ void sample_position(const WarpArgs& a, int64_t s, fl
 __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, Grid g) {
   __shared__ int queue[WARP_THREADS];
   __shared__ int qn;
+  __shared__ int bin_count[8], bin_start[8];
   __shared__ unsigned char flag[WARP_THREADS];
   const int64_t P = a.R * a.N;
   const int64_t s0 = (int64_t)blockIdx.x * WARP_THREADS;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) qn = 0;
+  if (threadIdx.x < 8) bin_count[threadIdx.x] = 0;
   flag[threadIdx.x] = 0;
   __syncthreads();
+  // phase 1: place the sample, look its table cell up.  Samples that need the exact search are queued, bucketed by the
+  // table's distance (= expected search radius) so that the lanes of a warp in phase 2 do similar amounts of work.
+  int my_bin = -1;
   {
     const int64_t s = s0 + threadIdx.x;
-    bool need = false;
     if (s < P) {
       float px, py, pz;
       sample_position(a, s, px, py, pz);
       float fx = (px - g.ox) * g.tinv, fy = (py - g.oy) * g.tinv, fz = (pz - g.oz) * g.tinv;
       if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.tnx && fy < (float)g.tny && fz < (float)g.tnz) {
         float dc = __ldg(g.center_dist + ((int)fz * g.tny + (int)fy) * g.tnx + (int)fx);
-        need = !(dc - g.thalf_diag > g.r_cap);
+        if (!(dc - g.thalf_diag > g.r_cap)) my_bin = min(7, (int)(dc * 40.0f));  // 2.5 cm classes
       }
     }
-    unsigned m = __ballot_sync(0xffffffffu, need);
-    int base = 0;
-    if (m) {
-      int leader = __ffs(m) - 1;
-      if (lane == leader) base = atomicAdd(&qn, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (need) queue[base + __popc(m & ((1u << lane) - 1))] = threadIdx.x;
-    }
+    if (my_bin >= 0) atomicAdd(&bin_count[my_bin], 1);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 7; b >= 0; --b) { bin_start[b] = acc; acc += bin_count[b]; }  // big radii first
+    qn = acc;
+  }
+  __syncthreads();
+  if (my_bin >= 0) queue[atomicAdd(&bin_start[my_bin], 1)] = threadIdx.x;
   __syncthreads();
   {
     const int n = qn;

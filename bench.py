@@ -247,7 +247,7 @@ def main():
     launches_per_step = st["kernel_launches"] + 5  # + the five grid-build kernels of dsnerf_set_frame
     evaluated = st["evaluated_samples"]
 
-    ctx.profile(1)
+    ctx.profile(1 | int(os.environ.get('DSNERF_DEBUG_PROFILE_BITS', '0')))
     ctx.profile_read(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()

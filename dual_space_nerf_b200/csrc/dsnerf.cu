@@ -329,7 +329,7 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
       if (ctx->tc_timing.ensure(sizeof(long long) * 128) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "timing buffer");
       timing = ctx->tc_timing.as<long long>();
     }
-    if (int e = tc_launch(ctx->tw, timing, ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
+    if (int e = tc_launch(ctx->tw, timing, (ctx->profile >> 3) & 3, ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
                           ctx->mlp_g.as<float4>(), density_only, ctx->sm_count, st))
       return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc: ") + cudaGetErrorString((cudaError_t)e));
   }
@@ -825,7 +825,7 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
 
 int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
   if (!ctx) return DSNERF_ERR_INVALID;
-  ctx->profile = enable & 7;
+  ctx->profile = enable & 31;
   return 0;
 }
 

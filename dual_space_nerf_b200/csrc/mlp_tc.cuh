@@ -12,22 +12,33 @@
 //     recorded in the forward pass; the seed is w_dens / max|w_dens| so every gradient stays inside
 //     fp16 range (the normal is scale invariant).
 //
-// Pipeline (one CTA = one SM, 10 warps)
+// Pipeline (CTA pair = two SMs of one TPC, cta_group::2; 18 warps per CTA)
 //   * measured on B200 (profiles/): an MMA whose A operand comes from shared memory occupies the tensor pipe for
 //     >= 128 cycles whatever N is (the 128 x 16 A tile is read at 32 B/cycle), so every MMA here is N = 256
-//     (128 cycles = the ideal rate); an earlier version with two N = 128 halves ran 1.7-2x slower per layer;
+//     (128 cycles = the ideal rate);
+//   * with cta_group::1 the kernel was SHARED-MEMORY-BANDWIDTH bound: per MMA the tensor core reads A (4 KB) and B
+//     (8 KB) = 96 B/clk of the SM's 128 B/clk, and the weight stream (TMA writes) plus the epilogue's operand stores
+//     add ~60 B/clk; MMAs issued every ~154 cycles.  cta_group::2 pairs two SMs on one M = 256 tile (each CTA owns
+//     128 points and its own accumulators): every CTA holds and streams only HALF of each weight slab (its N/2 rows
+//     of B), the tensor cores fetch the other half from the peer's shared memory, so operand reads drop to 64 B/clk,
+//     the L2 -> SM weight traffic halves and the ring doubles its depth (8 x 8 KB) in the same footprint;
+//   * the leader CTA's MMA warp issues for both; the peer's warp relays "my half landed" to the leader; epilogue warps
+//     of both CTAs arrive (remotely for the peer) on the leader's hand-off barriers; tcgen05.commit multicasts;
 //   * the A operand (fp16 hi + lo, K-major no-swizzle core matrices, 128 KB) is rewritten in place by the
-//     epilogue; two 256-column TMEM accumulators alternate between layers, so the epilogue of layer l (8 warps:
-//     tcgen05.ld -> bias/ReLU/mask bits/hi-lo split -> st.shared) overlaps the MMAs of layer l+1: the epilogue
-//     publishes its first 128 columns early and the next layer's first 8 k-steps start on them;
+//     epilogue; two 256-column TMEM accumulators alternate between layers, so the epilogue of layer l overlaps
+//     the MMAs of layer l+1: the epilogue publishes its output in four 64-column quarters and the next layer's
+//     k-steps start on each quarter as it lands;
+//   * 16 epilogue warps (4 per TMEM lane quarter, 16 columns of every 64-column quarter each): the epilogue is
+//     latency bound (tcgen05.ld, fences), so it is spread over 4 warps per scheduler, the next quarter's
+//     tcgen05.ld is in flight while the current one is processed, the arithmetic is packed (fp32x2 add/fma,
+//     half2 compare for the ReLU bits) and one lane per warp arrives on the hand-off barriers;
+//   * layer 4's positional-encoding k-steps do not depend on layer 3's epilogue and are issued first;
 //   * weights are pre-packed on the host into the exact shared-memory image, in consumption order, and streamed
-//     by one elected lane with cp.async.bulk (TMA engine) into a 4x16 KB mbarrier ring (cluster-ready: with
-//     TC_CLUSTER = 2 each CTA fetches half of every slab and multicasts it; the ring is latency- not
-//     bandwidth-bound on B200, so the default is 1);
+//     by one elected lane with cp.async.bulk (TMA engine) into a 4x16 KB mbarrier ring;
 //   * one elected lane of a converged warp issues all tcgen05.mma (slab-templated: descriptors are
 //     "base + immediate"); tcgen05.commit releases ring slots and publishes finished accumulators;
-//   * ReLU bits live in registers (28 words per thread), d sigma / d PE of layer 4 is parked in the idle A-lo
-//     region during the backward chain, cross-thread partial sums go through 8 TMEM cells per row.
+//   * ReLU bits live in registers (14 words per thread), d sigma / d PE of layer 4 is parked in the idle A-lo
+//     region during the backward chain, cross-thread partial sums go through shared memory once per tile.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -38,37 +49,39 @@
 namespace dsn {
 
 constexpr int TC_TILE = 128;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_SUBS = TC_EPI_WARPS / 4;          // column sub-blocks per 64-column quarter
+constexpr int TC_CPT = 64 / TC_SUBS;               // columns per thread per quarter (16)
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_STAGES = 4;
-constexpr int TC_CLUSTER = 1;
-constexpr uint32_t TC_STAGE_BYTES = 16384;
+constexpr uint32_t TC_STAGE_BYTES = 16384;  // per CTA: half of a weight slab
 // shared memory map (bytes)
 constexpr uint32_t SM_A_HI = 0;          // A operand, fp16 hi: [K/8 = 32 chunks][128 rows][8]
-constexpr uint32_t SM_A_LO = 65536;      // A operand, fp16 lo (forward only); backward: fp32 stash of layer 4's d sigma / d PE
+constexpr uint32_t SM_A_LO = 65536;      // A operand, fp16 lo (forward only); backward: fp32 stash of layer 4's d sigma / d PE + exchange
 constexpr uint32_t SM_PE_HI = 131072;    // positional encoding hi, 8 chunks
 constexpr uint32_t SM_PE_LO = 147456;    // positional encoding lo
 constexpr uint32_t SM_RING = 163840;
 constexpr uint32_t SM_BAR = SM_RING + TC_STAGES * TC_STAGE_BYTES;  // 229376
-constexpr uint32_t TC_SMEM = SM_BAR + 128;
+constexpr uint32_t TC_SMEM = SM_BAR + 256;
 constexpr uint32_t A_CHUNK = TC_TILE * 16;  // bytes between consecutive 8-wide K chunks of an A operand
+constexpr uint32_t SM_STASH = SM_A_LO;           // [64 PE columns][128 rows] fp32 (32 KB), backward chain only
+constexpr uint32_t SM_XCH = SM_A_LO + 32768;     // [3 subs][8][128 rows] fp32 partial sums at the end of a tile
 // tensor memory map (32-bit columns)
 constexpr uint32_t TM_ACC = 256;    // accumulator b (= op & 1) starts at column b * TM_ACC
-constexpr uint32_t TM_XCH = 256;    // 8 columns of cross-thread partial sums at the very end of a tile (accumulator 1 is idle then)
 constexpr uint32_t TM_COLS = 512;
 
 constexpr int TC_NUM_OPS = 15;
-enum { A_ACT = 0, A_PE = 1, A_ACT_PE = 2 };
+enum { A_ACT = 0, A_PE = 1, A_PE_ACT = 2 };  // A_PE_ACT: k-steps 0..3 come from the PE region, the rest from the activations
 
 enum { K_FWD = 0, K_RGB = 1, K_BWD = 2, K_BW4 = 3, K_BW0 = 4 };
 
 struct TcOp {
   uint32_t src_off;     // byte offset of the op's first slab in the packed weight blob
-  uint32_t slab_bytes;  // bytes per slab (<= TC_STAGE_BYTES, multiple of 32)
+  uint32_t slab_bytes;  // bytes per slab HALF (one CTA's share, <= TC_STAGE_BYTES, multiple of 32); a slab = [rank 0 half][rank 1 half]
   uint16_t n_slabs;
   uint16_t ksteps;      // k-steps (of 16) per slab
   uint8_t kind;         // K_FWD (N=256, 3-pass), K_RGB (N=128, 3-pass), K_BWD (N=256), K_BW4 (N=256 + 64 extra), K_BW0 (N=64)
-  uint8_t a_src;        // A_ACT, A_PE, A_ACT_PE (k-steps >= 16 come from the PE region)
+  uint8_t a_src;        // A_ACT, A_PE, A_PE_ACT
   uint8_t pad[2];
 };
 
@@ -80,7 +93,7 @@ struct TcParams {
   const float* b_rgb1;     // [128]
   const float* w_rgb2;     // [3][128]
   const float* w_dens;     // [256]
-  const float* seed;       // [256] w_dens / seed_scale
+  const uint32_t* seed_h2; // [128] packed half2 pairs of w_dens / seed_scale
   float b_rgb2[3];
   float b_dens;
   float seed_scale;
@@ -91,6 +104,7 @@ struct TcParams {
   float4* out_g;
   int density_only;
   long long* timing;       // debug: clock64 stamps of CTA 0 / first tile, NULL in production
+  int debug_noload;        // debug: skip the weight stream (garbage results) to measure its cost
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -107,43 +121,57 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint16_t cta_mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "h"(cta_mask) : "memory");
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint32_t mbar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(mbar), "h"(cta_mask) : "memory");
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// cta_group::2: arrives on the barrier at this CTA-relative offset in both CTAs of the pair once all prior MMAs are done
+__device__ __forceinline__ void tc_commit2(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(mbar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]   (single CTA, used by light_tc.cuh)
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem] on the CTA pair: M = 256 (128 rows per CTA), B rows split between the two CTAs
+__device__ __forceinline__ void tc_mma_ss2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
 }
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+// Remote arrive without a cluster-scope release: that form compiles to MEMBAR.ALL.GPU per arrival (and a cluster-scope
+// acquire on the waiting side to CCTL.IVALL, an L1 flush), which doubled the epilogue time.  What is published here is this
+// CTA's own shared memory, already made visible to the async proxy by fence.proxy.async, and is read by this SM's tensor core.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, 8 columns of packed fp16 pairs per k-step)
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
-               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) { mbar_wait(a, parity); }  // barrier the peer CTA arrives on
 // K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; SBO = 128 B between 8-row groups,
 // LBO = byte distance between the two 8-wide K chunks of one k-step.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {  // kind::f16, A=B=F16, D=F32, K-major, M=128
-  return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
-}
+#define DSN_R16(r) \
+  "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), \
+  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+#define DSN_RW16(r) \
+  "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), \
+  "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
 #define DSN_R32(r) \
   "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), \
   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),  \
@@ -154,10 +182,6 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {  // kind::f16, A=B=
   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),  \
   "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),  \
   "+r"(r[31])
-#define DSN_IN32(r) \
-  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),   \
-  "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),     \
-  "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -170,59 +194,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   tmem_ld32_nowait(taddr, r);
   tmem_wait_ld(r);
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-      ::"r"(taddr), DSN_IN32(r) : "memory");
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : DSN_R16(r) : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[16]) { asm volatile("tcgen05.wait::ld.sync.aligned;" : DSN_RW16(r)::"memory"); }
 // one lane of a fully converged warp (the warp stays converged, so descriptors live in uniform registers)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-// split two fp32 values into fp16 hi and lo pairs (x = hi + lo up to 2^-22 relative)
-__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(a, b);
-  float2 f = __half22float2(h);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = pack_h2(a - f.x, b - f.y);
-}
+__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 
-// ReLU bits of the 7 forward layers for this thread's 128 columns (4 words per layer), kept in registers.
+// ReLU bits of the 7 forward layers for this thread's 64 columns (2 words per layer), kept in registers.
+// Bit layout inside a word: pair j (columns 2j, 2j+1 of the thread's 16) of quarter q4 -> bits p and 16+p, p = j + 8*(q4&1).
 struct ReluBits {
-  uint32_t w[7][4];
-  __device__ __forceinline__ void put(int layer, int i, uint32_t v) {
+  uint32_t w[7][2];
+  __device__ __forceinline__ void put(int layer, uint32_t v0, uint32_t v1) {
 #pragma unroll
     for (int l = 0; l < 7; ++l)
-      if (l == layer) w[l][i] = v;
+      if (l == layer) { w[l][0] = v0; w[l][1] = v1; }
   }
-  __device__ __forceinline__ uint32_t get(int layer, int i) const {
-    uint32_t v = 0;
+  __device__ __forceinline__ void get(int layer, uint32_t& v0, uint32_t& v1) const {
+    v0 = 0; v1 = 0;
 #pragma unroll
     for (int l = 0; l < 7; ++l)
-      if (l == layer) v = w[l][i];
-    return v;
+      if (l == layer) { v0 = w[l][0]; v1 = w[l][1]; }
   }
 };
+// 0xffff in each half whose ReLU bit is set (P = bit position of the pair, compile-time)
+template <int P>
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t word) {
+  if (P == 15) return ((word >> 15) & 0x00010001u) * 0xFFFFu;  // bit 15 / 31 would read as -0 == 0 in a half compare
+  const uint32_t t = word & ((1u << P) | (1u << (16 + P)));
+  return __hne2_mask(as_h2(t), as_h2(0u));
+}
 
 // Issue all MMAs of one weight slab (KSTEPS k-steps) and release its ring slot.  Shapes are template
 // parameters so that every descriptor is "slab base + immediate": the issuing lane spends a couple of
@@ -230,162 +243,199 @@ struct ReluBits {
 //   a_word / a_lo_word / b_word: low 32 bits of the A-hi / A-lo / B-hi shared-memory descriptors at the slab's first k-step
 template <int ROWS, int KSTEPS, bool THREE, int NMMA, bool EXTRA>
 __device__ __forceinline__ void issue_slab(uint32_t d_main, uint32_t d_extra, uint32_t a_word, uint32_t a_lo_word, uint32_t b_word,
-                                           uint32_t first_acc, uint32_t empty_bar, uint16_t mc_mask) {
+                                           uint32_t first_acc, uint32_t empty_bar, bool do_commit = true) {  // ROWS = B rows held by ONE CTA
   constexpr uint32_t DHI = (128u >> 4) | (1u << 14);             // descriptor bits 32..63: SBO = 128 B, version 1
   constexpr uint32_t A_STEP = (2 * A_CHUNK) >> 4;                // one k-step along K in the A operand
   constexpr uint32_t B_STEP = (2 * ROWS * 16) >> 4;              // one k-step in the slab
   constexpr uint32_t B_LO = (KSTEPS * 2 * ROWS * 16) >> 4;       // hi part -> lo part of the slab
-  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NMMA >> 3) << 17) | ((128u >> 4) << 24);
-  constexpr uint32_t IDESC_X = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NMMA >> 3) << 17) | ((256u >> 4) << 24);   // M = 256 over the CTA pair
+  constexpr uint32_t IDESC_X = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((256u >> 4) << 24);
   if (elect_one()) {
 #pragma unroll
     for (int j = 0; j < KSTEPS; ++j) {
       const uint64_t da = ((uint64_t)DHI << 32) | (a_word + j * A_STEP);
       const uint64_t db = ((uint64_t)DHI << 32) | (b_word + j * B_STEP);
-      tc_mma_ss(d_main, da, db, IDESC, j == 0 ? first_acc : 1u);
+      tc_mma_ss2(d_main, da, db, IDESC, j == 0 ? first_acc : 1u);
       if (THREE) {
         const uint64_t dbl = ((uint64_t)DHI << 32) | (b_word + j * B_STEP + B_LO);
         const uint64_t dal = ((uint64_t)DHI << 32) | (a_lo_word + j * A_STEP);
-        tc_mma_ss(d_main, da, dbl, IDESC, 1u);
-        tc_mma_ss(d_main, dal, db, IDESC, 1u);
+        tc_mma_ss2(d_main, da, dbl, IDESC, 1u);
+        tc_mma_ss2(d_main, dal, db, IDESC, 1u);
       }
       if (EXTRA) {
-        const uint64_t dbx = ((uint64_t)DHI << 32) | (b_word + j * B_STEP + ((256 * 16) >> 4));
-        tc_mma_ss(d_extra, da, dbx, IDESC_X, j == 0 ? first_acc : 1u);
+        const uint64_t dbx = ((uint64_t)DHI << 32) | (b_word + j * B_STEP + ((128 * 16) >> 4));  // this CTA's 32 extra rows follow its 128 main rows
+        tc_mma_ss2(d_extra, da, dbx, IDESC_X, j == 0 ? first_acc : 1u);
       }
     }
-    tc_commit_mc(empty_bar, mc_mask);  // frees the ring slot (in every CTA of the cluster) once these MMAs have read it
+    if (do_commit) tc_commit2(empty_bar);  // frees the ring slot in both CTAs once these MMAs have read it
   }
   __syncwarp();
 }
 
+// State of the MMA-issuing warp (leader CTA) and the per-op slab loop.
+struct MmaState {
+  uint32_t stage, phase, a_phase, sbase, bar_full, bar_empty, bar_a;
+  int waited, noload;
+  // the producers' epilogues publish their 256 output columns in four quarters of 64 (= 4 k-steps of the A operand)
+  __device__ __forceinline__ void need_quarters(int nq) {
+    if (waited >= nq) return;
+    while (waited < nq) { mbar_wait(bar_a + 8 * waited, a_phase); ++waited; }
+    tc_fence_after();
+  }
+};
+template <int ROWS, int KSTEPS, bool THREE, int NMMA, bool EXTRA>
+__device__ __forceinline__ void run_op(MmaState& ms, int n_slabs, int a_src, uint32_t d_main, uint32_t d_extra) {
+  constexpr uint32_t A_LBO = (A_CHUNK >> 4) << 16;          // LBO field of every A descriptor
+  constexpr uint32_t B_LBO = ((ROWS * 16) >> 4) << 16;
+  if (a_src == A_PE) ms.need_quarters(4);
+  const uint32_t pe_steps = a_src == A_ACT ? 0u : 4u;        // leading k-steps served by the PE region
+  const uint32_t a_hi0 = A_LBO | ((ms.sbase + SM_A_HI) >> 4), a_lo0 = A_LBO | ((ms.sbase + SM_A_LO) >> 4);
+  const uint32_t p_hi0 = A_LBO | ((ms.sbase + SM_PE_HI) >> 4), p_lo0 = A_LBO | ((ms.sbase + SM_PE_LO) >> 4);
+  uint32_t kk = 0;
+  for (int s = 0; s < n_slabs; ++s, kk += KSTEPS) {
+    const bool from_pe = kk < pe_steps;
+    if (!from_pe) ms.need_quarters(min(4, (int)((kk - pe_steps + KSTEPS - 1) >> 2) + 1));
+    if (!ms.noload) mbar_wait(ms.bar_full + 8 * ms.stage, ms.phase);
+    tc_fence_after();
+    const uint32_t b_word = B_LBO | ((ms.sbase + SM_RING + ms.stage * TC_STAGE_BYTES) >> 4);
+    const uint32_t ac = ((from_pe ? kk : kk - pe_steps) * 2 * A_CHUNK) >> 4;
+    issue_slab<ROWS, KSTEPS, THREE, NMMA, EXTRA>(d_main, d_extra, (from_pe ? p_hi0 : a_hi0) + ac, (from_pe ? p_lo0 : a_lo0) + ac, b_word,
+                                                 (uint32_t)(kk > 0), ms.bar_empty + 8 * ms.stage, !(ms.noload & 2));
+    if (++ms.stage == TC_STAGES) { ms.stage = 0; ms.phase ^= 1; }
+  }
+}
+
+// octaves of the positional encoding owned by column sub-block `sub` (of 4): [pe_k0(sub), pe_k0(sub+1))
+__device__ __forceinline__ int pe_k0(int sub) { return sub == 0 ? 0 : (sub == 1 ? 2 : (sub == 2 ? 5 : (sub == 3 ? 8 : 10))); }
+// first of the 32 consecutive PE-gradient columns a sub-block reads to cover its own columns
+// (sub 0: 0..14, sub 1: 15..32, sub 2: 33..50, sub 3: 51..63)
+__device__ __forceinline__ int pe_ld0(int sub) { return sub == 0 ? 0 : (sub == 1 ? 8 : 32); }
+
 // ------------------------------------------------------------------------------------------ kernel
-__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + SM_BAR;             // [TC_STAGES]   weights landed
-  const uint32_t bar_empty = bar_full + 8 * TC_STAGES;  // [TC_STAGES]   ring slot consumed by every CTA of the cluster
-  const uint32_t bar_acc = bar_empty + 8 * TC_STAGES;   //               accumulator complete (MMA -> epilogue)
-  const uint32_t bar_a = bar_acc + 8;                   // [4]           epilogue done with column quarter q (epilogue -> MMA)
+  const uint32_t bar_full = sbase + SM_BAR;              // [TC_STAGES]   half slab landed (leader: its own AND the peer's, 2 arrivals)
+  const uint32_t bar_empty = bar_full + 8 * TC_STAGES;   // [TC_STAGES]   ring slot consumed (commit multicast to both CTAs)
+  const uint32_t bar_acc = bar_empty + 8 * TC_STAGES;    //               accumulator complete (MMA -> epilogue, both CTAs)
+  const uint32_t bar_a = bar_acc + 8;                    // [4]           (leader) both epilogues done with column quarter q
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * (2 * TC_STAGES + 6));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_CLUSTER); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, cta_rank == 0 ? 2 : 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_acc, 1);
-    for (int q4 = 0; q4 < 4; ++q4) mbar_init(bar_a + 8 * q4, TC_EPI_WARPS * 32);
+    for (int q4 = 0; q4 < 4; ++q4) mbar_init(bar_a + 8 * q4, 2 * TC_EPI_WARPS);  // one elected lane per epilogue warp of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_EPI_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == TC_EPI_WARPS) {  // same warp id in both CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into / arrives on them
+  cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t cta_rank = cluster_ctarank();
-  const uint16_t mc_mask = (uint16_t)((1u << TC_CLUSTER) - 1);
 
   const int64_t n_active = P.n_active_ptr ? (int64_t)*P.n_active_ptr : P.n_active_host;
   const int64_t n_tiles = (n_active + TC_TILE - 1) / TC_TILE;
-  // every CTA runs the same number of iterations (the ring of a cluster advances in lockstep); tiles past the end are dummies
-  const int64_t n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
+  // both CTAs of a pair run the leader's iteration count (the peer's last tile may be a dummy)
+  const int64_t lead = blockIdx.x & ~1u;
+  const int64_t n_iter = n_tiles > lead ? (n_tiles - lead + gridDim.x - 1) / gridDim.x : 0;
   const int n_ops = P.density_only ? 7 : TC_NUM_OPS;
 
   if (warp == TC_EPI_WARPS + 1) {
     // =============================== weight loader (one elected lane of a converged warp) =======
-    {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t it = 0; it < n_iter; ++it) {
-        for (int op = 0; op < n_ops; ++op) {
-          const TcOp o = c_tc_ops[op];
-          const uint32_t part = o.slab_bytes / TC_CLUSTER;
-          const uint8_t* src = P.wpack + o.src_off + cta_rank * part;
-          for (int s = 0; s < o.n_slabs; ++s) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(bar_full + 8 * stage, o.slab_bytes);
-              bulk_g2s_mc(sbase + SM_RING + stage * TC_STAGE_BYTES + cta_rank * part, src + (size_t)s * o.slab_bytes, part,
-                          bar_full + 8 * stage, mc_mask);
-            }
-            __syncwarp();
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+    uint32_t stage = 0, phase = 0;
+    for (int64_t it = 0; it < n_iter; ++it) {
+      for (int op = 0; op < n_ops; ++op) {
+        const TcOp o = c_tc_ops[op];
+        const uint8_t* src = P.wpack + o.src_off + (size_t)cta_rank * o.slab_bytes;
+        for (int s = 0; s < o.n_slabs; ++s) {
+          if (P.debug_noload) continue;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar_full + 8 * stage, o.slab_bytes);
+            bulk_g2s(sbase + SM_RING + stage * TC_STAGE_BYTES, src + (size_t)s * 2 * o.slab_bytes, o.slab_bytes, bar_full + 8 * stage);
           }
+          __syncwarp();
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS && cta_rank != 0) {
+    // =============================== peer CTA: relay "my half of the slab has landed" to the leader ==========
+    uint32_t stage = 0, phase = 0;
+    const uint32_t leader_pfull = mapa_u32(bar_full, 0);
+    for (int64_t it = 0; it < n_iter; ++it) {
+      for (int op = 0; op < n_ops; ++op) {
+        const int n_slabs = c_tc_ops[op].n_slabs;
+        for (int s = 0; s < n_slabs; ++s) {
+          if (P.debug_noload) continue;
+          mbar_wait(bar_full + 8 * stage, phase);
+          if (lane == 0) mbar_arrive_cluster(leader_pfull + 8 * stage);
+          __syncwarp();
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == TC_EPI_WARPS) {
-    // =============================== MMA issuer (one elected lane of a converged warp) =========
-    {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      constexpr uint32_t A_LBO = (A_CHUNK >> 4) << 16;  // LBO field of every A descriptor
-      for (int64_t it = 0; it < n_iter; ++it) {
-        for (int op = 0; op < n_ops; ++op) {
-          const TcOp o = c_tc_ops[op];
-          const bool mstamp = P.timing && blockIdx.x == 0 && it == 0 && lane == 0;
-          long long w_full = 0, w_a = 0, t_op0 = mstamp ? clock64() : 0;
-          const uint32_t d_main = tmem + (uint32_t)(op & 1) * TM_ACC;
-          const uint32_t d_extra = tmem + (uint32_t)((op & 1) ^ 1) * TM_ACC;
-          // the producer's epilogue publishes its 256 output columns in four quarters of 64 (= 4 k-steps of this op's A operand)
-          int waited = 0;
-          auto need_quarters = [&](int nq) {
-            if (waited >= nq) return;
-            long long t0 = mstamp ? clock64() : 0;
-            while (waited < nq) { mbar_wait(bar_a + 8 * waited, a_phase); ++waited; }
-            tc_fence_after();
-            if (mstamp) w_a += clock64() - t0;
-          };
-          need_quarters(o.a_src == A_PE ? 4 : 1);
-          const uint32_t rows = o.kind == K_FWD || o.kind == K_BWD ? 256u : (o.kind == K_RGB ? 128u : (o.kind == K_BW4 ? 320u : 64u));
-          const uint32_t b_lbo = ((rows * 16) >> 4) << 16;
-          uint32_t kk = 0;
-          for (int s = 0; s < o.n_slabs; ++s, kk += o.ksteps) {
-            if (kk < 16) need_quarters(min(4, (int)((kk + o.ksteps - 1) >> 2) + 1));
-            long long t1 = mstamp ? clock64() : 0;
-            mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
-            if (mstamp) w_full += clock64() - t1;
-            const uint32_t b_word = b_lbo | ((sbase + SM_RING + stage * TC_STAGE_BYTES) >> 4);
-            const uint32_t ebar = bar_empty + 8 * stage;
-            const bool from_pe = (o.a_src == A_PE) || (o.a_src == A_ACT_PE && kk >= 16);
-            const uint32_t pc = (o.a_src == A_PE ? kk : kk - 16) * 2;
-            const uint32_t a_word = A_LBO | ((from_pe ? sbase + SM_PE_HI + pc * A_CHUNK : sbase + SM_A_HI + kk * 2 * A_CHUNK) >> 4);
-            const uint32_t a_lo_word = A_LBO | ((from_pe ? sbase + SM_PE_LO + pc * A_CHUNK : sbase + SM_A_LO + kk * 2 * A_CHUNK) >> 4);
-            const uint32_t first_acc = (uint32_t)(kk > 0);
-            switch (o.kind) {
-              case K_FWD: issue_slab<256, 1, true, 256, false>(d_main, 0u, a_word, a_lo_word, b_word, first_acc, ebar, mc_mask); break;
-              case K_RGB: issue_slab<128, 2, true, 128, false>(d_main, 0u, a_word, a_lo_word, b_word, first_acc, ebar, mc_mask); break;
-              case K_BWD: issue_slab<256, 2, false, 256, false>(d_main, 0u, a_word, 0u, b_word, first_acc, ebar, mc_mask); break;
-              case K_BW4: issue_slab<320, 1, false, 256, true>(d_main, d_extra, a_word, 0u, b_word, first_acc, ebar, mc_mask); break;
-              default: issue_slab<64, 8, false, 64, false>(d_main, 0u, a_word, 0u, b_word, first_acc, ebar, mc_mask); break;
-            }
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-          }
-          need_quarters(4);
-          if (elect_one()) tc_commit(bar_acc);  // accumulator (and the extra columns of K_BW4) complete
-          __syncwarp();
-          a_phase ^= 1;
-          if (mstamp) { P.timing[64 + 3 * op] = w_full; P.timing[65 + 3 * op] = w_a; P.timing[66 + 3 * op] = clock64() - t_op0; }
+    // =============================== leader CTA: MMA issuer (one elected lane of a converged warp) ==========
+    // Measured: one iteration of the slab loop costs the issuing warp ~450 cycles of dependent scalar work whatever it
+    // issues, so a slab must carry more MMA time than that (2 forward k-steps = 6 MMAs = 768 cycles) and the loop body
+    // is kept minimal: kind switch hoisted out of it, one "landed" barrier per slab, shapes as template parameters.
+    MmaState ms;
+    ms.stage = 0; ms.phase = 0; ms.a_phase = 0;
+    ms.sbase = sbase; ms.bar_full = bar_full; ms.bar_empty = bar_empty; ms.bar_a = bar_a; ms.noload = P.debug_noload;
+    for (int64_t it = 0; it < n_iter; ++it) {
+      for (int op = 0; op < n_ops; ++op) {
+        const TcOp o = c_tc_ops[op];
+        const bool mstamp = P.timing && blockIdx.x == 0 && it == 0 && lane == 0;
+        const long long t_op0 = mstamp ? clock64() : 0;
+        const uint32_t d_main = tmem + (uint32_t)(op & 1) * TM_ACC;
+        const uint32_t d_extra = tmem + (uint32_t)((op & 1) ^ 1) * TM_ACC;
+        ms.waited = 0;
+        switch (o.kind) {
+          case K_FWD: run_op<128, 2, true, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_RGB: run_op<64, 4, true, 128, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_BWD: run_op<128, 4, false, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_BW4: run_op<160, 2, false, 256, true>(ms, o.n_slabs, o.a_src, d_main, d_extra); break;
+          default: run_op<32, 16, false, 64, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
         }
+        ms.need_quarters(4);
+        if (elect_one()) tc_commit2(bar_acc);  // accumulator (and the extra columns of K_BW4) complete, in both CTAs
+        __syncwarp();
+        ms.a_phase ^= 1;
+        if (mstamp) { P.timing[64 + 3 * op] = 0; P.timing[65 + 3 * op] = 0; P.timing[66 + 3 * op] = clock64() - t_op0; }
       }
     }
   } else {
     // =============================== epilogue warps ===========================================
     // warp w: TMEM lane quarter q = w % 4 (rows 32q..32q+31), column sub-block sub = w / 4: of every 64-column
-    // accumulator quarter this thread handles columns [32*sub, 32*sub + 32) of its row.
+    // accumulator quarter this thread handles columns [16*sub, 16*sub + 16) of its row.
     const int q = warp & 3, sub = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t row_off = (uint32_t)row * 16;
     uint32_t acc_phase = 0;
     ReluBits relu;
 #pragma unroll
-    for (int l = 0; l < 7; ++l)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) relu.w[l][i] = 0;
+    for (int l = 0; l < 7; ++l) { relu.w[l][0] = 0; relu.w[l][1] = 0; }
+    // publish quarter q4 of the A operand this warp has just written: writes -> async proxy, then one arrival per warp
+    const uint32_t leader_bar_a = mapa_u32(bar_a, 0);
+    auto publish = [&](int q4) {
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_bar_a + 8 * q4);
+    };
     float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
     if ((int64_t)blockIdx.x * TC_TILE + row < n_active) pt_next = P.active[(int64_t)blockIdx.x * TC_TILE + row];
+    const int k_lo = pe_k0(sub), k_hi = pe_k0(sub + 1);
+    float* stash = reinterpret_cast<float*>(smem + SM_STASH);  // [64 PE columns][128 rows] fp32, backward chain only
+    float* xch = reinterpret_cast<float*>(smem + SM_XCH);      // [3][8][128]
     for (int64_t it = 0; it < n_iter; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t base = tile * TC_TILE;
@@ -396,22 +446,22 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
         pt_next = nb < n_active ? P.active[nb] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const float xs[3] = {pt.x, pt.y, pt.z};
-      // ---- positional encoding (model/dimension_kernel.py:5-35) = A operand of layer 0 and tail of layer 4's
+      // ---- positional encoding (model/dimension_kernel.py:5-35) = A operand of layer 0 and head of layer 4's
       {
         auto put = [&](int c, float v) {
           __half hh = __float2half_rn(v);
           __half ll = __float2half_rn(v - __half2float(hh));
-          uint32_t off = (uint32_t)(c >> 3) * A_CHUNK + row * 16 + (c & 7) * 2;
+          uint32_t off = (uint32_t)(c >> 3) * A_CHUNK + row_off + (c & 7) * 2;
           *reinterpret_cast<__half*>(smem + SM_PE_HI + off) = hh;
           *reinterpret_cast<__half*>(smem + SM_PE_LO + off) = ll;
         };
         if (sub == 0) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) put(c, xs[c]);
-        } else {
+        } else if (sub == 3) {
           put(63, 0.f);
         }
-        for (int k = sub * 5; k < sub * 5 + 5; ++k) {
+        for (int k = k_lo; k < k_hi; ++k) {
           float f = (float)(1 << k);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -426,199 +476,255 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
       if (stamp) P.timing[0] = clock64();
       fence_proxy_async();
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) mbar_arrive(bar_a + 8 * q4);
+        for (int q4 = 0; q4 < 4; ++q4) mbar_arrive_cluster(leader_bar_a + 8 * q4);
+      }
 
-      float sigma_part = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
-      float* stash = reinterpret_cast<float*>(smem + SM_A_LO);  // [64 PE columns][128 rows] fp32, backward chain only
+      float2 sig2 = make_float2(0.f, 0.f);
+      float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f), e2 = make_float2(0.f, 0.f);
       for (int op = 0; op < n_ops; ++op) {
+        const uint32_t t_accb = t_lane + (uint32_t)(op & 1) * TM_ACC + sub * TC_CPT;
+        if (op == 7) {
+          // ---------- seed of the backward chain: G6 = (w_dens / scale) * relu'(a6).  It overwrites h6 (A-hi), which the
+          // rgb head's MMAs (this op) read: wait for them, write all four quarters (bW6 can start), then do the rgb tail.
+          uint32_t m0, m1;
+          relu.get(6, m0, m1);
+          uint4 sd[4][2];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            sd[q4][0] = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2));
+            sd[q4][1] = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2 + 4));
+          }
+          mbar_wait(bar_acc, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after();
+          if (stamp) P.timing[1 + 4 * op] = clock64();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t mw = (q4 >> 1) ? m1 : m0;
+            uint4 h0 = sd[q4][0], h1 = sd[q4][1];
+            const int pb = 8 * (q4 & 1);
+            if (pb == 0) {
+              h0.x &= relu_mask2<0>(mw); h0.y &= relu_mask2<1>(mw); h0.z &= relu_mask2<2>(mw); h0.w &= relu_mask2<3>(mw);
+              h1.x &= relu_mask2<4>(mw); h1.y &= relu_mask2<5>(mw); h1.z &= relu_mask2<6>(mw); h1.w &= relu_mask2<7>(mw);
+            } else {
+              h0.x &= relu_mask2<8>(mw); h0.y &= relu_mask2<9>(mw); h0.z &= relu_mask2<10>(mw); h0.w &= relu_mask2<11>(mw);
+              h1.x &= relu_mask2<12>(mw); h1.y &= relu_mask2<13>(mw); h1.z &= relu_mask2<14>(mw); h1.w &= relu_mask2<15>(mw);
+            }
+            const uint32_t off = (uint32_t)((q4 * 64 + sub * TC_CPT) / 8) * A_CHUNK + row_off;
+            *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = h0;
+            *reinterpret_cast<uint4*>(smem + SM_A_HI + off + A_CHUNK) = h1;
+            publish(q4);
+          }
+          if (stamp) P.timing[2 + 4 * op] = clock64();
+          // rgb head tail: relu(acc[0:128] + b) -> Linear(128,3) partials (model/spacenet.py:75-80); 2 x 16 columns per thread
+          uint32_t v0[16], v1[16];
+          tmem_ld16_nowait(t_accb, v0);
+          tmem_ld16_nowait(t_accb + 64, v1);
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const int col0 = hq * 64 + sub * TC_CPT;
+            float4 b[4], w0[4], w1[4], w2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              b[i] = __ldg(reinterpret_cast<const float4*>(P.b_rgb1 + col0) + i);
+              w0[i] = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + col0) + i);
+              w1[i] = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 128 + col0) + i);
+              w2[i] = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 256 + col0) + i);
+            }
+            if (hq == 0) tmem_wait_ld(v0); else tmem_wait_ld(v1);
+            const uint32_t(&v)[16] = hq ? v1 : v0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 ra = __fadd2_rn(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), make_float2(b[i].x, b[i].y));
+              float2 rb = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), make_float2(b[i].z, b[i].w));
+              ra.x = fmaxf(ra.x, 0.f); ra.y = fmaxf(ra.y, 0.f); rb.x = fmaxf(rb.x, 0.f); rb.y = fmaxf(rb.y, 0.f);
+              e0 = __ffma2_rn(make_float2(w0[i].x, w0[i].y), ra, e0); e0 = __ffma2_rn(make_float2(w0[i].z, w0[i].w), rb, e0);
+              e1 = __ffma2_rn(make_float2(w1[i].x, w1[i].y), ra, e1); e1 = __ffma2_rn(make_float2(w1[i].z, w1[i].w), rb, e1);
+              e2 = __ffma2_rn(make_float2(w2[i].x, w2[i].y), ra, e2); e2 = __ffma2_rn(make_float2(w2[i].z, w2[i].w), rb, e2);
+            }
+          }
+          if (stamp) { P.timing[3 + 4 * op] = clock64(); P.timing[4 + 4 * op] = clock64(); }
+          continue;
+        }
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        const uint32_t t_accb = t_lane + (uint32_t)(op & 1) * TM_ACC;
+        if (op == 14) break;  // the last op's accumulator is consumed by the tile-output stage below
         if (op == 10) {
-          // layer 4 backward also produced d sigma / d PE (64 columns) in the idle accumulator: park this thread's 32 of them
+          // layer 4 backward also produced d sigma / d PE (64 columns) in the idle accumulator, which the next op's MMAs
+          // overwrite: park the columns this thread will need for the chain rule (own octaves) before publishing anything
           uint32_t v[32];
-          tmem_ld32(t_lane + (uint32_t)((op & 1) ^ 1) * TM_ACC + sub * 32, v);
+          const int c0 = pe_ld0(sub);
+          tmem_ld32(t_lane + (uint32_t)((op & 1) ^ 1) * TM_ACC + c0, v);
+          const int cb = sub == 0 ? 0 : 3 + 6 * k_lo, ce = sub == 3 ? 63 : 3 + 6 * k_hi;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) stash[(sub * 32 + i) * TC_TILE + row] = __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i >= cb && c0 + i < ce) stash[(c0 + i) * TC_TILE + row] = __uint_as_float(v[i]);
         }
+        if (stamp) P.timing[1 + 4 * op] = clock64();
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(t_accb, va);
+        if (op <= 6) {
+          // ---------- forward layer: bias + ReLU, record ReLU bits, split to fp16 hi / lo = next A operand (in place)
+          const float* __restrict__ bias = P.bias + op * 256 + sub * TC_CPT;
+          const float* __restrict__ wdp = P.w_dens + sub * TC_CPT;
+          uint32_t mw0 = 0, mw1 = 0;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          if (stamp && (q4 & 1) == 0) P.timing[1 + 4 * op + q4] = clock64();
-          const int col0 = q4 * 64 + sub * 32;  // this thread's 32 output columns of the quarter
-          if (op <= 6) {
-            // ---------- forward layer: bias + ReLU, record ReLU bits, split to fp16 hi / lo = next A operand (in place)
-            const float* __restrict__ bias = P.bias + op * 256;
-            uint32_t v[32];
-            tmem_ld32(t_accb + col0, v);
-            uint32_t m = 0;
-            uint32_t hi[16], lo[16];
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t(&v)[16] = (q4 & 1) ? vb : va;
+            float4 b[4];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
-              float h0 = fmaxf(__uint_as_float(v[i]) + b.x, 0.f), h1 = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
-              float h2 = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), h3 = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
-              // ReLU bit = (h != 0): h >= +0, so bits(h) + 0x7fffffff carries into bit 31 iff h > 0; shifted in MSB-first
-              m = __funnelshift_l(__float_as_uint(h0) + 0x7fffffffu, m, 1);
-              m = __funnelshift_l(__float_as_uint(h1) + 0x7fffffffu, m, 1);
-              m = __funnelshift_l(__float_as_uint(h2) + 0x7fffffffu, m, 1);
-              m = __funnelshift_l(__float_as_uint(h3) + 0x7fffffffu, m, 1);
+            for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + q4 * 64) + i);
+            tmem_wait_ld(v);
+            if (q4 < 3) { if (q4 & 1) tmem_ld16_nowait(t_accb + (q4 + 1) * 64, va); else tmem_ld16_nowait(t_accb + (q4 + 1) * 64, vb); }
+            uint32_t hi[8], lo[8];
+            uint32_t mw = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b[j >> 1];
+              const float2 b2 = (j & 1) ? make_float2(bb.z, bb.w) : make_float2(bb.x, bb.y);
+              float2 h = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
+              h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
+              const __half2 hh = __floats2half2_rn(h.x, h.y);
+              const float2 hf = __half22float2(hh);
+              const float2 l = __ffma2_rn(hf, make_float2(-1.f, -1.f), h);  // exact: x = hi + lo up to 2^-22 relative
+              hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+              lo[j] = pack_h2(l.x, l.y);
+              // ReLU bit = (hi > 0); an activation below the fp16 subnormal range is 0 for the forward pass and the gradient alike
+              const int p = j + 8 * (q4 & 1);
+              mw |= __hgt2_mask(hh, as_h2(0u)) & ((1u << p) | (1u << (16 + p)));
               if (op == 6) {
-                const float4 wd = __ldg(reinterpret_cast<const float4*>(P.w_dens + col0 + i));
-                sigma_part = fmaf(wd.x, h0, sigma_part); sigma_part = fmaf(wd.y, h1, sigma_part);
-                sigma_part = fmaf(wd.z, h2, sigma_part); sigma_part = fmaf(wd.w, h3, sigma_part);
-              }
-              split_h2(h0, h1, hi[i / 2], lo[i / 2]);
-              split_h2(h2, h3, hi[i / 2 + 1], lo[i / 2 + 1]);
-            }
-            relu.put(op, q4, __brev(m));  // element i of the chunk -> bit i
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const uint32_t off = (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16;
-              *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
-              *reinterpret_cast<uint4*>(smem + SM_A_LO + off) = make_uint4(lo[4 * t], lo[4 * t + 1], lo[4 * t + 2], lo[4 * t + 3]);
-            }
-          } else if (op == 7) {
-            // ---------- rgb head: relu(acc[0:128] + b) -> Linear(128,3) partials (model/spacenet.py:75-80) ...
-            if (q4 < 2) {
-              uint32_t vr[32];
-              tmem_ld32(t_accb + col0, vr);
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(P.b_rgb1 + col0 + i));
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + col0 + i));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 128 + col0 + i));
-                const float4 w2 = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 256 + col0 + i));
-                const float r0 = fmaxf(__uint_as_float(vr[i]) + b.x, 0.f), r1 = fmaxf(__uint_as_float(vr[i + 1]) + b.y, 0.f);
-                const float r2 = fmaxf(__uint_as_float(vr[i + 2]) + b.z, 0.f), r3 = fmaxf(__uint_as_float(vr[i + 3]) + b.w, 0.f);
-                e0 = fmaf(w0.x, r0, e0); e0 = fmaf(w0.y, r1, e0); e0 = fmaf(w0.z, r2, e0); e0 = fmaf(w0.w, r3, e0);
-                e1 = fmaf(w1.x, r0, e1); e1 = fmaf(w1.y, r1, e1); e1 = fmaf(w1.z, r2, e1); e1 = fmaf(w1.w, r3, e1);
-                e2 = fmaf(w2.x, r0, e2); e2 = fmaf(w2.y, r1, e2); e2 = fmaf(w2.z, r2, e2); e2 = fmaf(w2.w, r3, e2);
+                const float2 wd = __ldg(reinterpret_cast<const float2*>(wdp + q4 * 64 + 2 * j));
+                sig2 = __ffma2_rn(wd, h, sig2);
               }
             }
-            // ... and the seed of the backward chain (the rgb head's MMAs have read the A operand): G6 = (w_dens / scale) * relu'(a6)
-            {
-              const uint32_t mb = relu.w[6][q4];
-              uint32_t hi[16];
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 sd = __ldg(reinterpret_cast<const float4*>(P.seed + col0 + i));
-                float g0 = ((mb >> i) & 1u) ? sd.x : 0.f, g1 = ((mb >> (i + 1)) & 1u) ? sd.y : 0.f;
-                float g2 = ((mb >> (i + 2)) & 1u) ? sd.z : 0.f, g3 = ((mb >> (i + 3)) & 1u) ? sd.w : 0.f;
-                hi[i / 2] = pack_h2(g0, g1);
-                hi[i / 2 + 1] = pack_h2(g2, g3);
-              }
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                *reinterpret_cast<uint4*>(smem + SM_A_HI + (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16) =
-                    make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
+            if (q4 >> 1) mw1 |= mw; else mw0 |= mw;
+            if (op != n_ops - 1) {  // density-only mode ends here: nothing consumes the operand (and the exchange area aliases A-lo)
+              const uint32_t off = (uint32_t)((q4 * 64 + sub * TC_CPT) / 8) * A_CHUNK + row_off;
+              *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(smem + SM_A_HI + off + A_CHUNK) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              *reinterpret_cast<uint4*>(smem + SM_A_LO + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              *reinterpret_cast<uint4*>(smem + SM_A_LO + off + A_CHUNK) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              publish(q4);
             }
-          } else if (op <= 13) {
-            // ---------- backward layer: G_{l-1} = (G_l W_l) * relu'(a_{l-1}), fp16 single pass, hi only
-            const uint32_t mb = relu.get(13 - op, q4);  // op 8 -> layer 5 ... op 13 -> layer 0
-            uint32_t v[32];
-            tmem_ld32(t_accb + col0, v);
-            uint32_t hi[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float g0 = ((mb >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
-              float g1 = ((mb >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
-              hi[i / 2] = pack_h2(g0, g1);
-            }
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              *reinterpret_cast<uint4*>(smem + SM_A_HI + (uint32_t)(col0 / 8 + t) * A_CHUNK + row * 16) =
-                  make_uint4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]);
+            if (stamp && q4 == 1) P.timing[2 + 4 * op] = clock64();
           }
-          if (stamp && (q4 & 1) == 1) P.timing[1 + 4 * op + q4] = clock64();
-          if (op != n_ops - 1) {
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(bar_a + 8 * q4);
+          relu.put(op, mw0, mw1);
+        } else {
+          // ---------- backward layer: G_{l-1} = (G_l W_l) * relu'(a_{l-1}), fp16 single pass, hi only
+          uint32_t m0, m1;
+          relu.get(13 - op, m0, m1);  // op 8 -> layer 5 ... op 13 -> layer 0
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t(&v)[16] = (q4 & 1) ? vb : va;
+            tmem_wait_ld(v);
+            if (q4 < 3) { if (q4 & 1) tmem_ld16_nowait(t_accb + (q4 + 1) * 64, va); else tmem_ld16_nowait(t_accb + (q4 + 1) * 64, vb); }
+            const uint32_t mw = (q4 >> 1) ? m1 : m0;
+            uint32_t g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            if ((q4 & 1) == 0) {
+              g[0] &= relu_mask2<0>(mw); g[1] &= relu_mask2<1>(mw); g[2] &= relu_mask2<2>(mw); g[3] &= relu_mask2<3>(mw);
+              g[4] &= relu_mask2<4>(mw); g[5] &= relu_mask2<5>(mw); g[6] &= relu_mask2<6>(mw); g[7] &= relu_mask2<7>(mw);
+            } else {
+              g[0] &= relu_mask2<8>(mw); g[1] &= relu_mask2<9>(mw); g[2] &= relu_mask2<10>(mw); g[3] &= relu_mask2<11>(mw);
+              g[4] &= relu_mask2<12>(mw); g[5] &= relu_mask2<13>(mw); g[6] &= relu_mask2<14>(mw); g[7] &= relu_mask2<15>(mw);
+            }
+            const uint32_t off = (uint32_t)((q4 * 64 + sub * TC_CPT) / 8) * A_CHUNK + row_off;
+            *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = make_uint4(g[0], g[1], g[2], g[3]);
+            *reinterpret_cast<uint4*>(smem + SM_A_HI + off + A_CHUNK) = make_uint4(g[4], g[5], g[6], g[7]);
+            publish(q4);
+            if (stamp && q4 == 1) P.timing[2 + 4 * op] = clock64();
           }
         }
+        if (stamp) { P.timing[3 + 4 * op] = clock64(); P.timing[4 + 4 * op] = clock64(); }
       }
-      // ---------- tile outputs: both accumulator halves of the last op are complete
+      // ---------- tile outputs
       {
         float gx[3] = {0.f, 0.f, 0.f};
         if (!P.density_only) {
-          // d sigma / d PE (64 columns) -> chain rule through the encoding; this thread owns octaves 5*sub .. 5*sub+4
-          // layer-0 part: accumulator 0 (op 14), columns 0..63; layer-4 part: the stash written at op 10
-          uint32_t g0[32], g1[32];
-          tmem_ld32(t_lane, g0);
-          tmem_ld32(t_lane + 32, g1);
-          auto gpe = [&](int c) -> float { return __uint_as_float(c < 32 ? g0[c] : g1[c - 32]) + stash[c * TC_TILE + row]; };
+          // d sigma / d PE -> chain rule through the encoding for this thread's own octaves: layer-0 part = accumulator 0
+          // (op 14, columns 0..63), layer-4 part = the stash written at op 10 (same thread, same columns)
+          uint32_t g[32];
+          tmem_ld32(t_lane + pe_ld0(sub), g);
           // sin/cos are still in the PE region (written by this very thread)
           auto pe_val = [&](int col) -> float {
-            const uint32_t off = (uint32_t)(col >> 3) * A_CHUNK + row * 16 + (col & 7) * 2;
+            const uint32_t off = (uint32_t)(col >> 3) * A_CHUNK + row_off + (col & 7) * 2;
             return __half2float(*reinterpret_cast<const __half*>(smem + SM_PE_HI + off)) +
                    __half2float(*reinterpret_cast<const __half*>(smem + SM_PE_LO + off));
           };
-          if (sub == 0) { gx[0] = gpe(0); gx[1] = gpe(1); gx[2] = gpe(2); }
-#pragma unroll
-          for (int kq = 0; kq < 5; ++kq) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const int k0 = kq, k1 = kq + 5;
-              const float gs = sub ? gpe(3 + 6 * k1 + c) : gpe(3 + 6 * k0 + c);
-              const float gc = sub ? gpe(6 + 6 * k1 + c) : gpe(6 + 6 * k0 + c);
-              const float f = sub ? (float)(1 << k1) : (float)(1 << k0);
-              const int ks = sub ? k1 : k0;
-              const float sn = pe_val(3 + 6 * ks + c), cs = pe_val(6 + 6 * ks + c);
-              gx[c] = fmaf((gs * cs - gc * sn), f, gx[c]);
-            }
+          // every branch below is warp uniform (sub is); C0 = pe_ld0(sub) as a literal keeps g[] in registers
+#define DSN_GPE(C, C0) (__uint_as_float(g[(C) - (C0)]) + stash[(C) * TC_TILE + row])
+#define DSN_OCTAVE(K, C0)                                                               \
+  {                                                                                     \
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                     \
+      const float gs = DSN_GPE(3 + 6 * (K) + c, C0), gc = DSN_GPE(6 + 6 * (K) + c, C0); \
+      const float sn = pe_val(3 + 6 * (K) + c), cs = pe_val(6 + 6 * (K) + c);           \
+      gx[c] = fmaf((gs * cs - gc * sn), (float)(1 << (K)), gx[c]);                      \
+    }                                                                                   \
+  }
+          if (sub == 0) {
+            gx[0] = DSN_GPE(0, 0); gx[1] = DSN_GPE(1, 0); gx[2] = DSN_GPE(2, 0);
+            DSN_OCTAVE(0, 0) DSN_OCTAVE(1, 0)
+          } else if (sub == 1) {
+            DSN_OCTAVE(2, 8) DSN_OCTAVE(3, 8) DSN_OCTAVE(4, 8)
+          } else if (sub == 2) {
+            DSN_OCTAVE(5, 32) DSN_OCTAVE(6, 32) DSN_OCTAVE(7, 32)
+          } else {
+            DSN_OCTAVE(8, 32) DSN_OCTAVE(9, 32)
           }
+#undef DSN_OCTAVE
+#undef DSN_GPE
         }
-        // cross-thread sums (the two threads of a row live in warps w and w+4): through 8 TMEM cells of the row
-        if (sub == 1) {
-          uint32_t x[8] = {__float_as_uint(sigma_part), __float_as_uint(e0), __float_as_uint(e1), __float_as_uint(e2),
-                           __float_as_uint(gx[0]), __float_as_uint(gx[1]), __float_as_uint(gx[2]), 0u};
-          tmem_st8(t_lane + TM_XCH, x);
-          tmem_wait_st();
-          tc_fence_before();
+        // cross-thread sums (the four threads of a row live in warps q, q+4, q+8, q+12) through shared memory
+        const float sigma_part = sig2.x + sig2.y;
+        const float ee0 = e0.x + e0.y, ee1 = e1.x + e1.y, ee2 = e2.x + e2.y;
+        if (sub != 0) {
+          float* x = xch + (sub - 1) * 8 * TC_TILE + row;
+          x[0] = sigma_part; x[TC_TILE] = ee0; x[2 * TC_TILE] = ee1; x[3 * TC_TILE] = ee2;
+          x[4 * TC_TILE] = gx[0]; x[5 * TC_TILE] = gx[1]; x[6 * TC_TILE] = gx[2];
         }
+        tc_fence_before();
         epi_bar();
-        if (sub == 0) {
-          tc_fence_after();
-          uint32_t x[8];
-          tmem_ld8(t_lane + TM_XCH, x);
-          if (live) {
-            const float sigma = sigma_part + __uint_as_float(x[0]) + P.b_dens;
-            if (P.density_only) {
-              P.out_a[base + row] = make_float4(sigma, 0.f, 0.f, 0.f);
-            } else {
-              P.out_a[base + row] = make_float4(sigma, e0 + __uint_as_float(x[1]) + P.b_rgb2[0], e1 + __uint_as_float(x[2]) + P.b_rgb2[1],
-                                                e2 + __uint_as_float(x[3]) + P.b_rgb2[2]);
-              P.out_g[base + row] = make_float4((gx[0] + __uint_as_float(x[4])) * P.seed_scale, (gx[1] + __uint_as_float(x[5])) * P.seed_scale,
-                                                (gx[2] + __uint_as_float(x[6])) * P.seed_scale, 0.f);
-            }
+        if (sub == 0 && live) {
+          float s[7] = {sigma_part, ee0, ee1, ee2, gx[0], gx[1], gx[2]};
+#pragma unroll
+          for (int k = 0; k < 7; ++k) s[k] += xch[k * TC_TILE + row] + xch[(8 + k) * TC_TILE + row] + xch[(16 + k) * TC_TILE + row];
+          const float sigma = s[0] + P.b_dens;
+          if (P.density_only) {
+            P.out_a[base + row] = make_float4(sigma, 0.f, 0.f, 0.f);
+          } else {
+            P.out_a[base + row] = make_float4(sigma, s[1] + P.b_rgb2[0], s[2] + P.b_rgb2[1], s[3] + P.b_rgb2[2]);
+            P.out_g[base + row] = make_float4(s[4] * P.seed_scale, s[5] * P.seed_scale, s[6] * P.seed_scale, 0.f);
           }
-          tc_fence_before();
         }
         if (stamp) P.timing[62] = clock64();
-        epi_bar();  // nobody overwrites the PE region / stash / TM_XCH of this tile before everyone is done with them
+        // No second barrier: the exchange area, the stash and the PE region are rewritten by the next tile only after
+        // MMAs that need an arrival from every epilogue warp, i.e. after every thread has left this block.
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // no CTA leaves while a peer may still multicast into its ring or arrive on its barriers
+  cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs / remote arrivals may still touch it
   if (warp == TC_EPI_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
   }
 }
 
 // ------------------------------------------------------------------------------------------ host
 struct TcWeights {
   void* d_pack = nullptr;
-  float* d_f32 = nullptr;  // biases 0..6 (7x256; row 0 per frame), b_rgb1 (128), w_rgb2 (384), w_dens (256), seed (256)
+  float* d_f32 = nullptr;  // biases 0..6 (7x256; row 0 per frame), b_rgb1 (128), w_rgb2 (384), w_dens (256), seed half2 pairs (128 words)
   float b_rgb2[3] = {0, 0, 0};
   float b_dens = 0.f, seed_scale = 1.f;
   TcOp ops[TC_NUM_OPS];
   static constexpr int F32_BRGB1 = 7 * 256, F32_WRGB2 = F32_BRGB1 + 128, F32_WDENS = F32_WRGB2 + 384, F32_SEED = F32_WDENS + 256,
-                       F32_TOTAL = F32_SEED + 256;
+                       F32_TOTAL = F32_SEED + 128;
   float* bias0_slot() const { return d_f32; }
 
   void release() {
@@ -628,31 +734,37 @@ struct TcWeights {
     d_f32 = nullptr;
   }
 
-  // B[n][k] (rows x K) packed as slabs of `ksteps` k-steps:
-  //   [hi: (2*ksteps chunks) x rows x 8 halves][lo: same]   -- exactly the image the UMMA descriptors address
-  static void pack_op(std::vector<__half>& blob, TcOp& op, int kind, int a_src, int rows, int K, int ksteps, bool with_lo,
+  // B[n][k] ((rows + extra) x K) packed as slabs of `ksteps` k-steps; every slab is split between the two CTAs of a pair:
+  //   slab = [rank 0 half][rank 1 half], half = [hi: (2*ksteps chunks) x hrows x 8 halves][lo: same]
+  // where a half holds rows/2 "main" rows (n = rank*rows/2 + i) followed by extra/2 "extra" rows
+  // (n = rows + rank*extra/2 + i) -- exactly the image the cta_group::2 UMMA descriptors address in each CTA.
+  static void pack_op(std::vector<__half>& blob, TcOp& op, int kind, int a_src, int rows, int extra, int K, int ksteps, bool with_lo,
                       const std::vector<float>& B) {
     const int n_slabs = K / (16 * ksteps);
-    const size_t part = (size_t)ksteps * 2 * rows * 8;  // halves per hi (or lo) part
-    const size_t slab = part * (with_lo ? 2 : 1);
+    const int hmain = rows / 2, hextra = extra / 2, hrows = hmain + hextra;
+    const size_t part = (size_t)ksteps * 2 * hrows * 8;  // halves per hi (or lo) part of one CTA's share
+    const size_t half = part * (with_lo ? 2 : 1);
     while (blob.size() % 64) blob.push_back(__float2half_rn(0.f));  // 128-byte aligned slabs
     op.src_off = (uint32_t)(blob.size() * sizeof(__half));
-    op.slab_bytes = (uint32_t)(slab * sizeof(__half));
+    op.slab_bytes = (uint32_t)(half * sizeof(__half));
     op.n_slabs = (uint16_t)n_slabs;
     op.ksteps = (uint16_t)ksteps;
     op.kind = (uint8_t)kind;
     op.a_src = (uint8_t)a_src;
     op.pad[0] = op.pad[1] = 0;
     const size_t base = blob.size();
-    blob.resize(base + slab * n_slabs);
-    for (int n = 0; n < rows; ++n)
-      for (int k = 0; k < K; ++k) {
-        const int s = k / (16 * ksteps), j = (k / 16) % ksteps, cc = (k % 16) / 8, e = k % 8;
-        const size_t off = base + (size_t)s * slab + ((size_t)(j * 2 + cc) * rows + n) * 8 + e;
-        const float w = B[(size_t)n * K + k];
-        const __half hh = __float2half_rn(w);
-        blob[off] = hh;
-        if (with_lo) blob[off + part] = __float2half_rn(w - __half2float(hh));
+    blob.resize(base + 2 * half * n_slabs);
+    for (int r = 0; r < 2; ++r)
+      for (int i = 0; i < hrows; ++i) {
+        const int n = i < hmain ? r * hmain + i : rows + r * hextra + (i - hmain);
+        for (int k = 0; k < K; ++k) {
+          const int s = k / (16 * ksteps), j = (k / 16) % ksteps, cc = (k % 16) / 8, e = k % 8;
+          const size_t off = base + ((size_t)s * 2 + r) * half + ((size_t)(j * 2 + cc) * hrows + i) * 8 + e;
+          const float w = B[(size_t)n * K + k];
+          const __half hh = __float2half_rn(w);
+          blob[off] = hh;
+          if (with_lo) blob[off + part] = __float2half_rn(w - __half2float(hh));
+        }
       }
   }
 
@@ -665,39 +777,47 @@ struct TcWeights {
     std::vector<__half> blob;
     std::vector<float> B;
     int oi = 0;
-    // forward layers 0..6: N = 256, 3-pass (hi + lo), one k-step per 16 KB slab
+    // forward layers 0..6: N = 256, 3-pass (hi + lo), two k-steps per slab (16 KB per CTA)
     for (int l = 0; l < 7; ++l) {
       const int in_dim = l == 0 ? 87 : (l == 4 ? 319 : 256);
       const int K = l == 0 ? 64 : (l == 4 ? 320 : 256);
       B.assign((size_t)256 * K, 0.f);
-      for (int n = 0; n < 256; ++n)
-        for (int k = 0; k < (l == 0 ? 63 : in_dim); ++k) B[(size_t)n * K + k] = (*W[l])[(size_t)n * in_dim + (l == 0 ? 8 + k : k)];
-      pack_op(blob, ops[oi++], K_FWD, l == 0 ? A_PE : (l == 4 ? A_ACT_PE : A_ACT), 256, K, 1, true, B);
+      for (int n = 0; n < 256; ++n) {
+        if (l == 0) {
+          for (int k = 0; k < 63; ++k) B[(size_t)n * K + k] = w0[(size_t)n * 87 + 8 + k];
+        } else if (l == 4) {  // K order: [PE 0..62, pad | h 0..255] so that the PE k-steps are issued first
+          for (int k = 0; k < 63; ++k) B[(size_t)n * K + k] = w4[(size_t)n * 319 + 256 + k];
+          for (int k = 0; k < 256; ++k) B[(size_t)n * K + 64 + k] = w4[(size_t)n * 319 + k];
+        } else {
+          for (int k = 0; k < 256; ++k) B[(size_t)n * K + k] = (*W[l])[(size_t)n * in_dim + k];
+        }
+      }
+      pack_op(blob, ops[oi++], K_FWD, l == 0 ? A_PE : (l == 4 ? A_PE_ACT : A_ACT), 256, 0, K, 2, true, B);
     }
     // rgb head first layer: 256 -> 128
     B.assign((size_t)128 * 256, 0.f);
     for (int n = 0; n < 128; ++n)
       for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = wr1[(size_t)n * 256 + k];
-    pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 256, 2, true, B);
+    pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 0, 256, 4, true, B);
     // backward through layers 6..1: B[n][k] = W[k][n] (n = input index, k = output index), 1-pass
     for (int l = 6; l >= 1; --l) {
       if (l == 4) {  // 256 hidden inputs + 63 PE inputs (+1 pad): rows 256..319 feed the extra N = 64 MMA
         B.assign((size_t)320 * 256, 0.f);
         for (int n = 0; n < 319; ++n)
           for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = w4[(size_t)k * 319 + n];
-        pack_op(blob, ops[oi++], K_BW4, A_ACT, 320, 256, 1, false, B);
+        pack_op(blob, ops[oi++], K_BW4, A_ACT, 256, 64, 256, 2, false, B);
       } else {
         B.assign((size_t)256 * 256, 0.f);
         for (int n = 0; n < 256; ++n)
           for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = (*W[l])[(size_t)k * 256 + n];
-        pack_op(blob, ops[oi++], K_BWD, A_ACT, 256, 256, 2, false, B);
+        pack_op(blob, ops[oi++], K_BWD, A_ACT, 256, 0, 256, 4, false, B);
       }
     }
     // layer 0 backward, PE columns only (N = 64); added to the stashed layer-4 PE gradient in the tile's last stage
     B.assign((size_t)64 * 256, 0.f);
     for (int n = 0; n < 63; ++n)
       for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = w0[(size_t)k * 87 + 8 + n];
-    pack_op(blob, ops[oi++], K_BW0, A_ACT, 64, 256, 8, false, B);
+    pack_op(blob, ops[oi++], K_BW0, A_ACT, 64, 0, 256, 16, false, B);
     if (oi != TC_NUM_OPS) return (int)cudaErrorUnknown;
     for (int i = 0; i < TC_NUM_OPS; ++i)
       if (ops[i].slab_bytes > TC_STAGE_BYTES || (ops[i].slab_bytes & 31) || (ops[i].src_off & 15)) return (int)cudaErrorInvalidValue;
@@ -715,7 +835,11 @@ struct TcWeights {
     float mx = 0.f;
     for (int i = 0; i < 256; ++i) mx = fmaxf(mx, fabsf(wd[i]));
     seed_scale = mx > 0.f ? mx : 1.f;
-    for (int i = 0; i < 256; ++i) { f[F32_WDENS + i] = wd[i]; f[F32_SEED + i] = wd[i] / seed_scale; }
+    for (int i = 0; i < 256; ++i) f[F32_WDENS + i] = wd[i];
+    for (int i = 0; i < 128; ++i) {
+      __half2 h = __floats2half2_rn(wd[2 * i] / seed_scale, wd[2 * i + 1] / seed_scale);
+      memcpy(&f[F32_SEED + i], &h, 4);
+    }
     e = cudaMalloc(reinterpret_cast<void**>(&d_f32), f.size() * sizeof(float));
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(d_f32, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -729,7 +853,7 @@ struct TcWeights {
 
 inline void tc_configure() { cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM); }
 
-inline int tc_launch(TcWeights& w, long long* timing, const float4* active, const unsigned long long* n_active_ptr, int64_t n_active_host,
+inline int tc_launch(TcWeights& w, long long* timing, int debug_noload, const float4* active, const unsigned long long* n_active_ptr, int64_t n_active_host,
                      float4* out_a, float4* out_g, int density_only, int sm_count, cudaStream_t st) {
   TcParams p{};
   p.wpack = reinterpret_cast<const uint8_t*>(w.d_pack);
@@ -737,7 +861,7 @@ inline int tc_launch(TcWeights& w, long long* timing, const float4* active, cons
   p.b_rgb1 = w.d_f32 + TcWeights::F32_BRGB1;
   p.w_rgb2 = w.d_f32 + TcWeights::F32_WRGB2;
   p.w_dens = w.d_f32 + TcWeights::F32_WDENS;
-  p.seed = w.d_f32 + TcWeights::F32_SEED;
+  p.seed_h2 = reinterpret_cast<const uint32_t*>(w.d_f32 + TcWeights::F32_SEED);
   for (int i = 0; i < 3; ++i) p.b_rgb2[i] = w.b_rgb2[i];
   p.b_dens = w.b_dens;
   p.seed_scale = w.seed_scale;
@@ -748,7 +872,8 @@ inline int tc_launch(TcWeights& w, long long* timing, const float4* active, cons
   p.out_g = out_g;
   p.density_only = density_only;
   p.timing = timing;
-  mlp_tc_kernel<<<sm_count / TC_CLUSTER * TC_CLUSTER, TC_THREADS, TC_SMEM, st>>>(p);
+  p.debug_noload = debug_noload;
+  mlp_tc_kernel<<<sm_count & ~1, TC_THREADS, TC_SMEM, st>>>(p);  // CTA pairs (__cluster_dims__(2,1,1))
   return (int)cudaGetLastError();
 }
 

@@ -10,7 +10,7 @@ cfg = SimpleNamespace(MODEL=SimpleNamespace(TYPE="nerf", COARSE_RAY_SAMPLING=64,
 r = Renderer(N.synthetic_net(0), None, cfg, torch.from_numpy(sc["canonical"]), device=0, faces=sc["faces"])
 r.eval()
 for _ in range(3): r.render(S.to_batch(sc, torch))
-r.ctx.profile(4)
+r.ctx.profile(4 | int(os.environ.get("DSNERF_DEBUG_PROFILE_BITS", "0")))
 r.render(S.to_batch(sc, torch)); torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 128)()
 r.ctx.check(r.ctx.L.dsnerf_debug_tc_timing(r.ctx.h, buf))
@@ -19,8 +19,11 @@ names = ["L0","L1","L2","L3","L4","L5","L6","rgb1","bW6","bW5","bW4","bW3","bW2"
 print("op     accwait  q0+q1  q2+q3 (cycles)")
 prev = t[0]
 for op in range(15):
-    a0, a1, a2, a3 = t[1 + 4 * op], t[2 + 4 * op], t[3 + 4 * op], t[4 + 4 * op]
-    print(f"{names[op]:6s} {a0 - prev:8d} {a1 - a0:8d} {a3 - a2:8d}")
+    a0, a1, a3 = t[1 + 4 * op], t[2 + 4 * op], t[3 + 4 * op]
+    if op == 14:
+        print(f"{names[op]:6s} (consumed by the tile-output stage)")
+        break
+    print(f"{names[op]:6s} {a0 - prev:8d} {a1 - a0:8d} {a3 - a1:8d}")
     prev = a3
 print("tile total", t[62] - t[0])
 print("MMA thread per op: wait_full  wait_a  total_issue_loop")

@@ -10,7 +10,9 @@
 //     rounding-sized change of a pre-activation flips ReLUs of the gradient path;
 //   * the backward-data chain for the normal runs single-pass fp16 through W^T using the ReLU bits
 //     recorded in the forward pass; the seed is w_dens / max|w_dens| so every gradient stays inside
-//     fp16 range (the normal is scale invariant).
+//     fp16 range (the normal is scale invariant);
+//   * the rgb head's 256 -> 128 layer runs single-pass fp16 as well: the essence enters the colour linearly and is
+//     not amplified by the density head (oracle emulation: max |d rgb| 2.9e-5 vs 2.7e-5 with 3 passes).
 //
 // Pipeline (CTA pair = two SMs of one TPC, cta_group::2; 18 warps per CTA)
 //   * measured on B200 (profiles/): an MMA whose A operand comes from shared memory occupies the tensor pipe for
@@ -71,7 +73,8 @@ constexpr uint32_t TM_ACC = 256;    // accumulator b (= op & 1) starts at column
 constexpr uint32_t TM_COLS = 512;
 
 constexpr int TC_NUM_OPS = 15;
-enum { A_ACT = 0, A_PE = 1, A_PE_ACT = 2 };  // A_PE_ACT: k-steps 0..3 come from the PE region, the rest from the activations
+enum { A_ACT = 0, A_PE = 1, A_PE_ACT = 2, A_ACT_LO = 3 };  // A_PE_ACT: k-steps 0..3 come from the PE region, the rest from the activations;
+                                                            // A_ACT_LO: operand parked in the A-lo region (seed of the backward chain)
 
 enum { K_FWD = 0, K_RGB = 1, K_BWD = 2, K_BW4 = 3, K_BW0 = 4 };
 
@@ -80,8 +83,8 @@ struct TcOp {
   uint32_t slab_bytes;  // bytes per slab HALF (one CTA's share, <= TC_STAGE_BYTES, multiple of 32); a slab = [rank 0 half][rank 1 half]
   uint16_t n_slabs;
   uint16_t ksteps;      // k-steps (of 16) per slab
-  uint8_t kind;         // K_FWD (N=256, 3-pass), K_RGB (N=128, 3-pass), K_BWD (N=256), K_BW4 (N=256 + 64 extra), K_BW0 (N=64)
-  uint8_t a_src;        // A_ACT, A_PE, A_PE_ACT
+  uint8_t kind;         // K_FWD (N=256, 3-pass), K_RGB (N=128, 1-pass), K_BWD (N=256), K_BW4 (N=256 + 64 extra), K_BW0 (N=64)
+  uint8_t a_src;        // A_ACT, A_PE, A_PE_ACT, A_ACT_LO
   uint8_t pad[2];
 };
 
@@ -288,8 +291,8 @@ __device__ __forceinline__ void run_op(MmaState& ms, int n_slabs, int a_src, uin
   constexpr uint32_t A_LBO = (A_CHUNK >> 4) << 16;          // LBO field of every A descriptor
   constexpr uint32_t B_LBO = ((ROWS * 16) >> 4) << 16;
   if (a_src == A_PE) ms.need_quarters(4);
-  const uint32_t pe_steps = a_src == A_ACT ? 0u : 4u;        // leading k-steps served by the PE region
-  const uint32_t a_hi0 = A_LBO | ((ms.sbase + SM_A_HI) >> 4), a_lo0 = A_LBO | ((ms.sbase + SM_A_LO) >> 4);
+  const uint32_t pe_steps = (a_src == A_PE || a_src == A_PE_ACT) ? 4u : 0u;  // leading k-steps served by the PE region
+  const uint32_t a_hi0 = A_LBO | ((ms.sbase + (a_src == A_ACT_LO ? SM_A_LO : SM_A_HI)) >> 4), a_lo0 = A_LBO | ((ms.sbase + SM_A_LO) >> 4);
   const uint32_t p_hi0 = A_LBO | ((ms.sbase + SM_PE_HI) >> 4), p_lo0 = A_LBO | ((ms.sbase + SM_PE_LO) >> 4);
   uint32_t kk = 0;
   for (int s = 0; s < n_slabs; ++s, kk += KSTEPS) {
@@ -396,10 +399,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         const long long t_op0 = mstamp ? clock64() : 0;
         const uint32_t d_main = tmem + (uint32_t)(op & 1) * TM_ACC;
         const uint32_t d_extra = tmem + (uint32_t)((op & 1) ^ 1) * TM_ACC;
-        ms.waited = 0;
+        ms.waited = op == 8 ? 4 : 0;  // op 8 (bW6) reads the seed that layer 6's epilogue published together with h6 (consumed by op 7)
         switch (o.kind) {
           case K_FWD: run_op<128, 2, true, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
-          case K_RGB: run_op<64, 4, true, 128, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_RGB: run_op<64, 8, false, 128, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
           case K_BWD: run_op<128, 4, false, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
           case K_BW4: run_op<160, 2, false, 256, true>(ms, o.n_slabs, o.a_src, d_main, d_extra); break;
           default: run_op<32, 16, false, 64, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
@@ -407,7 +410,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         ms.need_quarters(4);
         if (elect_one()) tc_commit2(bar_acc);  // accumulator (and the extra columns of K_BW4) complete, in both CTAs
         __syncwarp();
-        ms.a_phase ^= 1;
+        if (op != 8) ms.a_phase ^= 1;
         if (mstamp) { P.timing[64 + 3 * op] = 0; P.timing[65 + 3 * op] = 0; P.timing[66 + 3 * op] = clock64() - t_op0; }
       }
     }
@@ -487,38 +490,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       for (int op = 0; op < n_ops; ++op) {
         const uint32_t t_accb = t_lane + (uint32_t)(op & 1) * TM_ACC + sub * TC_CPT;
         if (op == 7) {
-          // ---------- seed of the backward chain: G6 = (w_dens / scale) * relu'(a6).  It overwrites h6 (A-hi), which the
-          // rgb head's MMAs (this op) read: wait for them, write all four quarters (bW6 can start), then do the rgb tail.
-          uint32_t m0, m1;
-          relu.get(6, m0, m1);
-          uint4 sd[4][2];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            sd[q4][0] = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2));
-            sd[q4][1] = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2 + 4));
-          }
+          // ---------- rgb head tail only.  Nothing is published: bW6 (op 8) already runs on the seed that layer 6's
+          // epilogue wrote next to h6.
           mbar_wait(bar_acc, acc_phase);
           acc_phase ^= 1;
           tc_fence_after();
-          if (stamp) P.timing[1 + 4 * op] = clock64();
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint32_t mw = (q4 >> 1) ? m1 : m0;
-            uint4 h0 = sd[q4][0], h1 = sd[q4][1];
-            const int pb = 8 * (q4 & 1);
-            if (pb == 0) {
-              h0.x &= relu_mask2<0>(mw); h0.y &= relu_mask2<1>(mw); h0.z &= relu_mask2<2>(mw); h0.w &= relu_mask2<3>(mw);
-              h1.x &= relu_mask2<4>(mw); h1.y &= relu_mask2<5>(mw); h1.z &= relu_mask2<6>(mw); h1.w &= relu_mask2<7>(mw);
-            } else {
-              h0.x &= relu_mask2<8>(mw); h0.y &= relu_mask2<9>(mw); h0.z &= relu_mask2<10>(mw); h0.w &= relu_mask2<11>(mw);
-              h1.x &= relu_mask2<12>(mw); h1.y &= relu_mask2<13>(mw); h1.z &= relu_mask2<14>(mw); h1.w &= relu_mask2<15>(mw);
-            }
-            const uint32_t off = (uint32_t)((q4 * 64 + sub * TC_CPT) / 8) * A_CHUNK + row_off;
-            *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = h0;
-            *reinterpret_cast<uint4*>(smem + SM_A_HI + off + A_CHUNK) = h1;
-            publish(q4);
-          }
-          if (stamp) P.timing[2 + 4 * op] = clock64();
+          if (stamp) { P.timing[1 + 4 * op] = clock64(); P.timing[2 + 4 * op] = clock64(); }
           // rgb head tail: relu(acc[0:128] + b) -> Linear(128,3) partials (model/spacenet.py:75-80); 2 x 16 columns per thread
           uint32_t v0[16], v1[16];
           tmem_ld16_nowait(t_accb, v0);
@@ -546,6 +523,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
               e2 = __ffma2_rn(make_float2(w2[i].x, w2[i].y), ra, e2); e2 = __ffma2_rn(make_float2(w2[i].z, w2[i].w), rb, e2);
             }
           }
+          tc_fence_before();
           if (stamp) { P.timing[3 + 4 * op] = clock64(); P.timing[4 + 4 * op] = clock64(); }
           continue;
         }
@@ -568,9 +546,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         uint32_t va[16], vb[16];
         tmem_ld16_nowait(t_accb, va);
         if (op <= 6) {
-          // ---------- forward layer: bias + ReLU, record ReLU bits, split to fp16 hi / lo = next A operand (in place)
+          // ---------- forward layer: bias + ReLU, record ReLU bits, split to fp16 hi / lo = next A operand (in place).
+          // Layer 6 feeds the single-pass rgb head (hi only) and the density head (fp32, here); instead of the lo part it
+          // writes the seed of the backward chain G6 = (w_dens / scale) * relu'(a6) into the A-lo region (op 8's operand).
           const float* __restrict__ bias = P.bias + op * 256 + sub * TC_CPT;
           const float* __restrict__ wdp = P.w_dens + sub * TC_CPT;
+          const bool last6 = op == 6;
           uint32_t mw0 = 0, mw1 = 0;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -578,6 +559,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             float4 b[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + q4 * 64) + i);
+            uint4 sd0 = make_uint4(0u, 0u, 0u, 0u), sd1 = sd0;
+            if (last6) {
+              sd0 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2));
+              sd1 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2 + 4));
+            }
+            const uint32_t sd[8] = {sd0.x, sd0.y, sd0.z, sd0.w, sd1.x, sd1.y, sd1.z, sd1.w};
             tmem_wait_ld(v);
             if (q4 < 3) { if (q4 & 1) tmem_ld16_nowait(t_accb + (q4 + 1) * 64, va); else tmem_ld16_nowait(t_accb + (q4 + 1) * 64, vb); }
             uint32_t hi[8], lo[8];
@@ -589,20 +576,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
               float2 h = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
               h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
               const __half2 hh = __floats2half2_rn(h.x, h.y);
-              const float2 hf = __half22float2(hh);
-              const float2 l = __ffma2_rn(hf, make_float2(-1.f, -1.f), h);  // exact: x = hi + lo up to 2^-22 relative
               hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
-              lo[j] = pack_h2(l.x, l.y);
               // ReLU bit = (hi > 0); an activation below the fp16 subnormal range is 0 for the forward pass and the gradient alike
+              const uint32_t m2 = __hgt2_mask(hh, as_h2(0u));
               const int p = j + 8 * (q4 & 1);
-              mw |= __hgt2_mask(hh, as_h2(0u)) & ((1u << p) | (1u << (16 + p)));
-              if (op == 6) {
+              mw |= m2 & ((1u << p) | (1u << (16 + p)));
+              if (last6) {
                 const float2 wd = __ldg(reinterpret_cast<const float2*>(wdp + q4 * 64 + 2 * j));
                 sig2 = __ffma2_rn(wd, h, sig2);
+                lo[j] = sd[j] & m2;
+              } else {
+                const float2 hf = __half22float2(hh);
+                const float2 l = __ffma2_rn(hf, make_float2(-1.f, -1.f), h);  // exact: x = hi + lo up to 2^-22 relative
+                lo[j] = pack_h2(l.x, l.y);
               }
             }
             if (q4 >> 1) mw1 |= mw; else mw0 |= mw;
-            if (op != n_ops - 1) {  // density-only mode ends here: nothing consumes the operand (and the exchange area aliases A-lo)
+            if (op != n_ops - 1) {  // density-only mode ends at layer 6: nothing consumes the operand (and the exchange area aliases A-lo)
               const uint32_t off = (uint32_t)((q4 * 64 + sub * TC_CPT) / 8) * A_CHUNK + row_off;
               *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(smem + SM_A_HI + off + A_CHUNK) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -798,7 +788,7 @@ struct TcWeights {
     B.assign((size_t)128 * 256, 0.f);
     for (int n = 0; n < 128; ++n)
       for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = wr1[(size_t)n * 256 + k];
-    pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 0, 256, 4, true, B);
+    pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 0, 256, 8, false, B);
     // backward through layers 6..1: B[n][k] = W[k][n] (n = input index, k = output index), 1-pass
     for (int l = 6; l >= 1; --l) {
       if (l == 4) {  // 256 hidden inputs + 63 PE inputs (+1 pad): rows 256..319 feed the extra N = 64 MMA
@@ -810,7 +800,7 @@ struct TcWeights {
         B.assign((size_t)256 * 256, 0.f);
         for (int n = 0; n < 256; ++n)
           for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = (*W[l])[(size_t)k * 256 + n];
-        pack_op(blob, ops[oi++], K_BWD, A_ACT, 256, 0, 256, 4, false, B);
+        pack_op(blob, ops[oi++], K_BWD, l == 6 ? A_ACT_LO : A_ACT, 256, 0, 256, 4, false, B);
       }
     }
     // layer 0 backward, PE columns only (N = 64); added to the stashed layer-4 PE gradient in the tile's last stage

@@ -47,64 +47,59 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  Polls NVML (the library behind
-    nvidia-smi) from a thread every 50 ms; falls back to one `nvidia-smi --query-gpu` call if pynvml is unavailable."""
+    """SM clock and throttle reasons DURING the timed region, the way B200_PROFILING.md prescribes: an `nvidia-smi
+    --query-gpu ... -lms` child process started before the region and killed after it.  (An in-process NVML polling
+    thread was measured to stretch the timed region by 2-30 ms per step: its queries serialise with kernel launches.)"""
 
-    def __init__(self, index):
-        self.index = index
-        self.sm, self.mx, self.reasons = [], [], set()
-        self._stop = threading.Event()
-        self.t = None
-        self.nv = None
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index, period_ms=100):
+        self.index, self.period_ms, self.proc, self.t0, self.t1 = index, period_ms, None, None, None
 
     def start(self):
         try:
-            import pynvml as nv
-
-            nv.nvmlInit()
-            self.nv = nv
-            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self.nv = None
+            self.proc = None
 
-    def _poll(self):
-        nv = self.nv
-        names = {
-            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
-            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
-            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
-            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
-        }
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+    def mark(self, which):  # wall-clock bounds of the timed region
+        if which == 0:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def stop(self):
-        if self.nv is None:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            out = ""
+        import datetime
+
+        rows = []
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
             try:
-                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=10).stdout.strip().split(",")
-                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[4:8]))
             except Exception:
-                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
-        self._stop.set()
-        if self.t:
-            self.t.join(timeout=2)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML polled every 50 ms during the timed region"}
+                continue
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        # a short region may fall between two samples: then take the samples that bracket it
+        use = inside if inside else sorted(rows, key=lambda r: min(abs(r[0] - self.t0), abs(r[0] - self.t1)))[:2]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in use for n, v in zip(names, r[4]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": max(r[2] for r in use), "power_w": max(r[3] for r in use),
+                "reasons": reasons, "samples": len(use), "samples_inside_region": len(inside),
+                "source": f"nvidia-smi --query-gpu -lms {self.period_ms} child process running across the timed region"}
 
 
 def cpu_port(rays_per_step, steps, warmup, sc=None, sd=None):
@@ -244,26 +239,46 @@ def main():
         step_device()
     torch.cuda.synchronize()
     st = ctx.stats()
-    launches_per_step = st["kernel_launches"] + 5  # + the five grid-build kernels of dsnerf_set_frame
+    launches_per_step = st["kernel_launches"] + 1  # render + per-frame grid build (counted by the library) + the clock probe
     evaluated = st["evaluated_samples"]
 
     ctx.profile(1 | int(os.environ.get('DSNERF_DEBUG_PROFILE_BITS', '0')))
     ctx.profile_read(reset=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    # SM clock inside the timed region: a 30 us one-warp probe kernel per step on the launch stream (clock64 vs global timer).
+    # NVML / nvidia-smi queries are NOT issued inside the timed region: each one was measured to stall kernel launches for
+    # 30-100 ms on this driver (ms_per_step 13.8 -> 23..88 ms); throttle reasons and power are sampled during an identical,
+    # untimed repeat of the region right after it.
+    d_clk = torch.zeros(args.steps, 2, device=dev)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for i in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (inside the bracket: ~0.1 ms of 256 MB writes per step)
         step_device()
+        ctx.check(L.dsnerf_debug_sm_clock(ctx.h, ctypes.c_void_p(d_clk.data_ptr() + 8 * i), sp))
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     mlp_ms, mlp_n = ctx.profile_read(reset=True)
     ctx.profile(0)
+    probe = d_clk.cpu().numpy()
+    sampler = ClockSampler(local_rank)
+    if not os.environ.get('DSNERF_NO_CLOCK_SAMPLER'):
+        sampler.start()
+        time.sleep(0.4)
+        sampler.mark(0)
+        t_rep = time.time()
+        while time.time() - t_rep < 1.0:  # identical load, untimed, long enough for several samples
+            flush.fill_(1)
+            step_device()
+            torch.cuda.synchronize()
+        sampler.mark(1)
+    clocks = sampler.stop()
+    clocks["sm_mhz_nvidia_smi_repeat"] = clocks.get("sm_mhz")
+    clocks["sm_mhz"] = float(np.median(probe[:, 0]))
+    clocks["sm_mhz_min"] = float(probe[:, 0].min())
+    clocks["source"] = ("sm_mhz: clock64/globaltimer probe kernel after every timed step (inside the timed region); reasons, power, "
+                        "sm_max_mhz: " + str(clocks.get("source")) + " during an untimed repeat of the same loop")
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

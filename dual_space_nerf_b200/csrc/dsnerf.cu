@@ -40,9 +40,13 @@ struct DevBuf {
 
 struct MeshGrid {
   Grid g{};
-  int ncell = 0;
-  DevBuf cent, tri_n, counts, start, cursor, sorted, cdist, cidx, rowmask, dc0, idx0, dc1, idx1;
-  void release() { cent.release(); tri_n.release(); counts.release(); start.release(); cursor.release(); sorted.release(); cdist.release(); cidx.release(); rowmask.release(); dc0.release(); idx0.release(); dc1.release(); idx1.release(); }
+  int ncell = 0, ntab = 0;
+  int launches = 0;  // kernels of the last build_grid
+  DevBuf cent, tri_n, counts, start, cursor, sorted, rowmask, seed_a, seed_b, tstate, trec, pool, pool_used, req, efar, estate, ereq;
+  void release() {
+    DevBuf* b[] = {&cent, &tri_n, &counts, &start, &cursor, &sorted, &rowmask, &seed_a, &seed_b, &tstate, &trec, &pool, &pool_used, &req, &efar, &estate, &ereq};
+    for (DevBuf* x : b) x->release();
+  }
 };
 
 // state_dict order
@@ -169,8 +173,11 @@ float transparency_radius(const float* verts, const int32_t* faces, int F) {
   return (float)(sqrt(0.1 * 0.1 + best) * 1.002 + 1e-4);
 }
 
-// (Re)build the nearest-centroid grid of a mesh: centroids, counting sort by cell, cell-centre
-// distance table.  h_verts is the host copy (bbox and r_cap are computed on the host).
+// (Re)build the nearest-centroid grid of a mesh: centroids, counting sort by cell, jump-flooded seeds; the lookup table
+// is only reset here (its cells are built on demand, see ensure_cells).  h_verts is the host copy (bbox and r_cap are
+// computed on the host).
+constexpr int kPoolEntries = 4 << 20;  // candidate-list pool per mesh (float4 entries, 64 MB)
+
 int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float* h_verts, int classify, cudaStream_t st) {
   const int F = ctx->F, V = ctx->V;
   float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
@@ -197,10 +204,11 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   g.tnx = 2 * g.nx; g.tny = 2 * g.ny; g.tnz = 2 * g.nz;
   g.thalf_diag = 0.5f * cell * 0.8660254f * 1.0001f;
   g.r_cap = r_cap;
+  g.classify = classify;
+  g.F = F;
   mg.ncell = g.nx * g.ny * g.nz;
-  const int nrow = g.ny * g.nz, ntab = 8 * mg.ncell;
-  const float cell0 = 2.0f * cell;  // level-0 lattice: 4 table cells per edge
-  const int n0x = (g.nx + 1) / 2, n0y = (g.ny + 1) / 2, n0z = (g.nz + 1) / 2, n0 = n0x * n0y * n0z;
+  mg.ntab = 8 * mg.ncell;
+  const int nrow = g.ny * g.nz;
   CK(mg.cent.ensure(sizeof(float) * 3 * F));
   CK(mg.tri_n.ensure(sizeof(float4) * F));
   CK(mg.counts.ensure(sizeof(int) * mg.ncell));
@@ -208,41 +216,80 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CK(mg.cursor.ensure(sizeof(int) * mg.ncell));
   CK(mg.sorted.ensure(sizeof(float4) * F));
   CK(mg.rowmask.ensure(sizeof(unsigned long long) * nrow));
-  CK(mg.cdist.ensure(sizeof(float) * ntab));
-  CK(mg.cidx.ensure(sizeof(int) * ntab));
-  CK(mg.dc0.ensure(sizeof(float) * n0));
-  CK(mg.idx0.ensure(sizeof(int) * n0));
-  CK(mg.dc1.ensure(sizeof(float) * mg.ncell));
-  CK(mg.idx1.ensure(sizeof(int) * mg.ncell));
+  CK(mg.seed_a.ensure(sizeof(int) * mg.ncell));
+  CK(mg.seed_b.ensure(sizeof(int) * mg.ncell));
+  CK(mg.tstate.ensure((size_t)mg.ntab + 4));
+  CK(mg.trec.ensure(sizeof(int2) * (size_t)mg.ntab));
+  CK(mg.req.ensure(sizeof(int) * (size_t)mg.ntab));
+  CK(mg.efar.ensure((size_t)mg.ncell + 4));
+  CK(mg.estate.ensure((size_t)mg.ncell + 4));
+  CK(mg.ereq.ensure(sizeof(int) * (size_t)mg.ncell));
+  CK(mg.pool.ensure(sizeof(float4) * (size_t)kPoolEntries));
+  CK(mg.pool_used.ensure(sizeof(int) * 16));
   g.cell_start = mg.start.as<int>();
   g.sorted = mg.sorted.as<float4>();
   g.row_mask = mg.rowmask.as<unsigned long long>();
-  g.center_dist = mg.cdist.as<float>();
-  g.center_idx = mg.cidx.as<int>();
   g.cent = mg.cent.as<float>();
+  g.tri_n = mg.tri_n.as<float4>();
+  g.tstate = mg.tstate.as<unsigned char>();
+  g.trec = mg.trec.as<int2>();
+  g.pool = mg.pool.as<float4>();
+  g.pool_cap = kPoolEntries;
+  g.pool_used = mg.pool_used.as<int>();
+  g.req = mg.req.as<int>();
+  g.enum_far = mg.efar.as<unsigned char>();
+  g.estate = mg.estate.as<unsigned char>();
+  g.ereq = mg.ereq.as<int>();
+  g.debug = (ctx->profile & 2) ? 1 : 0;
   int fb = (F + 255) / 256;
   centroid_kernel<<<fb, 256, 0, st>>>(d_verts, ctx->faces.as<int>(), F, mg.cent.as<float>(), mg.tri_n.as<float4>());
   CKL("centroid");
   CK(cudaMemsetAsync(mg.counts.p, 0, sizeof(int) * mg.ncell, st));
   CK(cudaMemsetAsync(mg.rowmask.p, 0, sizeof(unsigned long long) * nrow, st));
+  CK(cudaMemsetAsync(mg.tstate.p, 0, (size_t)mg.ntab + 4, st));
+  CK(cudaMemsetAsync(mg.estate.p, 0, (size_t)mg.ncell + 4, st));
+  CK(cudaMemsetAsync(mg.pool_used.p, 0, sizeof(int) * 16, st));
   grid_count_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.counts.as<int>(), mg.rowmask.as<unsigned long long>());
   CKL("grid_count");
   grid_scan_kernel<<<1, 1024, 0, st>>>(mg.counts.as<int>(), mg.ncell, mg.start.as<int>(), mg.cursor.as<int>());
   CKL("grid_scan");
   grid_fill_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.cursor.as<int>(), mg.sorted.as<float4>());
   CKL("grid_fill");
-  table_coarse_kernel<<<(n0 + 255) / 256, 256, 0, st>>>(g.ox, g.oy, g.oz, cell0, n0x, n0y, n0z, mg.cent.as<float>(), mg.tri_n.as<float4>(), F,
-                                                        classify, r_cap, mg.dc0.as<float>(), mg.idx0.as<int>());
-  CKL("table_coarse");
-  // level 1 (enumeration-cell resolution) seeded by level 0, then the lookup table (level 2) seeded by level 1
-  TableLevel l1{cell, cell * 0.8660254f * 1.0001f, g.nx, g.ny, g.nz};
-  table_level_kernel<<<(mg.ncell + TABLE_THREADS - 1) / TABLE_THREADS, TABLE_THREADS, 0, st>>>(g, l1, mg.tri_n.as<float4>(), n0x, n0y, n0z, mg.dc0.as<float>(), mg.idx0.as<int>(),
-                                                           classify, mg.dc1.as<float>(), mg.idx1.as<int>());
-  CKL("table_level1");
-  TableLevel l2{0.5f * cell, g.thalf_diag, g.tnx, g.tny, g.tnz};
-  table_level_kernel<<<(ntab + TABLE_THREADS - 1) / TABLE_THREADS, TABLE_THREADS, 0, st>>>(g, l2, mg.tri_n.as<float4>(), g.nx, g.ny, g.nz, mg.dc1.as<float>(), mg.idx1.as<int>(),
-                                                       classify, mg.cdist.as<float>(), mg.cidx.as<int>());
-  CKL("table_level2");
+  // seeds: jump flooding over the enumeration grid (approximate nearest centroid per cell; exactness comes from the scans)
+  const int cb = (mg.ncell + 255) / 256;
+  int* sa = mg.seed_a.as<int>();
+  int* sb = mg.seed_b.as<int>();
+  jfa_init_kernel<<<cb, 256, 0, st>>>(g, sa);
+  CKL("jfa_init");
+  int top = 1;
+  while (top * 2 < std::max(g.nx, std::max(g.ny, g.nz))) top *= 2;
+  for (int step = top; step >= 1; step >>= 1) {
+    jfa_pass_kernel<<<cb, 256, 0, st>>>(g, step, sa, sb);
+    CKL("jfa_pass");
+    std::swap(sa, sb);
+  }
+  jfa_pass_kernel<<<cb, 256, 0, st>>>(g, 1, sa, sb);
+  CKL("jfa_pass");
+  std::swap(sa, sb);
+  g.enum_seed = sa;
+  mg.launches = 4 + 1 + 1 + 1;  // centroid/count/scan/fill, jfa_init, final jfa pass, enum_far
+  for (int step = top; step >= 1; step >>= 1) ++mg.launches;
+  // enumeration cells provably farther than r_cap from every centroid (never requested, never searched)
+  enum_far_kernel<<<cb, 256, 0, st>>>(g, (int)ceil(r_cap / cell) + 2, mg.efar.as<unsigned char>());
+  CKL("enum_far");
+  return 0;
+}
+
+// Build the lookup-table cells requested by a mark kernel (launched by the caller through `mark`).
+template <class Mark>
+int ensure_cells(dsnerf_ctx* ctx, MeshGrid& mg, cudaStream_t st, Mark&& mark) {
+  CK(cudaMemsetAsync(mg.pool_used.as<int>() + 1, 0, 2 * sizeof(int), st));
+  mark();
+  CKL("mark");
+  build_cells_kernel<1><<<ctx->sm_count * 8, BUILD_WARPS * 32, 0, st>>>(mg.g);  // per requested enumeration cell
+  CKL("build_cells<1>");
+  build_cells_kernel<2><<<ctx->sm_count * 8, BUILD_WARPS * 32, 0, st>>>(mg.g);
+  CKL("build_cells<2>");
   return 0;
 }
 
@@ -346,6 +393,11 @@ int check_ready(dsnerf_ctx* ctx, bool need_frame) {
 }
 
 int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStream_t st) {
+  // canonical-space lookup cells of the active points (static mesh: cells stay built across frames)
+  if (int e = ensure_cells(ctx, ctx->g_canon, st, [&] {
+        mark_points_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(sa.active, sa.n_active, sa.n_active_host, ctx->g_canon.g);
+      }))
+    return e;
   if (flags & DSNERF_MLP_FP32_SIMT) {
     shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
     CKL("shade");
@@ -417,9 +469,13 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   wa.active = ctx->active.as<float4>(); wa.active_tri = ctx->active_tri.as<int>(); wa.sample_mask = ctx->ray_mask.as<unsigned>();
   wa.counters = cnt;
   wa.count_candidates = (ctx->profile & 2) ? 1 : 0;
+  if (int e = ensure_cells(ctx, ctx->g_posed, st, [&] {
+        mark_samples_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
+      }))
+    return e;
   sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
   CKL("sample_warp");
-  ++launches;
+  launches += 4;
   if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
   ++launches;
   ShadeArgs sa = base_shade_args(ctx);
@@ -428,7 +484,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   sa.ray_o = ray_o; sa.ray_d = ray_d; sa.near = near_use; sa.far = far_use; sa.z_in = z_in; sa.tvals = ctx->tvals.as<float>();
   sa.N = N;
   if (int e = launch_shade(ctx, sa, flags, st)) return e;
-  ++launches;
+  launches += 3;
   CompositeArgs ca{};
   ca.sample_mask = ctx->ray_mask.as<unsigned>();
   ca.raw = ctx->raw.as<float4>(); ca.ray_d = ray_d; ca.near = near_use; ca.far = far_use; ca.tvals = ctx->tvals.as<float>(); ca.z_in = z_in;
@@ -440,7 +496,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   CK(cudaEventRecord(ctx->stats_ready, st));
   ctx->stats.rays = R;
   ctx->stats.samples = P;
-  ctx->stats.kernel_launches = launches;
+  ctx->stats.kernel_launches = launches + ctx->g_posed.launches;  // incl. the per-frame grid build of dsnerf_set_frame
   return 0;
 }
 
@@ -826,6 +882,39 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
 int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
   if (!ctx) return DSNERF_ERR_INVALID;
   ctx->profile = enable & 31;
+  return 0;
+}
+
+namespace {
+// SM clock as the SM sees it: cycles of clock64 per nanosecond of the global timer over a ~30 us spin (one warp)
+__global__ void sm_clock_probe_kernel(float* __restrict__ out, unsigned spin_ns) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  long long c0 = clock64();
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < spin_ns);
+  long long c1 = clock64();
+  out[0] = (float)((double)(c1 - c0) * 1.0e3 / (double)(t1 - t0));
+  out[1] = (float)(t1 - t0) * 1e-3f;
+}
+}  // namespace
+
+int dsnerf_debug_sm_clock(dsnerf_ctx* ctx, float* d_out2, void* stream) {
+  if (!ctx || !d_out2) return DSNERF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  sm_clock_probe_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_out2, 30000u);
+  CKL("sm_clock_probe");
+  return 0;
+}
+
+int dsnerf_debug_table(dsnerf_ctx* ctx, int which, int* out16) {
+  if (!ctx || !out16) return DSNERF_ERR_INVALID;
+  MeshGrid& mg = which ? ctx->g_canon : ctx->g_posed;
+  if (!mg.pool_used.p) return DSNERF_ERR_STATE;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out16, mg.pool_used.p, sizeof(int) * 16, cudaMemcpyDeviceToHost));
+  out16[3] = mg.ncell;
+  out16[11] = mg.ntab;
   return 0;
 }
 

@@ -71,9 +71,26 @@ __device__ __forceinline__ V3 map_to_triangle(float u, float v, float h, V3 c0, 
 // ---------------------------------------------------------------------------------------------
 // Uniform grid over triangle centroids (one per mesh: posed = per frame, canonical = static).
 // Enumeration grid: cells are x-fastest, so a run of cells along x is one contiguous run of sorted
-// centroids; one 64-bit occupancy word per (z,y) row lets the scan skip empty rows and trim ranges.
-// Lookup table: twice as fine as the enumeration grid; per cell the distance from the cell centre
-// to its nearest centroid (or "provably transparent") and that centroid's index (search seed).
+// centroids; one 64-bit occupancy word per (z,y) row lets a scan skip empty rows and trim ranges.
+// Every enumeration cell also carries an approximate nearest centroid (jump flooding), the seed of
+// all exact searches.
+//
+// Lookup table: twice as fine as the enumeration grid and built LAZILY, only for the cells that the
+// points of a call actually fall into (mark_*_kernel -> build_cells_kernel).  A built cell holds
+//   * cnt == -1: every point of the cell is farther than r_cap from all centroids or PROVABLY
+//     transparent (posed mesh only) -> no search at all;
+//   * cnt >= 0: the CANDIDATE LIST of the cell, i.e. every centroid that can be the nearest one of
+//     some point of the cell (off = first entry in the pool, (x, y, z, bits(index)) each);
+//   * cnt == -2: list too long / pool exhausted -> exact ball scan seeded with centroid `off`.
+// Candidate filter: with c0 the nearest centroid of the cell centre x and a the cell's half edge,
+// f(p) = |p-c|^2 - |p-c0|^2 is linear in p, so its minimum over the cube is f(x) - 2a|c-c0|_1: c
+// can beat c0 (and hence be nearest) somewhere in the cell only if f(x) <= 2a|c-c0|_1.  All such c
+// lie within dmin + 2*half_diag of x.  The list is a superset of the possible exact winners (slack
+// covers fp32 rounding), so searching it with the reference arithmetic returns the same index as a
+// brute-force scan, ties included.
+// Transparency proof (posed): the signed plane distance h of a triangle is 1-Lipschitz and the
+// centroid lies in the plane, so |(x-c).n_c| > 0.1 + half_diag for every listed c implies |h| > 0.1
+// = max_dist of get_transparent_mask (utils/render_utils.py:103) for every point of the cell.
 struct Grid {
   float ox, oy, oz;     // origin of cell (0,0,0) of both lattices
   float cell, inv_cell; // enumeration cell edge
@@ -82,12 +99,24 @@ struct Grid {
   int tnx, tny, tnz;    // table cells (2nx, 2ny, 2nz)
   float thalf_diag;     // table cell half diagonal (rounded up)
   float r_cap;          // beyond this distance to the nearest centroid a point is provably transparent
+  int classify;         // 1: posed mesh (transparency proof), 0: canonical
+  int F;
   const int* __restrict__ cell_start;              // ncell+1
   const float4* __restrict__ sorted;               // (x,y,z,bits(idx)) sorted by cell
   const unsigned long long* __restrict__ row_mask; // (nz*ny) occupancy bits along x
   const float* __restrict__ cent;                  // (F,3) centroids by index
-  const float* __restrict__ center_dist;           // table: distance centre -> nearest centroid (huge = provably transparent)
-  const int* __restrict__ center_idx;              // table: index of that centroid
+  const float4* __restrict__ tri_n;                // (F) unit normals (classification only)
+  const int* __restrict__ enum_seed;               // per enumeration cell: approximately nearest centroid
+  const unsigned char* __restrict__ enum_far;      // per enumeration cell: 1 = every point of it is farther than r_cap from all centroids
+  unsigned char* __restrict__ estate;              // per enumeration cell (posed): 0 untouched, 1 requested, 2 certified transparent, 3 not certified
+  int* __restrict__ ereq;                          // requested enumeration cells of the current call (count in pool_used[2])
+  unsigned char* __restrict__ tstate;              // per table cell: 0 untouched, 1 requested, 2 built
+  int2* __restrict__ trec;                         // per table cell: (off, cnt), see above
+  float4* __restrict__ pool;                       // candidate lists
+  int pool_cap;
+  int* __restrict__ pool_used;                     // [0] entries used, [1] table-cell requests, [2] enumeration-cell requests, [4..10] debug counters
+  int* __restrict__ req;                           // requested table cells of the current call
+  int debug;                                       // count build outcomes in pool_used[4..10]
 };
 
 __global__ void centroid_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int F, float* __restrict__ cent,
@@ -191,199 +220,395 @@ __device__ __forceinline__ void scan_ball(const Grid& g, float px, float py, flo
   }
 }
 
-// ---- lookup-table construction ---------------------------------------------------------------
-// Level 0: brute force (tiled through shared memory) on a lattice 4x coarser than the table: nearest centroid of
-// every coarse cell centre.  Only seeds level 1.
-__global__ void table_coarse_kernel(float ox, float oy, float oz, float cell0, int n0x, int n0y, int n0z, const float* __restrict__ cent,
-                                    const float4* __restrict__ tri_n, int F, int classify, float r_cap, float* __restrict__ dc0,
-                                    int* __restrict__ idx0) {
-  __shared__ float sx[1024], sy[1024], sz[1024], snx[1024], sny[1024], snz[1024];
-  int n = n0x * n0y * n0z;
+// ---- seeds: approximately nearest centroid per enumeration cell (jump flooding) ------------------
+__global__ void jfa_init_kernel(Grid g, int* __restrict__ seed) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int cx = c % n0x, cy = (c / n0x) % n0y, cz = c / (n0x * n0y);
-  float px = ox + (cx + 0.5f) * cell0, py = oy + (cy + 0.5f) * cell0, pz = oz + (cz + 0.5f) * cell0;
-  float best = 3.0e38f;
-  int besti = 0;
-  for (int base = 0; base < F; base += 1024) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-      int f = base + i;
-      bool ok = f < F;
-      sx[i] = ok ? cent[3 * f] : 1.0e18f;
-      sy[i] = ok ? cent[3 * f + 1] : 1.0e18f;
-      sz[i] = ok ? cent[3 * f + 2] : 1.0e18f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int i = 0; i < 1024; ++i) {
-      float dx = px - sx[i], dy = py - sy[i], dz = pz - sz[i];
-      float d2 = dx * dx + dy * dy + dz * dz;
-      if (d2 < best) { best = d2; besti = base + i; }
-    }
-  }
-  float dc = sqrtf(best) * 1.00001f + 1e-7f;
-  // Same transparency proof as for the table cells, one level up: a certified coarse cell certifies every table cell inside
-  // it, which spares the far band (the most expensive scans) in table_fine_kernel.
-  const float hd0 = cell0 * 0.8660254f * 1.001f;
-  const float h_thr = 0.1f + hd0 + 1e-4f;
-  bool undecided = classify && (c < n) && (dc > h_thr) && (dc - hd0 <= r_cap);
-  bool search = (c < n) && (!classify || dc <= h_thr);
-  if (__syncthreads_or(undecided)) {
-    float thr = dc + 2.0f * hd0 + 1e-5f;
-    float thr2 = undecided ? thr * thr : -1.0f;
-    for (int base = 0; base < F; base += 1024) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-        int f = base + i;
-        bool ok = f < F;
-        float4 nq = ok ? tri_n[f] : make_float4(0.f, 0.f, 0.f, 0.f);
-        sx[i] = ok ? cent[3 * f] : 1.0e18f;
-        sy[i] = ok ? cent[3 * f + 1] : 1.0e18f;
-        sz[i] = ok ? cent[3 * f + 2] : 1.0e18f;
-        snx[i] = nq.x; sny[i] = nq.y; snz[i] = nq.z;
+  if (c >= g.nx * g.ny * g.nz) return;
+  int b = g.cell_start[c], e = g.cell_start[c + 1];
+  seed[c] = b < e ? __float_as_int(g.sorted[b].w) : -1;
+}
+__global__ void jfa_pass_kernel(Grid g, int step, const int* __restrict__ in, int* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.nx * g.ny * g.nz) return;
+  int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+  float px = g.ox + (cx + 0.5f) * g.cell, py = g.oy + (cy + 0.5f) * g.cell, pz = g.oz + (cz + 0.5f) * g.cell;
+  int best = in[c];
+  float bd = 3.0e38f;
+  if (best >= 0) { float dx = px - g.cent[3 * best], dy = py - g.cent[3 * best + 1], dz = pz - g.cent[3 * best + 2]; bd = dx * dx + dy * dy + dz * dz; }
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        int x = cx + dx * step, y = cy + dy * step, z = cz + dz * step;
+        if ((dx | dy | dz) == 0 || x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz) continue;
+        int cand = in[(z * g.ny + y) * g.nx + x];
+        if (cand < 0 || cand == best) continue;
+        float ex = px - g.cent[3 * cand], ey = py - g.cent[3 * cand + 1], ez = pz - g.cent[3 * cand + 2];
+        float d = ex * ex + ey * ey + ez * ez;
+        if (d < bd) { bd = d; best = cand; }
       }
-      __syncthreads();
-#pragma unroll 4
-      for (int i = 0; i < 1024; ++i) {
-        float dx = px - sx[i], dy = py - sy[i], dz = pz - sz[i];
-        if (dx * dx + dy * dy + dz * dz <= thr2) {
-          float h = dx * snx[i] + dy * sny[i] + dz * snz[i];
-          if (!(fabsf(h) > h_thr)) search = true;
-        }
-      }
-    }
-  }
-  // +huge marks a far or certified (provably transparent) coarse cell
-  if (c < n) { dc0[c] = (search && dc - hd0 <= r_cap) ? dc : 3.0e30f; idx0[c] = besti; }
+  out[c] = best;
 }
 
-// Finer levels, each seeded by its parent (cells twice as large): per cell the distance dc from the centre to its
-// nearest centroid (found through the enumeration grid) and that centroid's index; +huge when every point of the cell is
-// farther than r_cap from all centroids or PROVABLY transparent.  Proof: for p in the cell, its nearest centroid c*
-// satisfies |centre - c*| <= dc + 2*half_diag (candidate set), the signed plane distance h is 1-Lipschitz, so
-// |h*(centre)| > 0.1 + half_diag for every candidate implies |h*(p)| > 0.1 = max_dist of get_transparent_mask
-// (utils/render_utils.py:103).  A far/certified parent settles all its children.  The last level is the lookup table.
-struct TableLevel {
-  float cell, half_diag;
-  int nx, ny, nz;
-};
-
-constexpr int TABLE_THREADS = 256;
-
-__global__ void __launch_bounds__(TABLE_THREADS) table_level_kernel(Grid g, TableLevel lv, const float4* __restrict__ tri_n, int pnx, int pny, int pnz,
-                                                                    const float* __restrict__ p_dc, const int* __restrict__ p_idx, int classify,
-                                                                    float* __restrict__ out, int* __restrict__ out_idx) {
-  // Most cells are settled by their parent (far / certified); the others are compacted into a per-block queue so that the
-  // scans below run with full warps.
-  __shared__ int queue[TABLE_THREADS];
-  __shared__ int qn;
-  const int n = lv.nx * lv.ny * lv.nz;
-  const int c0 = blockIdx.x * TABLE_THREADS;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) qn = 0;
-  __syncthreads();
-  {
-    int c = c0 + threadIdx.x;
-    bool need = false;
-    if (c < n) {
-      int cx = c % lv.nx, cy = (c / lv.nx) % lv.ny, cz = c / (lv.nx * lv.ny);
-      int pc = (min(cz / 2, pnz - 1) * pny + min(cy / 2, pny - 1)) * pnx + min(cx / 2, pnx - 1);
-      if (p_dc[pc] > 1.0e29f) { out[c] = 3.0e30f; out_idx[c] = p_idx[pc]; }
-      else need = true;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, need);
-    if (m) {
-      int leader = __ffs(m) - 1, base = 0;
-      if (lane == leader) base = atomicAdd(&qn, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (need) queue[base + __popc(m & ((1u << lane) - 1))] = threadIdx.x;
+// Exact far test per enumeration cell: for a point p of cell A and a centroid q of occupied cell B the per-axis gap is at
+// least max(0, |A_k - B_k| - 1) cells, so cell^2 * min_B sum_k max(0, |A_k - B_k| - 1)^2 > r_cap^2 proves that every point of
+// A is farther than r_cap from all centroids (=> transparent, see transparency_radius).  Rows are searched through the
+// occupancy words (nearest set bit on either side of the cell's x).
+__global__ void enum_far_kernel(Grid g, int window, unsigned char* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.nx * g.ny * g.nz) return;
+  int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+  const float need = (g.r_cap * 1.0002f + 1e-5f) * g.inv_cell;
+  const float need2 = need * need;
+  bool far = true;
+  for (int z = max(0, cz - window); z <= min(g.nz - 1, cz + window) && far; ++z) {
+    int gz = max(0, abs(z - cz) - 1);
+    for (int y = max(0, cy - window); y <= min(g.ny - 1, cy + window); ++y) {
+      unsigned long long m = __ldg(g.row_mask + z * g.ny + y);
+      if (!m) continue;
+      int gy = max(0, abs(y - cy) - 1);
+      // nearest set bit at or below cx, and at or above cx
+      unsigned long long lo = m & (cx >= 63 ? ~0ull : ((2ull << cx) - 1ull)), hi = m & (~0ull << cx);
+      int dx = 1 << 20;
+      if (lo) dx = min(dx, cx - (63 - __clzll((long long)lo)));
+      if (hi) dx = min(dx, (__ffsll((long long)hi) - 1) - cx);
+      int gx = max(0, dx - 1);
+      if ((float)(gx * gx + gy * gy + gz * gz) <= need2) { far = false; break; }
     }
   }
-  __syncthreads();
-  if (threadIdx.x >= qn) return;
-  const int c = c0 + queue[threadIdx.x];
-  int cx = c % lv.nx, cy = (c / lv.nx) % lv.ny, cz = c / (lv.nx * lv.ny);
-  float px = g.ox + (cx + 0.5f) * lv.cell, py = g.oy + (cy + 0.5f) * lv.cell, pz = g.oz + (cz + 0.5f) * lv.cell;
-  int pc = (min(cz / 2, pnz - 1) * pny + min(cy / 2, pny - 1)) * pnx + min(cx / 2, pnx - 1);
-  int seed = p_idx[pc];
-  float sx = px - g.cent[3 * seed], sy = py - g.cent[3 * seed + 1], sz = pz - g.cent[3 * seed + 2];
-  float best = sx * sx + sy * sy + sz * sz;
-  int besti = seed;
-  float rho2 = best * 1.0001f + 1e-12f;
-  scan_ball(g, px, py, pz, sqrtf(rho2) * 1.0001f, rho2, [&](float4 q) {
-    float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-    float d2 = dx * dx + dy * dy + dz * dz;
-    if (d2 < best) { best = d2; besti = __float_as_int(q.w); rho2 = best * 1.0001f + 1e-12f; }
-  });
-  float dc = sqrtf(best) * 1.00001f + 1e-7f;
-  out_idx[c] = besti;
-  if (dc - lv.half_diag > g.r_cap) { out[c] = 3.0e30f; return; }
-  const float h_thr = 0.1f + lv.half_diag * 1.001f + 1e-4f;
-  bool search = !classify || dc <= h_thr;  // the nearest centroid itself is a candidate with |h| <= dc
-  if (!search) {
-    float thr = dc + 2.0f * lv.half_diag * 1.001f + 1e-5f;
-    float thr2 = thr * thr;
-    float live2 = thr2;  // set negative to cut the scan short once the cell is known to need searching
-    scan_ball(g, px, py, pz, thr * 1.0001f, live2, [&](float4 q) {
-      float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-      if (dx * dx + dy * dy + dz * dz <= thr2) {
-        float4 nq = __ldg(tri_n + __float_as_int(q.w));
-        float h = dx * nq.x + dy * nq.y + dz * nq.z;
-        if (!(fabsf(h) > h_thr)) { search = true; live2 = -1.0f; }  // NaN normal (degenerate triangle) keeps the cell searchable
-      }
-    });
-  }
-  out[c] = search ? dc : 3.0e30f;
+  out[c] = far ? 1 : 0;
 }
 
-// Exact nearest centroid: squared L2 accumulated as d0*d0, fma(d1,d1,.), fma(d2,d2,.) and
-// strict '<' with lowest index on ties -- the arithmetic of pytorch3d 0.4.0 knn_points(K=1)
-// as called at utils/render_utils.py:95.  Returns -1 when the point is provably farther than
-// g.r_cap from every centroid or sits in a provably transparent cell.  The scan visits only
-// grid rows that intersect the ball of the current best radius, which starts at the exact
-// distance to a seed centroid, so it returns the same index as a full scan.
-// `hint` (>= 0) is a caller-supplied seed (the posed-space triangle for the canonical search);
-// without it the seed is the table's centroid nearest to the cell centre.
-__device__ __forceinline__ int nearest_centroid(const Grid& g, float px, float py, float pz, unsigned long long* cand_counter,
-                                                int hint = -1) {
+// ---- lazy lookup table -----------------------------------------------------------------------
+__device__ __forceinline__ int table_cell(const Grid& g, float px, float py, float pz) {
   float fx = (px - g.ox) * g.tinv, fy = (py - g.oy) * g.tinv, fz = (pz - g.oz) * g.tinv;
   // points outside the table region are farther than r_cap from the mesh by construction
   if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.tnx && fy < (float)g.tny && fz < (float)g.tnz)) return -1;
-  const int cell = ((int)fz * g.tny + (int)fy) * g.tnx + (int)fx;
-  float dc = __ldg(g.center_dist + cell);
-  if (hint < 0) {
-    if (dc - g.thalf_diag > g.r_cap) return -1;
-    hint = __ldg(g.center_idx + cell);
-  } else if (dc > 1.0e29f) {
-    dc = g.r_cap;  // classified cell, but the caller vouches for a nearby centroid: let the hint set the radius
+  return ((int)fz * g.tny + (int)fy) * g.tnx + (int)fx;
+}
+__device__ __forceinline__ int parent_cell(const Grid& g, int cell) {  // enumeration cell that contains a table cell
+  int tx = cell % g.tnx, ty = (cell / g.tnx) % g.tny, tz = cell / (g.tnx * g.tny);
+  return ((tz >> 1) * g.ny + (ty >> 1)) * g.nx + (tx >> 1);
+}
+// table cell of a point, or -1 when the point is outside the table or in a provably far enumeration cell
+__device__ __forceinline__ int live_cell(const Grid& g, float px, float py, float pz) {
+  int cell = table_cell(g, px, py, pz);
+  if (cell >= 0 && __ldg(g.enum_far + parent_cell(g, cell))) cell = -1;
+  return cell;
+}
+// byte-wide "0 -> 1" compare-and-swap through the containing word; true for the one thread that made the transition
+__device__ __forceinline__ bool claim_byte(unsigned char* bytes, int i) {
+  unsigned int* word = reinterpret_cast<unsigned int*>(bytes + (i & ~3));
+  const unsigned sh = (unsigned)(i & 3) * 8u;
+  unsigned old = *word;
+  for (;;) {
+    if ((old >> sh) & 0xffu) return false;  // somebody else requested / built it
+    unsigned seen = atomicCAS(word, old, old | (1u << sh));
+    if (seen == old) return true;
+    old = seen;
   }
-  // true nearest distance <= dc + half_diag; a candidate beyond that bound means the point is farther than r_cap anyway
-  const float bound = fminf(dc + g.thalf_diag, g.r_cap * 1.0001f + g.thalf_diag);
-  const float rho2_init = bound * bound * 1.0001f;
+}
+// request the table cell of a point (and, for the posed mesh, its enumeration cell): one atomic per distinct cell of a
+// warp, and only while the cell is untouched
+__device__ __forceinline__ void request_cell(const Grid& g, int cell) {
+  bool want = cell >= 0 && g.tstate[cell] == 0;
+  unsigned act = __ballot_sync(0xffffffffu, want);
+  if (!want) return;
+  unsigned peers = __match_any_sync(act, cell);
+  if ((__ffs(peers) - 1) != (int)(threadIdx.x & 31)) return;
+  if (!claim_byte(g.tstate, cell)) return;
+  g.req[atomicAdd(g.pool_used + 1, 1)] = cell;
+  const int par = parent_cell(g, cell);
+  if (g.estate[par] == 0 && claim_byte(g.estate, par)) g.ereq[atomicAdd(g.pool_used + 2, 1)] = par;
+}
+
+// Warp-cooperative visit of every centroid stored in a grid cell that intersects the ball (p, rho): the (z, y) rows of the
+// ball's bounding box are dealt to the lanes (a row costs three dependent loads before its centroids can be read, so 32
+// rows in flight hide that latency), each lane walks its row's run of centroids serially.  visit(q) runs per lane.
+template <class Visit>
+__device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py, float pz, float rho, Visit&& visit) {
+  const int lane = threadIdx.x & 31;
+  const float rho2 = rho * rho;
+  const int z0 = max(0, (int)floorf((pz - rho - g.oz) * g.inv_cell)), z1 = min(g.nz - 1, (int)floorf((pz + rho - g.oz) * g.inv_cell));
+  const int y0 = max(0, (int)floorf((py - rho - g.oy) * g.inv_cell)), y1 = min(g.ny - 1, (int)floorf((py + rho - g.oy) * g.inv_cell));
+  const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+  for (int r = lane; r < nrows; r += 32) {
+    const int cz = z0 + r / ny, cy = y0 + r % ny;
+    unsigned long long m = __ldg(g.row_mask + cz * g.ny + cy);
+    if (!m) continue;
+    const float zl = g.oz + cz * g.cell, yl = g.oy + cy * g.cell;
+    const float dz = fmaxf(0.f, fmaxf(zl - pz, pz - (zl + g.cell)));
+    const float dy = fmaxf(0.f, fmaxf(yl - py, py - (yl + g.cell)));
+    const float rem = rho2 - (dz * dz + dy * dy) * 0.9999f;
+    if (rem < 0.f) continue;
+    const float rx = sqrtf(rem) * 1.0001f + 1e-6f;
+    int x0 = max(0, (int)floorf((px - rx - g.ox) * g.inv_cell)), x1 = min(g.nx - 1, (int)floorf((px + rx - g.ox) * g.inv_cell));
+    if (x0 > x1) continue;
+    m &= (x1 - x0 >= 63 ? ~0ull : ((1ull << (x1 - x0 + 1)) - 1ull)) << x0;
+    if (!m) continue;
+    x0 = __ffsll((long long)m) - 1;
+    x1 = 63 - __clzll((long long)m);
+    const int row = (cz * g.ny + cy) * g.nx;
+    const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+    for (int j = b; j < e; ++j) visit(__ldg(g.sorted + j));
+  }
+  __syncwarp();
+}
+
+constexpr int LIST_CAP = 64;      // longest candidate list kept; longer ones fall back to the ball scan
+constexpr int BUF_CAP = 384;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
+constexpr int BUILD_WARPS = 4;
+
+// Candidate filter of a cube (centre x, half edge a) against a reference centroid r with |x - r|^2 = dr2: a centroid q
+// (|x - q|^2 = d) can be nearer than r somewhere in the cube only if d - dr2 <= 2a|q - r|_1 (slack for fp32 rounding).
+__device__ __forceinline__ bool can_beat(float d, float dr2, float a, float l1) { return d - dr2 <= 2.0f * a * l1 * 1.0002f + 1e-7f + 2e-6f * d; }
+
+// Settle one table cell from a buffered candidate superset S[0..n) (all lanes of the warp call this): exact nearest c0 of the
+// cell centre, filter against c0, transparency proof (posed mesh), list -> pool.  `list` is a LIST_CAP scratch buffer.
+__device__ __forceinline__ int2 settle_cell(const Grid& g, const float4* S, int n, float4* list, float px, float py, float pz, float a, float rho,
+                                            int& kind) {
+  const int lane = threadIdx.x & 31;
+  float mb = 3.0e38f;
+  int mi = 0x7fffffff;
+  float c0x = 0.f, c0y = 0.f, c0z = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    float4 q = S[i];
+    float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+    float d = dx * dx + dy * dy + dz * dz;
+    int id = __float_as_int(q.w);
+    if (d < mb || (d == mb && id < mi)) { mb = d; mi = id; c0x = q.x; c0y = q.y; c0z = q.z; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, mb, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    float ox = __shfl_xor_sync(0xffffffffu, c0x, o), oy = __shfl_xor_sync(0xffffffffu, c0y, o), oz = __shfl_xor_sync(0xffffffffu, c0z, o);
+    if (ob < mb || (ob == mb && oi < mi)) { mb = ob; mi = oi; c0x = ox; c0y = oy; c0z = oz; }
+  }
+  const float best = mb, dmin = sqrtf(mb);
+  kind = 4;
+  if (dmin * 0.9999f - rho > g.r_cap) return make_int2(mi, -1);  // far
+  const float h_thr = 0.1f + rho * 1.001f + 1e-4f;
+  bool search = !g.classify;
+  int keep = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    bool cand = false;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      q = S[i];
+      float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+      float d = dx * dx + dy * dy + dz * dz;
+      cand = can_beat(d, best, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
+      if (cand && g.classify) {
+        float4 nq = __ldg(g.tri_n + __float_as_int(q.w));
+        float h = dx * nq.x + dy * nq.y + dz * nq.z;
+        if (!(fabsf(h) > h_thr)) search = true;  // NaN normal (degenerate triangle) keeps the cell searchable
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    if (cand) {
+      int slot = keep + __popc(m & ((1u << lane) - 1));
+      if (list != nullptr && slot < LIST_CAP) list[slot] = q;
+    }
+    keep += __popc(m);
+  }
+  search = __any_sync(0xffffffffu, search);
+  __syncwarp();
+  kind = 5;
+  if (!search) return make_int2(mi, -1);  // certified transparent
+  kind = 7;
+  int2 rec = make_int2(mi, -2);
+  if (keep <= LIST_CAP && list != nullptr) {
+    int off = 0;
+    if (lane == 0) off = atomicAdd(g.pool_used, keep);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + keep <= g.pool_cap) {
+      for (int i = lane; i < keep; i += 32) g.pool[off + i] = list[i];
+      rec = make_int2(off, keep);
+      kind = 6;
+    }
+  }
+  __syncwarp();
+  return rec;
+}
+
+// Build requested cells, one warp per REQUESTED ENUMERATION CELL (LEVEL 1) or per left-over table cell (LEVEL 2).
+// LEVEL 1: one ball scan collects the candidate superset of the whole 4 cm cell (reference = jump-flooded seed; any reference
+// is valid because the nearest centroid of a point beats every other one).  Posed mesh: if the proof certifies the whole cell,
+// its requested table cells are settled at once; otherwise (and for the canonical mesh) each requested table cell of it is
+// settled from the buffered superset (a table cell's candidates are a subset of its parent's) without another scan.
+// LEVEL 2: table cells still unsettled (parent built by an earlier call, or its superset overflowed): own scan.
+template <int LEVEL>
+__global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
+  __shared__ float4 buf[BUILD_WARPS][BUF_CAP];
+  __shared__ float4 lst[BUILD_WARPS][LIST_CAP];
+  __shared__ int cnt_s[BUILD_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n_req = g.pool_used[LEVEL == 1 ? 2 : 1];
+  const float tcell = 1.0f / g.tinv;
+  const float ecell = LEVEL == 1 ? g.cell : tcell;
+  const float a = 0.5f * ecell * 1.0002f + 2e-6f;  // half edge of the cell, rounded up (covers the rounding of the cell lookup)
+  const float at = 0.5f * tcell * 1.0002f + 2e-6f;
+  const float rho = LEVEL == 1 ? 2.0f * g.thalf_diag : g.thalf_diag;
+  const int lnx = LEVEL == 1 ? g.nx : g.tnx, lny = LEVEL == 1 ? g.ny : g.tny;
+  for (int r = blockIdx.x * BUILD_WARPS + w; r < n_req; r += gridDim.x * BUILD_WARPS) {
+    const int cell = LEVEL == 1 ? g.ereq[r] : g.req[r];
+    if (LEVEL == 2 && g.tstate[cell] == 2) continue;  // settled through its enumeration cell
+    const int tx = cell % lnx, ty = (cell / lnx) % lny, tz = cell / (lnx * lny);
+    const int par = LEVEL == 1 ? cell : ((tz >> 1) * g.ny + (ty >> 1)) * g.nx + (tx >> 1);
+    int kind = 4, visits = 0;
+    if (LEVEL == 2 && g.classify && g.estate[par] == 2) {  // the whole enumeration cell is certified transparent
+      if (lane == 0) { g.trec[cell] = make_int2(0, -1); g.tstate[cell] = 2; }
+      if (g.debug && lane == 0) atomicAdd(g.pool_used + 4, 1);
+      continue;
+    }
+    const float px = g.ox + (tx + 0.5f) * ecell, py = g.oy + (ty + 0.5f) * ecell, pz = g.oz + (tz + 0.5f) * ecell;
+    const int cref = __ldg(g.enum_seed + par);
+    const float rx = __ldg(g.cent + 3 * cref), ry = __ldg(g.cent + 3 * cref + 1), rz = __ldg(g.cent + 3 * cref + 2);
+    const float dref2 = (px - rx) * (px - rx) + (py - ry) * (py - ry) + (pz - rz) * (pz - rz);
+    if (lane == 0) cnt_s[w] = 0;
+    __syncwarp();
+    float mb = dref2;
+    int mi = cref;
+    warp_scan_ball(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q) {
+      float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+      float d = dx * dx + dy * dy + dz * dz;
+      ++visits;
+      if (d < mb) { mb = d; mi = __float_as_int(q.w); }
+      if (can_beat(d, dref2, a, fabsf(q.x - rx) + fabsf(q.y - ry) + fabsf(q.z - rz))) {
+        int slot = atomicAdd(&cnt_s[w], 1);
+        if (slot < BUF_CAP) buf[w][slot] = q;
+      }
+    });
+    int nbuf = cnt_s[w];
+    if (nbuf > BUF_CAP) {
+      // superset too long against the seed: take the centre's true nearest centroid (found by the scan above) as the
+      // reference and scan once more (smaller ball, tighter filter)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, mb, o);
+        int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ob < mb || (ob == mb && oi < mi)) { mb = ob; mi = oi; }
+      }
+      const float c0x = __ldg(g.cent + 3 * mi), c0y = __ldg(g.cent + 3 * mi + 1), c0z = __ldg(g.cent + 3 * mi + 2);
+      __syncwarp();
+      if (lane == 0) cnt_s[w] = 0;
+      __syncwarp();
+      warp_scan_ball(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q) {
+        float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+        ++visits;
+        if (can_beat(dx * dx + dy * dy + dz * dz, mb, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z))) {
+          int slot = atomicAdd(&cnt_s[w], 1);
+          if (slot < BUF_CAP) buf[w][slot] = q;
+        }
+      });
+      nbuf = cnt_s[w];
+    }
+    const bool overflow = nbuf > BUF_CAP;
+    if (LEVEL == 1) {
+      // the enumeration cell itself: proof only (never a list)
+      int2 prec = make_int2(0, -2);
+      if (!overflow && g.classify) prec = settle_cell(g, buf[w], nbuf, nullptr, px, py, pz, a, rho, kind);
+      const bool certified = prec.y == -1;
+      if (lane == 0) g.estate[cell] = certified ? 2 : 3;
+      // its requested table cells
+      for (int k = 0; k < 8; ++k) {
+        const int cx = 2 * tx + (k & 1), cy = 2 * ty + ((k >> 1) & 1), cz = 2 * tz + (k >> 2);
+        const int child = (cz * g.tny + cy) * g.tnx + cx;
+        if (g.tstate[child] != 1) continue;  // warp uniform
+        int2 rec = make_int2(0, -1);
+        int ck = 4;
+        if (!certified) {
+          if (overflow) continue;  // left to LEVEL 2
+          rec = settle_cell(g, buf[w], nbuf, lst[w], g.ox + (cx + 0.5f) * tcell, g.oy + (cy + 0.5f) * tcell, g.oz + (cz + 0.5f) * tcell, at,
+                            g.thalf_diag, ck);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          g.trec[child] = rec;
+          __threadfence();
+          g.tstate[child] = 2;
+          if (g.debug) { atomicAdd(g.pool_used + ck, 1); if (rec.y > 0) atomicAdd(g.pool_used + 8, rec.y); }
+        }
+      }
+    } else {
+      int2 rec;
+      if (overflow) { rec = make_int2(mi, -2); kind = 7; }  // (mi: best centroid seen by this lane's rows; any centroid seeds the scan)
+      else rec = settle_cell(g, buf[w], nbuf, lst[w], px, py, pz, a, rho, kind);
+      __syncwarp();
+      if (lane == 0) {
+        g.trec[cell] = rec;
+        g.tstate[cell] = 2;
+        if (g.debug) { atomicAdd(g.pool_used + kind, 1); if (rec.y > 0) atomicAdd(g.pool_used + 8, rec.y); }
+      }
+    }
+    if (g.debug) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
+      if (lane == 0) atomicAdd(g.pool_used + (LEVEL == 1 ? 9 : 10), visits);
+    }
+  }
+}
+
+// Exact nearest centroid of a point: squared L2 accumulated as d0*d0, fma(d1,d1,.), fma(d2,d2,.) and strict '<' with
+// lowest index on ties -- the arithmetic of pytorch3d 0.4.0 knn_points(K=1) as called at utils/render_utils.py:95.
+// (a) over a candidate list of a built table cell
+__device__ __forceinline__ int list_nearest(const Grid& g, int off, int cnt, float px, float py, float pz) {
+  float best = 3.0e38f;
+  int besti = 0x7fffffff;
+  const float4* __restrict__ L = g.pool + off;
+#pragma unroll 4
+  for (int i = 0; i < cnt; ++i) {
+    float4 c = __ldg(L + i);
+    float dx = xsub(px, c.x), dy = xsub(py, c.y), dz = xsub(pz, c.z);
+    float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+    int id = __float_as_int(c.w);
+    if (d < best || (d == best && id < besti)) { best = d; besti = id; }
+  }
+  return besti;
+}
+// (b) ball scan through the enumeration grid, seeded with any centroid `hint`: visits every grid row that intersects the
+// ball of the current best radius, so it returns the same index as a full scan.
+__device__ __forceinline__ int scan_nearest(const Grid& g, float px, float py, float pz, int hint) {
   float best, rho2;
   int besti = hint;
   {
     float dx = xsub(px, __ldg(g.cent + 3 * hint)), dy = xsub(py, __ldg(g.cent + 3 * hint + 1)), dz = xsub(pz, __ldg(g.cent + 3 * hint + 2));
     best = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
-    rho2 = fminf(rho2_init, best * 1.0001f + 1e-12f);
+    rho2 = best * 1.0001f + 1e-12f;
   }
-  unsigned ncand = 0;
   scan_ball(g, px, py, pz, sqrtf(rho2) * 1.0001f, rho2, [&](float4 c) {
     float dx = xsub(px, c.x), dy = xsub(py, c.y), dz = xsub(pz, c.z);
     float d = xmul(dx, dx);
     d = xfma(dy, dy, d);
     d = xfma(dz, dz, d);
     int id = __float_as_int(c.w);
-    ++ncand;
     if (d < best || (d == best && id < besti)) {
       best = d;
       besti = id;
       rho2 = fminf(rho2, best * 1.0001f + 1e-12f);
     }
   });
-  if (cand_counter && ncand) atomicAdd(cand_counter, (unsigned long long)ncand);
-  if (best > rho2_init) besti = -1;
   return besti;
+}
+// (c) exhaustive
+__device__ __forceinline__ int brute_nearest(const float* __restrict__ cent, int F, float px, float py, float pz) {
+  float best = 3.0e38f;
+  int idx = 0;
+  for (int f = 0; f < F; ++f) {
+    float dx = xsub(px, cent[3 * f]), dy = xsub(py, cent[3 * f + 1]), dz = xsub(pz, cent[3 * f + 2]);
+    float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+    if (d < best) { best = d; idx = f; }
+  }
+  return idx;
+}
+// Nearest centroid of a point whose table cell has been built; -1 = no search needed (provably transparent / far).
+__device__ __forceinline__ int table_nearest(const Grid& g, int cell, float px, float py, float pz) {
+  if (cell < 0) return -1;
+  const int2 rec = g.trec[cell];
+  if (rec.y == -1) return -1;
+  if (rec.y >= 0) return list_nearest(g, rec.x, rec.y, px, py, pz);
+  return scan_nearest(g, px, py, pz, rec.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -530,6 +755,29 @@ __device__ __forceinline__ void sample_position(const WarpArgs& a, int64_t s, fl
   pz = xadd(a.ray_o[3 * r + 2], xmul(a.ray_d[3 * r + 2], z));
 }
 
+// pass 0: request the table cell of every sample (the cells are then built by build_cells_kernel)
+__global__ void __launch_bounds__(WARP_THREADS) mark_samples_kernel(WarpArgs a, Grid g) {
+  const int64_t P = a.R * a.N;
+  const int64_t s = (int64_t)blockIdx.x * WARP_THREADS + threadIdx.x;
+  int cell = -1;
+  if (s < P) {
+    float px, py, pz;
+    sample_position(a, s, px, py, pz);
+    cell = live_cell(g, px, py, pz);
+  }
+  request_cell(g, cell);
+}
+// same for explicit points (x, y, z, *) records, n given on the device or by the host
+__global__ void __launch_bounds__(256) mark_points_kernel(const float4* __restrict__ pts, const unsigned long long* __restrict__ n_ptr, int64_t n_host, Grid g) {
+  const int64_t n = n_ptr ? (int64_t)*n_ptr : n_host;
+  for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < n; t0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = t0 + threadIdx.x;
+    int cell = -1;
+    if (t < n) { float4 p = pts[t]; cell = live_cell(g, p.x, p.y, p.z); }
+    request_cell(g, cell);
+  }
+}
+
 __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, Grid g) {
   __shared__ int queue[WARP_THREADS];
   __shared__ int qn;
@@ -542,17 +790,17 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
   flag[threadIdx.x] = 0;
   __syncthreads();
   // phase 1: place the sample, look its table cell up.  Samples that need the exact search are queued, bucketed by the
-  // table's distance (= expected search radius) so that the lanes of a warp in phase 2 do similar amounts of work.
+  // length of their cell's candidate list (= work) so that the lanes of a warp in phase 2 do similar amounts of work.
   int my_bin = -1;
   {
     const int64_t s = s0 + threadIdx.x;
     if (s < P) {
       float px, py, pz;
       sample_position(a, s, px, py, pz);
-      float fx = (px - g.ox) * g.tinv, fy = (py - g.oy) * g.tinv, fz = (pz - g.oz) * g.tinv;
-      if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.tnx && fy < (float)g.tny && fz < (float)g.tnz) {
-        float dc = __ldg(g.center_dist + ((int)fz * g.tny + (int)fy) * g.tnx + (int)fx);
-        if (!(dc - g.thalf_diag > g.r_cap)) my_bin = min(7, (int)(dc * 40.0f));  // 2.5 cm classes
+      const int cell = live_cell(g, px, py, pz);
+      if (cell >= 0) {
+        const int cnt = g.trec[cell].y;
+        if (cnt != -1) my_bin = cnt < 0 ? 7 : min(6, cnt >> 3);
       }
     }
     if (my_bin >= 0) atomicAdd(&bin_count[my_bin], 1);
@@ -560,7 +808,7 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int b = 7; b >= 0; --b) { bin_start[b] = acc; acc += bin_count[b]; }  // big radii first
+    for (int b = 7; b >= 0; --b) { bin_start[b] = acc; acc += bin_count[b]; }  // long lists first
     qn = acc;
   }
   __syncthreads();
@@ -576,7 +824,7 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
       t = queue[threadIdx.x];
       float px, py, pz;
       sample_position(a, s0 + t, px, py, pz);
-      idx = nearest_centroid(g, px, py, pz, a.count_candidates ? a.counters + 1 : nullptr);
+      idx = table_nearest(g, table_cell(g, px, py, pz), px, py, pz);
       if (idx >= 0) {
         int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
         float u, v, h;
@@ -611,24 +859,21 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
   }
 }
 
-// stand-alone warp op (dsnerf_warp_points)
+// stand-alone warp op (dsnerf_warp_points): reports the reference's values for every point, transparent or not, so it
+// does not use the lookup table: exact ball scan seeded by the enumeration cell's approximate nearest centroid; points
+// outside the grid fall back to the exhaustive scan (rare: far from the mesh).
 __global__ void warp_points_kernel(const float* __restrict__ pts, int64_t P, const float* __restrict__ posed, const float* __restrict__ canon,
                                    const int* __restrict__ faces, Grid g, int F, const float* __restrict__ cent,
                                    float* __restrict__ xyz_cano, uint8_t* __restrict__ transparent, int* __restrict__ idx_out) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= P) return;
   float px = pts[3 * s], py = pts[3 * s + 1], pz = pts[3 * s + 2];
-  int idx = nearest_centroid(g, px, py, pz, nullptr);
-  if (idx < 0) {
-    // provably transparent, but the stand-alone op still reports the reference's values:
-    // fall back to the exhaustive scan for this point (rare: far from the mesh)
-    float best = 3.0e38f;
-    for (int f = 0; f < F; ++f) {
-      float dx = xsub(px, cent[3 * f]), dy = xsub(py, cent[3 * f + 1]), dz = xsub(pz, cent[3 * f + 2]);
-      float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
-      if (d < best) { best = d; idx = f; }
-    }
-  }
+  int idx;
+  float fx = (px - g.ox) * g.inv_cell, fy = (py - g.oy) * g.inv_cell, fz = (pz - g.oz) * g.inv_cell;
+  if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz)
+    idx = scan_nearest(g, px, py, pz, g.enum_seed[((int)fz * g.ny + (int)fy) * g.nx + (int)fx]);
+  else
+    idx = brute_nearest(cent, F, px, py, pz);
   int i0 = faces[3 * idx], i1 = faces[3 * idx + 1], i2 = faces[3 * idx + 2];
   float u, v, h;
   project_point(v3(px, py, pz), ldv3(posed, i0), ldv3(posed, i1), ldv3(posed, i2), u, v, h);

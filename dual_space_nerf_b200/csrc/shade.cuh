@@ -72,16 +72,9 @@ __device__ __forceinline__ void shade_inputs(const ShadeArgs& a, const Grid& gc,
   ma = a.mlp_a[t];
   float4 mg = a.mlp_g[t];
   sample = __float_as_int(ac.w);
-  // the canonical point was emitted on canonical triangle active_tri[t]: its centroid is an excellent seed
-  int idx = nearest_centroid(gc, ac.x, ac.y, ac.z, nullptr, a.active_tri ? a.active_tri[t] : -1);
-  if (idx < 0) {  // cannot happen for warped points; keep the exact answer anyway
-    float best = 3.0e38f;
-    for (int f = 0; f < a.F; ++f) {
-      float dx = xsub(ac.x, a.cent_canon[3 * f]), dy = xsub(ac.y, a.cent_canon[3 * f + 1]), dz = xsub(ac.z, a.cent_canon[3 * f + 2]);
-      float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
-      if (d < best) { best = d; idx = f; }
-    }
-  }
+  // exact nearest canonical centroid through the canonical mesh's lookup table (cells requested by mark_points_kernel)
+  int idx = table_nearest(gc, live_cell(gc, ac.x, ac.y, ac.z), ac.x, ac.y, ac.z);
+  if (idx < 0) idx = brute_nearest(a.cent_canon, a.F, ac.x, ac.y, ac.z);  // outside the table / far: cannot happen for warped points
   int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
   V3 nw = normal_to_world(v3(mg.x, mg.y, mg.z), ldv3(a.canon, i0), ldv3(a.canon, i1), ldv3(a.canon, i2),
                           ldv3(a.posed, i0), ldv3(a.posed, i1), ldv3(a.posed, i2));

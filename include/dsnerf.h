@@ -152,6 +152,15 @@ int dsnerf_profile(dsnerf_ctx* ctx, int enable);
 /* debug (profile bit 4): clock64 stamps of the tensor-core kernel's first tile, 64 values */
 int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out64);
 int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int reset);
+/* debug: counters of the lazily built lookup table of the posed (which = 0) or canonical (1) mesh, 16 ints:
+ * [0] candidate-list entries in use, [1] cells requested by the last call, [2] table cells, [3] enumeration cells,
+ * with profile bit 2 also [4] far cells, [5] certified transparent, [6] cells with a list, [7] scan fallbacks,
+ * [8] list entries, [9]/[10] centroids visited by the two build passes. */
+int dsnerf_debug_table(dsnerf_ctx* ctx, int which, int* out16);
+/* Measurement aid: enqueue a one-warp kernel on `stream` that spins ~30 us and writes (SM MHz, microseconds) =
+ * clock64 cycles per global-timer time to two DEVICE floats.  Lets a benchmark record the SM clock inside its timed
+ * region without NVML queries (which stall kernel launches for tens of milliseconds on this driver). */
+int dsnerf_debug_sm_clock(dsnerf_ctx* ctx, float* d_out2, void* stream);
 
 #ifdef __cplusplus
 }

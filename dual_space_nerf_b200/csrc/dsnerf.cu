@@ -907,6 +907,20 @@ int dsnerf_debug_sm_clock(dsnerf_ctx* ctx, float* d_out2, void* stream) {
   return 0;
 }
 
+int dsnerf_debug_active(dsnerf_ctx* ctx, int64_t capacity, float* active_xyz_id, int32_t* active_tri, int64_t* n_out) {
+  if (!ctx || !n_out) return DSNERF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long n = 0;
+  if (!ctx->counters.p) { *n_out = 0; return 0; }
+  CK(cudaMemcpy(&n, ctx->counters.p, sizeof(n), cudaMemcpyDeviceToHost));
+  *n_out = (int64_t)n;
+  int64_t m = std::min<int64_t>((int64_t)n, capacity);
+  if (m > 0 && active_xyz_id) CK(cudaMemcpy(active_xyz_id, ctx->active.p, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+  if (m > 0 && active_tri) CK(cudaMemcpy(active_tri, ctx->active_tri.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int dsnerf_debug_table(dsnerf_ctx* ctx, int which, int* out16) {
   if (!ctx || !out16) return DSNERF_ERR_INVALID;
   MeshGrid& mg = which ? ctx->g_canon : ctx->g_posed;

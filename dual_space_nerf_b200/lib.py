@@ -18,7 +18,7 @@ ENTRY_POINTS = [
     "dsnerf_abi_version", "dsnerf_create", "dsnerf_destroy", "dsnerf_last_error", "dsnerf_set_weights",
     "dsnerf_set_mesh", "dsnerf_set_frame", "dsnerf_render", "dsnerf_render_host", "dsnerf_render_z",
     "dsnerf_resample", "dsnerf_composite", "dsnerf_warp_points", "dsnerf_query_density", "dsnerf_eval_points",
-    "dsnerf_get_stats", "dsnerf_profile", "dsnerf_profile_read", "dsnerf_debug_tc_timing", "dsnerf_debug_table", "dsnerf_debug_sm_clock",
+    "dsnerf_get_stats", "dsnerf_profile", "dsnerf_profile_read", "dsnerf_debug_tc_timing", "dsnerf_debug_table", "dsnerf_debug_sm_clock", "dsnerf_debug_active",
 ]
 
 
@@ -72,6 +72,7 @@ def load():
     L.dsnerf_debug_tc_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     L.dsnerf_debug_table.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_int)]
     L.dsnerf_debug_sm_clock.argtypes = [vp, vp, vp]
+    L.dsnerf_debug_active.argtypes = [vp, i64, vp, vp, ctypes.POINTER(ctypes.c_int64)]
     for name in ENTRY_POINTS:
         fn = getattr(L, name)
         if name not in ("dsnerf_destroy", "dsnerf_last_error"):

@@ -157,6 +157,10 @@ int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, 
  * with profile bit 2 also [4] far cells, [5] certified transparent, [6] cells with a list, [7] scan fallbacks,
  * [8] list entries, [9]/[10] centroids visited by the two build passes. */
 int dsnerf_debug_table(dsnerf_ctx* ctx, int which, int* out16);
+/* Test aid: the active list of the last dsnerf_render* call on this context, copied to HOST buffers: per evaluated
+ * sample (x_cano, y_cano, z_cano, bits(sample id = ray * n_samples + i)) and the posed-space nearest triangle.
+ * Order is not deterministic.  n_out receives the list length (may exceed capacity). */
+int dsnerf_debug_active(dsnerf_ctx* ctx, int64_t capacity, float* active_xyz_id, int32_t* active_tri, int64_t* n_out);
 /* Measurement aid: enqueue a one-warp kernel on `stream` that spins ~30 us and writes (SM MHz, microseconds) =
  * clock64 cycles per global-timer time to two DEVICE floats.  Lets a benchmark record the SM clock inside its timed
  * region without NVML queries (which stall kernel launches for tens of milliseconds on this driver). */

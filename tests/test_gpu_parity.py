@@ -120,6 +120,41 @@ def test_stage_ops_bit_exact_vs_golden(scene64, state_dict):
     assert np.all(dens.cpu().numpy().ravel()[g["mask"]] == 0)
 
 
+def test_lazy_table_candidate_lists_vs_bruteforce(state_dict):
+    """The render path's nearest-triangle search (lazily built lookup table + candidate lists, csrc/geom.cuh) against the
+    oracle's brute-force scan on EVERY sample of a 128x128x64 frame: same set of evaluated samples, same triangle index,
+    bit-identical canonical point -- twice on one frame (second call reuses the built cells) and on a second posed surface."""
+    import ctypes
+
+    from oracle import oracle as O
+
+    for variant in (0, 1):
+        sc = S.make_scene(128, 128)
+        if variant:  # a different posed surface (the synthetic pose seeds only change the network input)
+            sc["posed"] = sc["posed"].copy()
+            sc["posed"][:, 1] += (0.05 * np.sin(3.0 * sc["posed"][:, 2])).astype(np.float32)
+        n = 64
+        r = make_renderer(sc, n)
+        pts, z, _, _ = O.gg_sampling(sc["ray_o"], sc["ray_d"], n, sc["near"], sc["far"], sc["posed"])
+        cano, mask, idx, _, _ = O.world_to_canonical(pts.reshape(-1, 3), sc["posed"], sc["canonical"], sc["faces"])
+        want = np.nonzero(~mask)[0]
+        for rep in range(2):
+            r.render(S.to_batch(sc, torch))
+            torch.cuda.synchronize()
+            cap = pts.shape[0] * n
+            act = np.empty((cap, 4), np.float32)
+            tri = np.empty(cap, np.int32)
+            cnt = ctypes.c_int64(0)
+            r.ctx.check(r.ctx.L.dsnerf_debug_active(r.ctx.h, cap, act.ctypes.data_as(ctypes.c_void_p), tri.ctypes.data_as(ctypes.c_void_p),
+                                                    ctypes.byref(cnt)))
+            m = cnt.value
+            sid = act[:m, 3].view(np.int32)
+            order = np.argsort(sid)
+            assert m == len(want) and np.array_equal(sid[order], want.astype(np.int32)), (m, len(want))
+            assert np.array_equal(tri[:m][order], idx[want].astype(np.int32))
+            assert C.bits_equal(act[:m, :3][order], cano[want]) == 0
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

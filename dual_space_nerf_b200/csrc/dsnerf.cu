@@ -220,7 +220,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CK(mg.seed_b.ensure(sizeof(int) * mg.ncell));
   CK(mg.tstate.ensure((size_t)mg.ntab + 4));
   CK(mg.trec.ensure(sizeof(int2) * (size_t)mg.ntab));
-  CK(mg.req.ensure(sizeof(int) * (size_t)mg.ntab));
+  CK(mg.req.ensure(sizeof(int) * (size_t)mg.ntab));  // LEVEL-2 left-overs
   CK(mg.efar.ensure((size_t)mg.ncell + 4));
   CK(mg.estate.ensure((size_t)mg.ncell + 4));
   CK(mg.ereq.ensure(sizeof(int) * (size_t)mg.ncell));
@@ -236,7 +236,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   g.pool = mg.pool.as<float4>();
   g.pool_cap = kPoolEntries;
   g.pool_used = mg.pool_used.as<int>();
-  g.req = mg.req.as<int>();
+  g.req2 = mg.req.as<int>();
   g.enum_far = mg.efar.as<unsigned char>();
   g.estate = mg.estate.as<unsigned char>();
   g.ereq = mg.ereq.as<int>();
@@ -283,7 +283,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
 // Build the lookup-table cells requested by a mark kernel (launched by the caller through `mark`).
 template <class Mark>
 int ensure_cells(dsnerf_ctx* ctx, MeshGrid& mg, cudaStream_t st, Mark&& mark) {
-  CK(cudaMemsetAsync(mg.pool_used.as<int>() + 1, 0, 2 * sizeof(int), st));
+  CK(cudaMemsetAsync(mg.pool_used.as<int>() + 1, 0, 3 * sizeof(int), st));
   mark();
   CKL("mark");
   build_cells_kernel<1><<<ctx->sm_count * 8, BUILD_WARPS * 32, 0, st>>>(mg.g);  // per requested enumeration cell
@@ -927,8 +927,8 @@ int dsnerf_debug_table(dsnerf_ctx* ctx, int which, int* out16) {
   if (!mg.pool_used.p) return DSNERF_ERR_STATE;
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out16, mg.pool_used.p, sizeof(int) * 16, cudaMemcpyDeviceToHost));
-  out16[3] = mg.ncell;
   out16[11] = mg.ntab;
+  out16[12] = mg.ncell;
   return 0;
 }
 

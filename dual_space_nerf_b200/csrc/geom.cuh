@@ -110,12 +110,12 @@ struct Grid {
   const unsigned char* __restrict__ enum_far;      // per enumeration cell: 1 = every point of it is farther than r_cap from all centroids
   unsigned char* __restrict__ estate;              // per enumeration cell (posed): 0 untouched, 1 requested, 2 certified transparent, 3 not certified
   int* __restrict__ ereq;                          // requested enumeration cells of the current call (count in pool_used[2])
+  int* __restrict__ req2;                          // table cells left to LEVEL 2 (count in pool_used[3])
   unsigned char* __restrict__ tstate;              // per table cell: 0 untouched, 1 requested, 2 built
   int2* __restrict__ trec;                         // per table cell: (off, cnt), see above
   float4* __restrict__ pool;                       // candidate lists
   int pool_cap;
-  int* __restrict__ pool_used;                     // [0] entries used, [1] table-cell requests, [2] enumeration-cell requests, [4..10] debug counters
-  int* __restrict__ req;                           // requested table cells of the current call
+  int* __restrict__ pool_used;                     // [0] entries used, [1] table-cell requests, [2] enumeration-cell requests, [3] LEVEL-2 left-overs, [4..10] debug counters
   int debug;                                       // count build outcomes in pool_used[4..10]
 };
 
@@ -149,32 +149,40 @@ __global__ void grid_count_kernel(Grid g, const float* __restrict__ cent, int F,
   atomicOr(&row_mask[cz * g.ny + cy], 1ull << cx);
 }
 
-// single-block exclusive scan: counts[ncell] -> start[ncell+1]; also copies start into cursor
-__global__ void grid_scan_kernel(const int* __restrict__ counts, int ncell, int* __restrict__ start, int* __restrict__ cursor) {
+// single-block exclusive scan: counts[ncell] -> start[ncell+1]; also copies start into cursor.
+// 8192 elements per round: coalesced load into shared memory, 8 contiguous elements per thread, one block scan of the partials.
+__global__ void __launch_bounds__(1024) grid_scan_kernel(const int* __restrict__ counts, int ncell, int* __restrict__ start, int* __restrict__ cursor) {
+  __shared__ int sh[8192];
   __shared__ int warp_sums[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < ncell; base += blockDim.x) {
-    int i = base + threadIdx.x;
-    int v = i < ncell ? counts[i] : 0;
-    int s = v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < ncell; base += 8192) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8192; i += 1024) sh[i] = base + i < ncell ? counts[base + i] : 0;
+    __syncthreads();
+    int v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = sh[threadIdx.x * 8 + k]; sum += v[k]; }
+    int s = sum;
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
     if (lane == 31) warp_sums[wid] = s;
     __syncthreads();
     if (wid == 0) {
-      int w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+      int w = warp_sums[lane];
       for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
       warp_sums[lane] = w;
     }
     __syncthreads();
-    int excl = carry + (wid ? warp_sums[wid - 1] : 0) + s - v;
-    if (i < ncell) { start[i] = excl; cursor[i] = excl; }
+    int excl = carry + (wid ? warp_sums[wid - 1] : 0) + s - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sh[threadIdx.x * 8 + k] = excl; excl += v[k]; }
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-    __syncthreads();
+    for (int i = threadIdx.x; i < 8192; i += 1024)
+      if (base + i < ncell) { start[base + i] = sh[i]; cursor[base + i] = sh[i]; }
+    if (threadIdx.x == 1023) carry = excl;
   }
+  __syncthreads();
   if (threadIdx.x == 0) start[ncell] = carry;
 }
 
@@ -316,9 +324,14 @@ __device__ __forceinline__ void request_cell(const Grid& g, int cell) {
   unsigned peers = __match_any_sync(act, cell);
   if ((__ffs(peers) - 1) != (int)(threadIdx.x & 31)) return;
   if (!claim_byte(g.tstate, cell)) return;
-  g.req[atomicAdd(g.pool_used + 1, 1)] = cell;
+  atomicAdd(g.pool_used + 1, 1);
   const int par = parent_cell(g, cell);
-  if (g.estate[par] == 0 && claim_byte(g.estate, par)) g.ereq[atomicAdd(g.pool_used + 2, 1)] = par;
+  const unsigned char es = g.estate[par];
+  if (es == 0) {
+    if (claim_byte(g.estate, par)) g.ereq[atomicAdd(g.pool_used + 2, 1)] = par;  // built (with its requested children) by LEVEL 1
+  } else if (es >= 2) {
+    g.req2[atomicAdd(g.pool_used + 3, 1)] = cell;  // parent settled by an earlier call of this frame: LEVEL 2
+  }
 }
 
 // Warp-cooperative visit of every centroid stored in a grid cell that intersects the ball (p, rho): the (z, y) rows of the
@@ -355,7 +368,7 @@ __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py
 }
 
 constexpr int LIST_CAP = 64;      // longest candidate list kept; longer ones fall back to the ball scan
-constexpr int BUF_CAP = 384;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
+constexpr int BUF_CAP = 640;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
 constexpr int BUILD_WARPS = 4;
 
 // Candidate filter of a cube (centre x, half edge a) against a reference centroid r with |x - r|^2 = dr2: a centroid q
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
   __shared__ float4 lst[BUILD_WARPS][LIST_CAP];
   __shared__ int cnt_s[BUILD_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n_req = g.pool_used[LEVEL == 1 ? 2 : 1];
+  const int n_req = g.pool_used[LEVEL == 1 ? 2 : 3];
   const float tcell = 1.0f / g.tinv;
   const float ecell = LEVEL == 1 ? g.cell : tcell;
   const float a = 0.5f * ecell * 1.0002f + 2e-6f;  // half edge of the cell, rounded up (covers the rounding of the cell lookup)
@@ -452,8 +465,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
   const float rho = LEVEL == 1 ? 2.0f * g.thalf_diag : g.thalf_diag;
   const int lnx = LEVEL == 1 ? g.nx : g.tnx, lny = LEVEL == 1 ? g.ny : g.tny;
   for (int r = blockIdx.x * BUILD_WARPS + w; r < n_req; r += gridDim.x * BUILD_WARPS) {
-    const int cell = LEVEL == 1 ? g.ereq[r] : g.req[r];
-    if (LEVEL == 2 && g.tstate[cell] == 2) continue;  // settled through its enumeration cell
+    const int cell = LEVEL == 1 ? g.ereq[r] : g.req2[r];
     const int tx = cell % lnx, ty = (cell / lnx) % lny, tz = cell / (lnx * lny);
     const int par = LEVEL == 1 ? cell : ((tz >> 1) * g.ny + (ty >> 1)) * g.nx + (tx >> 1);
     int kind = 4, visits = 0;
@@ -519,7 +531,10 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
         int2 rec = make_int2(0, -1);
         int ck = 4;
         if (!certified) {
-          if (overflow) continue;  // left to LEVEL 2
+          if (overflow) {  // left to LEVEL 2
+            if (lane == 0) g.req2[atomicAdd(g.pool_used + 3, 1)] = child;
+            continue;
+          }
           rec = settle_cell(g, buf[w], nbuf, lst[w], g.ox + (cx + 0.5f) * tcell, g.oy + (cy + 0.5f) * tcell, g.oz + (cz + 0.5f) * tcell, at,
                             g.thalf_diag, ck);
         }

@@ -153,9 +153,10 @@ int dsnerf_profile(dsnerf_ctx* ctx, int enable);
 int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out64);
 int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int reset);
 /* debug: counters of the lazily built lookup table of the posed (which = 0) or canonical (1) mesh, 16 ints:
- * [0] candidate-list entries in use, [1] cells requested by the last call, [2] table cells, [3] enumeration cells,
- * with profile bit 2 also [4] far cells, [5] certified transparent, [6] cells with a list, [7] scan fallbacks,
- * [8] list entries, [9]/[10] centroids visited by the two build passes. */
+ * [0] candidate-list entries in use, [1] table cells / [2] enumeration cells requested by the last call, [3] table cells left
+ * to the second build level, [11] table cells, [12] enumeration cells; with profile bit 2 also [4] far / settled through the
+ * parent, [5] certified transparent, [6] cells with a list, [7] scan fallbacks, [8] list entries, [9]/[10] centroids visited
+ * by the two build levels. */
 int dsnerf_debug_table(dsnerf_ctx* ctx, int which, int* out16);
 /* Test aid: the active list of the last dsnerf_render* call on this context, copied to HOST buffers: per evaluated
  * sample (x_cano, y_cano, z_cano, bits(sample id = ray * n_samples + i)) and the posed-space nearest triangle.

@@ -12,7 +12,7 @@ r = Renderer(N.synthetic_net(0), None, cfg, torch.from_numpy(sc["canonical"]), d
 r.eval()
 r.ctx.profile(2)
 r.render(S.to_batch(sc, torch)); torch.cuda.synchronize()
-names = ["pool entries", "requested", "enum requested", "enum cells", "far|parent", "certified", "lists", "fallback", "list entries", "L1 visits", "L2 visits"]
+names = ["pool entries", "requested", "enum requested", "level-2 leftovers", "far|parent", "certified", "lists", "fallback", "list entries", "L1 visits", "L2 visits", "table cells", "enum cells"]
 for which, nm in ((0, "posed"), (1, "canonical")):
     buf = (ctypes.c_int * 16)()
     r.ctx.check(r.ctx.L.dsnerf_debug_table(r.ctx.h, which, buf))

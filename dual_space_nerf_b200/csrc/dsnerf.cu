@@ -82,7 +82,7 @@ struct dsnerf_ctx {
   int F = 0, V = 0;
   std::vector<int32_t> h_faces;
   std::vector<float> h_canon;
-  DevBuf faces, canon, posed, vq;
+  DevBuf faces, canon, posed, vq, gg_bins;
   MeshGrid g_canon, g_posed;
   // ---- frame
   bool have_frame = false;
@@ -455,10 +455,24 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
     gg_prep_kernel<<<(ctx->V + 255) / 256, 256, 0, st>>>(ctx->posed.as<float>(), ctx->V, ray_o, ctx->vq.as<float4>(), qbox);
     CKL("gg_prep");
     float gamma2 = (float)(0.05 * 0.05);  // python double 0.05**2 rounded to fp32 (pts_utils.py:36)
-    gg_bounds_kernel<<<(unsigned)((R + GG_THREADS - 1) / GG_THREADS), GG_THREADS, 0, st>>>(
-        ctx->vq.as<float4>(), ctx->V, qbox, ray_d, near, far, R, gamma2, 0.05f, ctx->near2.as<float>(), ctx->far2.as<float>());
+    const float gamma_pad = 0.05f * 1.002f + 1e-4f;
+    // direction tiles: [GgFrame (64 B)][bad flag][counts][lists]
+    const size_t gg_bytes = 256 + sizeof(int) * (size_t)GG_TILES * GG_TILES * (1 + GG_CAP);
+    CK(ctx->gg_bins.ensure(gg_bytes));
+    GgFrame* frame = ctx->gg_bins.as<GgFrame>();
+    int* bad = reinterpret_cast<int*>(ctx->gg_bins.as<char>() + 128);
+    int* counts = reinterpret_cast<int*>(ctx->gg_bins.as<char>() + 256);
+    int* lists = counts + GG_TILES * GG_TILES;
+    CK(cudaMemsetAsync(bad, 0, 128 + sizeof(int) * GG_TILES * GG_TILES, st));
+    gg_frame_kernel<<<1, 32, 0, st>>>(qbox, gamma_pad, frame);
+    CKL("gg_frame");
+    gg_bin_kernel<<<(ctx->V + 255) / 256, 256, 0, st>>>(ctx->vq.as<float4>(), ctx->V, gamma_pad, frame, counts, lists, bad);
+    CKL("gg_bin");
+    gg_bounds_kernel<<<(unsigned)((R * 32 + GG_THREADS - 1) / GG_THREADS), GG_THREADS, 0, st>>>(
+        ctx->vq.as<float4>(), ctx->V, qbox, frame, counts, lists, bad, ray_d, near, far, R, gamma2, 0.05f, ctx->near2.as<float>(),
+        ctx->far2.as<float>());
     CKL("gg_bounds");
-    launches += 2;
+    launches += 4;
     near_use = ctx->near2.as<float>();
     far_use = ctx->far2.as<float>();
   }
@@ -537,7 +551,7 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->light_w2, &ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->near2, &ctx->far2, &ctx->raw,
+  DevBuf* bufs[] = {&ctx->light_w2, &ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->gg_bins, &ctx->near2, &ctx->far2, &ctx->raw,
                     &ctx->active, &ctx->active_tri, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io};
   for (DevBuf* b : bufs) b->release();
   ctx->g_canon.release();

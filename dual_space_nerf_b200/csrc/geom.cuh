@@ -659,23 +659,124 @@ __global__ void gg_prep_kernel(const float* __restrict__ xyz, int V, const float
 }
 
 constexpr int GG_THREADS = 256;
-constexpr int GG_VCHUNK = 2048;  // vertices staged per smem tile (32 KB)
+constexpr int GG_TILES = 48;     // direction tiles per axis
+constexpr int GG_CAP = 384;      // vertices per tile (a gamma = 5 cm cone holds ~75 vertices of an SMPL-sized mesh); fuller tiles fall back to the exhaustive scan
 
+// Every ray's LINE passes through the same point o0 (the reference uses the first ray's origin for all rays, and its test
+// |q|^2 - (q.u)^2 < gamma^2 has no t >= 0 restriction), so "vertex v is within gamma of the line" only depends on the line's
+// direction: it must lie inside the cone of half angle asin(gamma / |q_v|) around q_v.  Directions are binned in a gnomonic
+// chart (a, b) = (u.e1, u.e2) / (u.c) around c = direction of the centre of the vertex box; each vertex is entered into
+// every tile its (conservatively bounded) cone touches, a ray tests the vertices of its own tile only -- with the reference's
+// arithmetic, so near/far stay bit-identical.  ok = 0 (camera inside / very close to the mesh) selects the exhaustive scan.
+struct GgFrame {
+  float c[3], e1[3], e2[3];
+  float a0, b0, inv_da, inv_db;
+  int ok;
+};
+
+__global__ void gg_frame_kernel(const unsigned* __restrict__ qbox, float gamma_pad, GgFrame* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) { lo[k] = key2f(qbox[k]) - gamma_pad; hi[k] = key2f(qbox[3 + k]) + gamma_pad; }
+  GgFrame f;
+  float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+  float n = sqrtf(cx * cx + cy * cy + cz * cz);
+  f.ok = n > 1e-3f;
+  if (!f.ok) n = 1.f;
+  f.c[0] = cx / n; f.c[1] = cy / n; f.c[2] = cz / n;
+  // any unit vector not parallel to c
+  float hx = fabsf(f.c[0]) < 0.6f ? 1.f : 0.f, hy = hx == 0.f ? 1.f : 0.f;
+  float e1x = f.c[1] * 0.f - f.c[2] * hy, e1y = f.c[2] * hx - f.c[0] * 0.f, e1z = f.c[0] * hy - f.c[1] * hx;
+  float en = sqrtf(e1x * e1x + e1y * e1y + e1z * e1z);
+  f.e1[0] = e1x / en; f.e1[1] = e1y / en; f.e1[2] = e1z / en;
+  f.e2[0] = f.c[1] * f.e1[2] - f.c[2] * f.e1[1]; f.e2[1] = f.c[2] * f.e1[0] - f.c[0] * f.e1[2]; f.e2[2] = f.c[0] * f.e1[1] - f.c[1] * f.e1[0];
+  // chart extent = box of the 8 projected corners of the padded vertex box (a projective map keeps convex hulls)
+  float amin = 3e38f, amax = -3e38f, bmin = 3e38f, bmax = -3e38f;
+  for (int k = 0; k < 8; ++k) {
+    float x = (k & 1) ? hi[0] : lo[0], y = (k & 2) ? hi[1] : lo[1], z = (k & 4) ? hi[2] : lo[2];
+    float s = x * f.c[0] + y * f.c[1] + z * f.c[2];
+    if (!(s > 0.05f * n)) f.ok = 0;  // a corner is beside / behind the chart plane
+    float a = (x * f.e1[0] + y * f.e1[1] + z * f.e1[2]) / s, b = (x * f.e2[0] + y * f.e2[1] + z * f.e2[2]) / s;
+    amin = fminf(amin, a); amax = fmaxf(amax, a); bmin = fminf(bmin, b); bmax = fmaxf(bmax, b);
+  }
+  float da = (amax - amin) * 1.001f + 1e-6f, db = (bmax - bmin) * 1.001f + 1e-6f;
+  f.a0 = amin - 0.0005f * da; f.b0 = bmin - 0.0005f * db;
+  f.inv_da = (float)GG_TILES / da; f.inv_db = (float)GG_TILES / db;
+  if (!(da < 8.f && db < 8.f)) f.ok = 0;
+  *out = f;
+}
+
+__global__ void gg_bin_kernel(const float4* __restrict__ vq, int V, float gamma_pad, const GgFrame* __restrict__ fr, int* __restrict__ counts,
+                              int* __restrict__ lists, int* __restrict__ bad) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const GgFrame f = *fr;
+  if (!f.ok) return;
+  float4 q = vq[v];
+  float qn = sqrtf(q.w);
+  float s = q.x * f.c[0] + q.y * f.c[1] + q.z * f.c[2];
+  if (!(qn > 2.f * gamma_pad) || !(s > 0.f)) { atomicExch(bad, 1); return; }
+  float cth = fminf(1.f, s / qn);
+  float theta = acosf(cth), alpha = asinf(fminf(1.f, gamma_pad / qn));
+  if (!(theta + alpha < 1.2f)) { atomicExch(bad, 1); return; }
+  // the gnomonic chart stretches angles by at most 1 / cos^2 within the cone
+  float cc = cosf(theta + alpha);
+  float r = alpha / (cc * cc) * 1.02f + 1e-6f;
+  float a = (q.x * f.e1[0] + q.y * f.e1[1] + q.z * f.e1[2]) / s, b = (q.x * f.e2[0] + q.y * f.e2[1] + q.z * f.e2[2]) / s;
+  int i0 = max(0, (int)floorf((a - r - f.a0) * f.inv_da)), i1 = min(GG_TILES - 1, (int)floorf((a + r - f.a0) * f.inv_da));
+  int j0 = max(0, (int)floorf((b - r - f.b0) * f.inv_db)), j1 = min(GG_TILES - 1, (int)floorf((b + r - f.b0) * f.inv_db));
+  for (int j = j0; j <= j1; ++j)
+    for (int i = i0; i <= i1; ++i) {
+      int t = j * GG_TILES + i;
+      int slot = atomicAdd(counts + t, 1);
+      if (slot < GG_CAP) lists[t * GG_CAP + slot] = v;
+    }
+}
+
+// One warp per ray: the lanes share the vertices of the ray's direction tile (or all vertices when the tile is overfull /
+// the chart is unusable), then reduce min / max.  min and max are order independent, so the result equals the reference's.
 __global__ void __launch_bounds__(GG_THREADS) gg_bounds_kernel(const float4* __restrict__ vq, int V, const unsigned* __restrict__ qbox,
+                                                               const GgFrame* __restrict__ fr, const int* __restrict__ counts,
+                                                               const int* __restrict__ lists, const int* __restrict__ bad,
                                                                const float* __restrict__ ray_d, const float* __restrict__ near_in,
                                                                const float* __restrict__ far_in, int64_t R, float gamma2, float gamma,
                                                                float* __restrict__ near_out, float* __restrict__ far_out) {
-  __shared__ float4 sv[GG_VCHUNK];
-  int64_t r = (int64_t)blockIdx.x * GG_THREADS + threadIdx.x;
-  bool live = r < R;
-  float dx = 0.f, dy = 0.f, dz = 1.f;
-  if (live) { dx = ray_d[3 * r]; dy = ray_d[3 * r + 1]; dz = ray_d[3 * r + 2]; }
-  float norm = xnorm3(v3(dx, dy, dz));
-  float ux = xdiv(dx, norm), uy = xdiv(dy, norm), uz = xdiv(dz, norm);
-  // cull: a vertex can be within gamma of the ray's LINE (the test below has no t >= 0 restriction) only if the line
-  // meets the vertex box inflated by gamma (+ rounding slack); rays of whole blocks far from the body skip the scan
-  bool maybe = false;
-  if (live) {
+  const int64_t r = ((int64_t)blockIdx.x * GG_THREADS + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float dx = ray_d[3 * r], dy = ray_d[3 * r + 1], dz = ray_d[3 * r + 2];
+  const float norm = xnorm3(v3(dx, dy, dz));
+  const float ux = xdiv(dx, norm), uy = xdiv(dy, norm), uz = xdiv(dz, norm);
+  float zmin = 99999.0f, zmax = -99999.0f;
+  bool any = false;
+  auto test = [&](float4 q) {
+    float z0 = xadd(xadd(xmul(q.x, ux), xmul(q.y, uy)), xmul(q.z, uz));
+    float tmp = xsub(q.w, xmul(z0, z0));
+    if (tmp < gamma2) {
+      float del = xsqrt(xsub(gamma2, tmp));
+      zmin = fminf(zmin, xsub(z0, del));
+      zmax = fmaxf(zmax, xadd(z0, del));
+      any = true;
+    }
+  };
+  const GgFrame f = *fr;
+  bool full = !f.ok || *bad != 0;
+  int tile = -1;
+  if (!full) {
+    float s = ux * f.c[0] + uy * f.c[1] + uz * f.c[2];
+    if (fabsf(s) > 1e-6f) {
+      float a = (ux * f.e1[0] + uy * f.e1[1] + uz * f.e1[2]) / s, b = (ux * f.e2[0] + uy * f.e2[1] + uz * f.e2[2]) / s;
+      float fa = (a - f.a0) * f.inv_da, fb = (b - f.b0) * f.inv_db;
+      if (fa >= 0.f && fb >= 0.f && fa < (float)GG_TILES && fb < (float)GG_TILES) tile = (int)fb * GG_TILES + (int)fa;
+    }
+  }
+  int n = 0;
+  if (tile >= 0) {
+    n = __ldg(counts + tile);
+    if (n > GG_CAP) full = true;  // overfull tile
+  }
+  if (full) {
+    // exhaustive: cull by the padded vertex box first (the line can be within gamma of a vertex only if it meets the box)
     const float pad = gamma * 1.001f + 1e-4f;
     float t0 = -3e38f, t1 = 3e38f;
     const float u[3] = {ux, uy, uz};
@@ -691,33 +792,19 @@ __global__ void __launch_bounds__(GG_THREADS) gg_bounds_kernel(const float4* __r
         t1 = fminf(t1, fmaxf(a, b));
       }
     }
-    maybe = ok && (t0 <= t1 * (1.0f + 1e-5f) + 1e-5f);
+    if (ok && (t0 <= t1 * (1.0f + 1e-5f) + 1e-5f))
+      for (int i = lane; i < V; i += 32) test(__ldg(vq + i));
+  } else {
+    const int* __restrict__ L = lists + tile * GG_CAP;
+    for (int i = lane; i < n; i += 32) test(__ldg(vq + __ldg(L + i)));
   }
-  float zmin = 99999.0f, zmax = -99999.0f;
-  bool any = false;
-  if (__syncthreads_or(maybe)) {
-    for (int base = 0; base < V; base += GG_VCHUNK) {
-      int n = min(GG_VCHUNK, V - base);
-      __syncthreads();
-      for (int i = threadIdx.x; i < n; i += GG_THREADS) sv[i] = vq[base + i];
-      __syncthreads();
-      if (maybe) {
-#pragma unroll 4
-        for (int i = 0; i < n; ++i) {
-          float4 q = sv[i];
-          float z0 = xadd(xadd(xmul(q.x, ux), xmul(q.y, uy)), xmul(q.z, uz));
-          float tmp = xsub(q.w, xmul(z0, z0));
-          if (tmp < gamma2) {
-            float del = xsqrt(xsub(gamma2, tmp));
-            zmin = fminf(zmin, xsub(z0, del));
-            zmax = fmaxf(zmax, xadd(z0, del));
-            any = true;
-          }
-        }
-      }
-    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+    zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
   }
-  if (!live) return;
+  any = __any_sync(0xffffffffu, any);
+  if (lane != 0) return;
   zmin = xdiv(zmin, norm);
   zmax = xdiv(zmax, norm);
   bool use = any && (zmin < zmax);

@@ -402,7 +402,7 @@ int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStrea
     shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
     CKL("shade");
   } else {
-    light_tc_kernel<<<ctx->sm_count * 3, LT_THREADS, LT_SMEM, st>>>(sa, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
+    light_tc_kernel<<<ctx->sm_count * 2, LT_THREADS, LT_SMEM, st>>>(sa, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
     CKL("light_tc");
   }
   return 0;

@@ -299,9 +299,11 @@ __device__ __forceinline__ int parent_cell(const Grid& g, int cell) {  // enumer
 }
 // table cell of a point, or -1 when the point is outside the table or in a provably far enumeration cell
 __device__ __forceinline__ int live_cell(const Grid& g, float px, float py, float pz) {
-  int cell = table_cell(g, px, py, pz);
-  if (cell >= 0 && __ldg(g.enum_far + parent_cell(g, cell))) cell = -1;
-  return cell;
+  float fx = (px - g.ox) * g.tinv, fy = (py - g.oy) * g.tinv, fz = (pz - g.oz) * g.tinv;
+  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.tnx && fy < (float)g.tny && fz < (float)g.tnz)) return -1;
+  const int tx = (int)fx, ty = (int)fy, tz = (int)fz;
+  if (__ldg(g.enum_far + ((tz >> 1) * g.ny + (ty >> 1)) * g.nx + (tx >> 1))) return -1;
+  return (tz * g.tny + ty) * g.tnx + tx;
 }
 // byte-wide "0 -> 1" compare-and-swap through the containing word; true for the one thread that made the transition
 __device__ __forceinline__ bool claim_byte(unsigned char* bytes, int i) {
@@ -849,8 +851,10 @@ struct WarpArgs {
 constexpr int WARP_THREADS = 256;
 
 __device__ __forceinline__ void sample_position(const WarpArgs& a, int64_t s, float& px, float& py, float& pz) {
-  int64_t r = s / a.N;
-  int i = (int)(s - r * a.N);
+  int64_t r;
+  int i;
+  if (s < 0x7fffffffLL) { unsigned q = (unsigned)s / (unsigned)a.N; r = q; i = (int)((unsigned)s - q * (unsigned)a.N); }  // (64-bit division is ~5x dearer)
+  else { r = s / a.N; i = (int)(s - r * a.N); }
   float z = a.z_in ? a.z_in[s] : sample_z(a.near[r], a.far[r], __ldg(a.tvals + i));
   px = xadd(a.ray_o[3 * r], xmul(a.ray_d[3 * r], z));
   py = xadd(a.ray_o[3 * r + 1], xmul(a.ray_d[3 * r + 1], z));

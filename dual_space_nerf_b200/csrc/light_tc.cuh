@@ -7,8 +7,10 @@
 //      second layer.  Its weights are packed on the host into the B-operand image and fetched once per CTA with
 //      cp.async.bulk, so they stay resident in shared memory for every tile of the CTA;
 //   C. tcgen05.ld of the thread's accumulator row, bias + ReLU + 128 -> 1 dot + ELU in fp32, colour = (out+1)*essence.
-// ~71 KB of shared memory and 128 TMEM columns per CTA: three CTAs share an SM, so phases A/C of one CTA overlap the
-// MMAs of another.  Only the middle layer is rounded to fp16 (single pass): the lighting term is smooth and enters the
+// A CTA runs TWO such tiles side by side (256 threads: two independent 4-warp halves with their own A operand,
+// accumulator, mbarrier and named barrier) on one copy of the second-layer weights: ~103 KB of shared memory and 256 TMEM
+// columns per CTA, two CTAs = 16 warps per SM.  The kernel is latency bound (dependent gathers of shade_inputs), so the
+// number of independent tiles in flight per SM is what counts (3 x 4 warps with one tile per CTA: 1.72 ms).  Only the middle layer is rounded to fp16 (single pass): the lighting term is smooth and enters the
 // colour linearly (measured effect on |d rgb| is ~1e-5); the fp32 SIMT kernel in shade.cuh remains as
 // the verification path.
 #pragma once
@@ -17,33 +19,38 @@
 
 namespace dsn {
 
-constexpr int LT_THREADS = 128;
+constexpr int LT_THREADS = 256;
+constexpr int LT_ROWS = 128;                        // rows (samples) per half
 constexpr uint32_t LT_SM_W2 = 0;                    // B operand: [16 k-chunks][128 rows][8] fp16 = 32 KB
-constexpr uint32_t LT_SM_A = 32768;                 // A operand: [16 k-chunks][128 rows][8] fp16 = 32 KB
-constexpr uint32_t LT_SM_W1 = 65536;                // fp32 [128][12]: 9 weights, bias, 2 pad
+constexpr uint32_t LT_SM_A = 32768;                 // A operands: 2 halves x [16 k-chunks][128 rows][8] fp16 = 2 x 32 KB
+constexpr uint32_t LT_SM_W1 = 98304;                // fp32 [128][12]: 9 weights, bias, 2 pad
 constexpr uint32_t LT_SM_B2 = LT_SM_W1 + 128 * 12 * 4;
 constexpr uint32_t LT_SM_W3 = LT_SM_B2 + 512;
-constexpr uint32_t LT_SM_BAR = LT_SM_W3 + 512;      // 2 mbarriers + tmem slot
+constexpr uint32_t LT_SM_BAR = LT_SM_W3 + 512;      // 3 mbarriers + tmem slot
 constexpr uint32_t LT_SMEM = LT_SM_BAR + 64;
-constexpr uint32_t LT_TMEM_COLS = 128;
+constexpr uint32_t LT_TMEM_COLS = 256;
 
-__global__ void __launch_bounds__(LT_THREADS, 3) light_tc_kernel(ShadeArgs a, LightWeights L, const uint8_t* __restrict__ w2_packed, Grid gc) {
+__global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, LightWeights L, const uint8_t* __restrict__ w2_packed, Grid gc) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_w = sbase + LT_SM_BAR, bar_mma = bar_w + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + LT_SM_BAR + 16);
+  const int half = threadIdx.x >> 7;                 // independent 4-warp half of the CTA
+  const int row = threadIdx.x & (LT_ROWS - 1);
+  const int hwarp = (threadIdx.x >> 5) & 3;          // warp within the half = TMEM lane quarter
+  const uint32_t bar_w = sbase + LT_SM_BAR, bar_mma = bar_w + 8 + 8 * half;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + LT_SM_BAR + 24);
   float* w1p = reinterpret_cast<float*>(smem + LT_SM_W1);
   float* b2 = reinterpret_cast<float*>(smem + LT_SM_B2);
   float* w3 = reinterpret_cast<float*>(smem + LT_SM_W3);
-  const int warp = threadIdx.x >> 5;
-  const int row = threadIdx.x;
+  uint8_t* a_op = smem + LT_SM_A + half * 32768;
+  auto half_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(bar_w + 8, 1);
+    mbar_init(bar_w + 16, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -55,19 +62,19 @@ __global__ void __launch_bounds__(LT_THREADS, 3) light_tc_kernel(ShadeArgs a, Li
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = *tmem_slot + (uint32_t)half * 128u;
   if (threadIdx.x == 0) {  // second-layer weights: one bulk copy, resident for the whole kernel
     mbar_expect_tx(bar_w, 32768);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(sbase + LT_SM_W2), "l"(w2_packed), "r"(32768u), "r"(bar_w) : "memory");
   }
   const int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
-  const int64_t n_tiles = (n_active + LT_THREADS - 1) / LT_THREADS;
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const int64_t n_tiles = (n_active + LT_ROWS - 1) / LT_ROWS;
+  const uint32_t t_lane = tmem + ((uint32_t)(hwarp * 32) << 16);
   uint32_t mma_phase = 0;
   bool w_ready = false;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t t = tile * LT_THREADS + row;
+  for (int64_t tile = (int64_t)blockIdx.x * 2 + half; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
+    const int64_t t = tile * LT_ROWS + row;
     const bool live = t < n_active;
     float in[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float4 ma = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -92,22 +99,22 @@ __global__ void __launch_bounds__(LT_THREADS, 3) light_tc_kernel(ShadeArgs a, Li
         }
         pk[e / 2] = pack_h2(hv[0], hv[1]);
       }
-      *reinterpret_cast<uint4*>(smem + LT_SM_A + (uint32_t)kc * (LT_THREADS * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(a_op + (uint32_t)kc * (LT_ROWS * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     fence_proxy_async();
-    __syncthreads();
+    half_bar();
     // ---- second layer on the tensor core
-    if (warp == 0) {
+    if (hwarp == 0) {
       if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
       tc_fence_after();
       if (elect_one()) {
         constexpr uint32_t DHI = (128u >> 4) | (1u << 14);
-        constexpr uint32_t LBO = ((LT_THREADS * 16) >> 4) << 16;
+        constexpr uint32_t LBO = ((LT_ROWS * 16) >> 4) << 16;
         constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t a0 = LBO | ((sbase + LT_SM_A) >> 4), b0 = LBO | ((sbase + LT_SM_W2) >> 4);
+        const uint32_t a0 = LBO | ((sbase + LT_SM_A + half * 32768) >> 4), b0 = LBO | ((sbase + LT_SM_W2) >> 4);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint32_t step = (uint32_t)k * ((2 * LT_THREADS * 16) >> 4);
+          const uint32_t step = (uint32_t)k * ((2 * LT_ROWS * 16) >> 4);
           tc_mma_ss(tmem, ((uint64_t)DHI << 32) | (a0 + step), ((uint64_t)DHI << 32) | (b0 + step), IDESC, k > 0 ? 1u : 0u);
         }
         tc_commit(bar_mma);
@@ -136,15 +143,15 @@ __global__ void __launch_bounds__(LT_THREADS, 3) light_tc_kernel(ShadeArgs a, Li
     const float light = (out > 0.f ? out : expm1f(out)) + 1.0f;
     if (live) a.raw[sample] = make_float4(light * ma.y, light * ma.z, light * ma.w, ma.x);
     tc_fence_before();
-    __syncthreads();  // accumulator and A operand are reused by the next tile
+    half_bar();  // accumulator and A operand are reused by the half's next tile
     tc_fence_after();
   }
-  if (warp == 0 && !w_ready) mbar_wait(bar_w, 0);  // never leave with the bulk copy in flight
+  if (hwarp == 0 && !w_ready) mbar_wait(bar_w, 0);  // never leave with the bulk copy in flight
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (threadIdx.x < 32) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(LT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(LT_TMEM_COLS) : "memory");
   }
 }
 

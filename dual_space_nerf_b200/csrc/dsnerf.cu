@@ -484,7 +484,8 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   wa.counters = cnt;
   wa.count_candidates = (ctx->profile & 2) ? 1 : 0;
   if (int e = ensure_cells(ctx, ctx->g_posed, st, [&] {
-        mark_samples_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
+        const int64_t mark_threads = R * ((N + MARK_SPT - 1) / MARK_SPT);
+        mark_samples_kernel<<<(unsigned)((mark_threads + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
       }))
     return e;
   sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);

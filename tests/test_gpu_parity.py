@@ -155,6 +155,18 @@ def test_lazy_table_candidate_lists_vs_bruteforce(state_dict):
             assert C.bits_equal(act[:m, :3][order], cano[want]) == 0
 
 
+def test_sample_count_not_multiple_of_8_vs_oracle(scene64, state_dict):
+    """A sample count that is neither a power of two nor a multiple of 8 (ragged chunks in the marking kernel)."""
+    sc = scene64
+    rays = np.nonzero(sc["hit_box"])[0][::3]
+    n = 20
+    r = make_renderer(sc, n)
+    out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    ref, st = oracle_run(sc, state_dict, n, rays)
+    assert np.array_equal(out["z_vals"], ref["z_vals"])
+    C.check_rays(out, ref, kink_rays(st, n), what="n_samples = 20")
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

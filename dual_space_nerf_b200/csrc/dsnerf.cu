@@ -234,7 +234,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   g.tstate = mg.tstate.as<unsigned char>();
   g.trec = mg.trec.as<int2>();
   g.pool = mg.pool.as<float4>();
-  g.pool_cap = kPoolEntries;
+  g.pool_cap = (ctx->profile & 32) ? 4096 : kPoolEntries;  // profile bit 32 (tests): tiny pool, most cells fall back to the ball scan
   g.pool_used = mg.pool_used.as<int>();
   g.req2 = mg.req.as<int>();
   g.enum_far = mg.efar.as<unsigned char>();
@@ -896,7 +896,7 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
 
 int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
   if (!ctx) return DSNERF_ERR_INVALID;
-  ctx->profile = enable & 31;
+  ctx->profile = enable & 63;
   return 0;
 }
 

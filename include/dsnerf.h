@@ -147,7 +147,9 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
 /* Profiling switches (bit mask): 1 = CUDA-event timing of the MLP kernel inside render calls
  * (read back with dsnerf_profile_read: accumulated milliseconds / launches since the last
  * reset); 2 = count nearest-centroid distance evaluations (dsnerf_stats_t.nn_candidates; slows
- * the warp kernel, never enable it in a timed run). */
+ * the warp kernel, never enable it in a timed run); 4 = clock stamps of the tensor-core kernel; 8, 16 = debug switches of its
+ * weight stream (garbage results); 32 = test switch: shrink the candidate-list pool of meshes built from now on to 4096
+ * entries so that most lookup cells take the ball-scan fallback (results must not change). */
 int dsnerf_profile(dsnerf_ctx* ctx, int enable);
 /* debug (profile bit 4): clock64 stamps of the tensor-core kernel's first tile, 64 values */
 int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out64);

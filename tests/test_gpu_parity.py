@@ -167,6 +167,52 @@ def test_sample_count_not_multiple_of_8_vs_oracle(scene64, state_dict):
     C.check_rays(out, ref, kink_rays(st, n), what="n_samples = 20")
 
 
+def test_gg_bounds_fallback_paths_bit_exact(state_dict):
+    """geometry_guided_ray_marching (utils/pts_utils.py:18-53) away from the benchmark camera: the direction-tile chart is
+    unusable when the common ray origin sits inside / right next to the body (exhaustive path), and rays may point anywhere.
+    near/far (through z_vals) must stay bit-identical to the oracle."""
+    from oracle import oracle as O
+
+    sc = S.make_scene(64, 64)
+    rng = np.random.RandomState(7)
+    n = 16
+    centre = sc["posed"].mean(0)
+    for origin in (centre, centre + np.array([0.0, -0.45, 0.3], np.float32), centre + np.array([0.0, -6.0, 0.0], np.float32)):
+        R = 3000
+        d = rng.randn(R, 3).astype(np.float32)
+        d[: R // 2] = (sc["posed"][rng.randint(0, len(sc["posed"]), R // 2)] - origin + 0.03 * rng.randn(R // 2, 3)).astype(np.float32)
+        s2 = dict(sc)
+        s2["ray_o"] = np.repeat(origin[None].astype(np.float32), R, 0)
+        s2["ray_d"] = d
+        s2["near"] = np.full(R, 0.1, np.float32)
+        s2["far"] = np.full(R, 4.0, np.float32)
+        r = make_renderer(s2, n)
+        b = S.to_batch(s2, torch)
+        out = to_np(r.render(b)["coarse"])
+        _, z, _, _ = O.gg_sampling(s2["ray_o"], s2["ray_d"], n, s2["near"], s2["far"], s2["posed"])
+        assert np.array_equal(out["z_vals"], z), f"origin {origin}"
+        assert (z[:, 0] != 0.1).mean() > 0.2  # GG did move near/far for a good share of the rays
+
+
+def test_tiny_candidate_pool_falls_back_to_scans(scene64, state_dict):
+    """With the candidate-list pool shrunk to 4096 entries most lookup cells take the ball-scan fallback: identical output."""
+    sc = scene64
+    rays = np.nonzero(sc["hit_box"])[0][::2]
+    r1 = make_renderer(sc, 32)
+    a = to_np(r1.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    r2 = make_renderer(sc, 32)
+    r2.ctx.profile(32)
+    import ctypes
+
+    faces = np.ascontiguousarray(sc["faces"], np.int32)
+    canon = np.ascontiguousarray(sc["canonical"], np.float32)
+    r2.ctx.check(r2.ctx.L.dsnerf_set_mesh(r2.ctx.h, faces.ctypes.data_as(ctypes.c_void_p), faces.shape[0],
+                                          canon.ctypes.data_as(ctypes.c_void_p), canon.shape[0]))  # rebuild the canonical grid with the tiny pool
+    b = to_np(r2.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    for k in ("color", "depth_map", "acc_map", "z_vals"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

@@ -364,13 +364,21 @@ __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py
     x1 = 63 - __clzll((long long)m);
     const int row = (cz * g.ny + cy) * g.nx;
     const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
-    for (int j = b; j < e; ++j) visit(__ldg(g.sorted + j));
+    if (b < e) {
+      float4 q = __ldg(g.sorted + b);
+      for (int j = b + 1; j < e; ++j) {
+        const float4 qn = __ldg(g.sorted + j);  // next load in flight while q is visited
+        visit(q);
+        q = qn;
+      }
+      visit(q);
+    }
   }
   __syncwarp();
 }
 
 constexpr int LIST_CAP = 64;      // longest candidate list kept; longer ones fall back to the ball scan
-constexpr int BUF_CAP = 640;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
+constexpr int BUF_CAP = 448;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
 constexpr int BUILD_WARPS = 4;
 
 // Candidate filter of a cube (centre x, half edge a) against a reference centroid r with |x - r|^2 = dr2: a centroid q
@@ -543,7 +551,6 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
         __syncwarp();
         if (lane == 0) {
           g.trec[child] = rec;
-          __threadfence();
           g.tstate[child] = 2;
           if (g.debug) { atomicAdd(g.pool_used + ck, 1); if (rec.y > 0) atomicAdd(g.pool_used + 8, rec.y); }
         }

@@ -314,6 +314,44 @@ __device__ __forceinline__ int pe_k0(int sub) { return sub == 0 ? 0 : (sub == 1 
 // (sub 0: 0..14, sub 1: 15..32, sub 2: 33..50, sub 3: 51..63)
 __device__ __forceinline__ int pe_ld0(int sub) { return sub == 0 ? 0 : (sub == 1 ? 8 : 32); }
 
+// sin / cos of 2^k * x for the positional encoding, ~30 instructions instead of sincosf's ~60 (the encoding is 30 sincos per
+// point, ~4.5 k cycles of the whole SM per tile with sincosf).  y = x / 2pi is held as a two-float (yh, yl); 2^k * y is exact,
+// its fraction is reduced to |r| <= 1/8 turn exactly, and sin / cos (2 pi r) are degree-9 / degree-8 polynomials in r with the
+// low part of r folded in.  Max |error| 8e-8 against float64 over |x| <= 30, k = 0..9 (tests/test_host.py restates and checks
+// it; CUDA's sincosf is <= 1.2e-7 there).  The reference's torch.sin / cos (model/dimension_kernel.py:27-33) carry ~6e-8.
+__device__ __forceinline__ void pe_turns(float x, float& yh, float& yl) {
+  const float chi = 0.15915493667125702f, clo = 6.4206382432985265e-09f;  // 1 / 2pi = chi + clo
+  yh = __fmul_rn(x, chi);
+  yl = __fmaf_rn(x, clo, __fmaf_rn(x, chi, -yh));
+}
+__device__ __forceinline__ void pe_sincos(float yh, float yl, int k, float& sn, float& cs) {
+  const float sc = __int_as_float((127 + k) << 23);  // 2^k
+  const float th = yh * sc, tl = yl * sc;             // exact
+  const float fh = th - rintf(th);                    // exact, |fh| <= 1/2
+  const float q = rintf(fh * 4.0f);                   // quarter turns, -2..2
+  const float rh = __fmaf_rn(q, -0.25f, fh);          // exact, |rh| <= 1/8
+  const float s = __fadd_rn(rh, tl);
+  const float e = __fsub_rn(tl, __fsub_rn(s, rh));    // s + e = rh + tl
+  const float u = s * s;
+  float ps = 41.46822738647461f;
+  ps = __fmaf_rn(ps, u, -76.69773864746094f);
+  ps = __fmaf_rn(ps, u, 81.6052017211914f);
+  ps = __fmaf_rn(ps, u, -41.34170150756836f);
+  ps = __fmaf_rn(ps, u, -1.7484555e-07f);             // low part of 2 pi
+  float pc = 59.41782760620117f;
+  pc = __fmaf_rn(pc, u, -85.44869995117188f);
+  pc = __fmaf_rn(pc, u, 64.93936920166016f);
+  pc = __fmaf_rn(pc, u, -19.739208221435547f);
+  const float s0 = __fmaf_rn(s, ps, s * 6.2831854820251465f);
+  const float c0 = __fmaf_rn(pc, u, 1.0f);
+  const float e2 = e * 6.2831854820251465f;
+  const float s1 = __fmaf_rn(e2, c0, s0), c1 = __fmaf_rn(-e2, s0, c0);
+  const int qi = (int)q & 3;
+  const float a = (qi & 1) ? c1 : s1, b = (qi & 1) ? s1 : c1;  // (sin, cos) before the signs
+  sn = (qi & 2) ? -a : a;
+  cs = ((qi + 1) & 2) ? -b : b;
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -464,12 +502,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         } else if (sub == 3) {
           put(63, 0.f);
         }
+        float yh[3], yl[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pe_turns(xs[c], yh[c], yl[c]);
         for (int k = k_lo; k < k_hi; ++k) {
-          float f = (float)(1 << k);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float sn, cs;
-            sincosf(xs[c] * f, &sn, &cs);
+            pe_sincos(yh[c], yl[c], k, sn, cs);
             put(3 + 6 * k + c, sn);
             put(6 + 6 * k + c, cs);
           }

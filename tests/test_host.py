@@ -131,3 +131,55 @@ def test_sharded_render_equals_unsharded_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_pe_sincos_algorithm_accuracy():
+    """The tensor-core kernel's positional encoding does not call sincosf: csrc/mlp_tc.cuh:pe_sincos reduces 2^k * x / 2pi
+    exactly (two-float) and evaluates sin / cos (2 pi r), |r| <= 1/8, by polynomials.  Restated here operation by operation
+    in fp32 (fma emulated through float64) and held to 1e-7 absolute against float64 over the encoding's whole input range."""
+    f32 = np.float32
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+    def mul(a, b):
+        return (a.astype(np.float64) * b.astype(np.float64)).astype(f32)
+
+    def add(a, b):
+        return (a.astype(np.float64) + b.astype(np.float64)).astype(f32)
+
+    def full(x, v):
+        return np.full_like(x, f32(v))
+
+    rng = np.random.RandomState(0)
+    x = np.concatenate([rng.uniform(-1.5, 1.5, 200000), rng.uniform(-1e-3, 1e-3, 20000), rng.uniform(-30, 30, 30000),
+                        [0.0, 1.0, -1.0, 0.125, 0.25]]).astype(f32)
+    chi, clo = f32(0.15915493667125702), f32(6.4206382432985265e-09)
+    yh = mul(x, full(x, chi))
+    yl = fma(x, full(x, clo), fma(x, full(x, chi), -yh))
+    for k in range(10):
+        sc = f32(2.0 ** k)
+        th, tl = mul(yh, full(x, sc)), mul(yl, full(x, sc))
+        fh = add(th, -np.rint(th).astype(f32))
+        q = np.rint(mul(fh, full(x, 4.0))).astype(f32)
+        rh = fma(q, full(x, -0.25), fh)
+        s = add(rh, tl)
+        e = add(tl, -add(s, -rh))
+        u = mul(s, s)
+        ps = full(x, 41.46822738647461)
+        for c in (-76.69773864746094, 81.6052017211914, -41.34170150756836, -1.7484555e-07):
+            ps = fma(ps, u, full(x, c))
+        pc = full(x, 59.41782760620117)
+        for c in (-85.44869995117188, 64.93936920166016, -19.739208221435547):
+            pc = fma(pc, u, full(x, c))
+        s0 = fma(s, ps, mul(s, full(x, 6.2831854820251465)))
+        c0 = fma(pc, u, full(x, 1.0))
+        e2 = mul(e, full(x, 6.2831854820251465))
+        s1, c1 = fma(e2, c0, s0), fma(-e2, s0, c0)
+        qi = q.astype(np.int32) & 3
+        a = np.where(qi & 1, c1, s1)
+        b = np.where(qi & 1, s1, c1)
+        sn = np.where(qi & 2, -a, a)
+        cs = np.where((qi + 1) & 2, -b, b)
+        arg = x.astype(np.float64) * 2.0 ** k
+        assert np.abs(sn - np.sin(arg)).max() < 1e-7 and np.abs(cs - np.cos(arg)).max() < 1e-7, k

@@ -881,6 +881,18 @@ int dsnerf_resample(dsnerf_ctx* ctx, const float* z_in, const float* weights, in
   return 0;
 }
 
+int dsnerf_ppts_to_pts(dsnerf_ctx* ctx, const float* ppts, const float* bw, const float* A, int64_t P, float* out, void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (P < 0) return fail(ctx, DSNERF_ERR_INVALID, "bad size");
+  if (P == 0) return 0;
+  if (!ppts || !bw || !A || !out) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  lbs_inverse_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(ppts, bw, A, P, out);
+  CKL("lbs_inverse");
+  return 0;
+}
+
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
   if (!ctx || !out) return DSNERF_ERR_INVALID;
   if (ctx->stats.rays > 0) {

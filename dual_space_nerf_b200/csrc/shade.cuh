@@ -283,4 +283,34 @@ __global__ void __launch_bounds__(128) resample_kernel(const float* __restrict__
   }
 }
 
+// utils/blend_utils.py:72-81 ppts_to_pts: x_c = R^-1 (x_p - t) with [R|t] = sum_j bw[j] A_j (no caller in the reference;
+// SURVEY.md 8a #23).  One thread per point; HBM bound: 27 floats in (3 + 24 weights, coalesced along p), 3 out = 120 B/point;
+// the 24 joint transforms (1.5 KB) are staged in shared memory.  The blended 3x3 is inverted through its cofactors.
+__global__ void __launch_bounds__(256) lbs_inverse_kernel(const float* __restrict__ ppts, const float* __restrict__ bw,
+                                                          const float* __restrict__ A, int64_t P, float* __restrict__ out) {
+  __shared__ float sA[24 * 12];  // rows 0..2 of each 4x4
+  for (int i = threadIdx.x; i < 24 * 12; i += blockDim.x) sA[i] = A[(i / 12) * 16 + (i % 12)];
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float m[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) m[k] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < 24; ++j) {
+    const float w = __ldg(bw + (int64_t)j * P + p);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) m[k] = fmaf(w, sA[j * 12 + k], m[k]);
+  }
+  const float dx = ppts[3 * p] - m[3], dy = ppts[3 * p + 1] - m[7], dz = ppts[3 * p + 2] - m[11];
+  // cofactors of R = [m0 m1 m2; m4 m5 m6; m8 m9 m10]
+  const float c00 = m[5] * m[10] - m[6] * m[9], c01 = m[6] * m[8] - m[4] * m[10], c02 = m[4] * m[9] - m[5] * m[8];
+  const float c10 = m[2] * m[9] - m[1] * m[10], c11 = m[0] * m[10] - m[2] * m[8], c12 = m[1] * m[8] - m[0] * m[9];
+  const float c20 = m[1] * m[6] - m[2] * m[5], c21 = m[2] * m[4] - m[0] * m[6], c22 = m[0] * m[5] - m[1] * m[4];
+  const float inv = 1.0f / (m[0] * c00 + m[1] * c01 + m[2] * c02);  // singular blend -> inf / NaN (torch.inverse raises)
+  out[3 * p] = (c00 * dx + c10 * dy + c20 * dz) * inv;
+  out[3 * p + 1] = (c01 * dx + c11 * dy + c21 * dz) * inv;
+  out[3 * p + 2] = (c02 * dx + c12 * dy + c22 * dz) * inv;
+}
+
 }  // namespace dsn

@@ -141,6 +141,12 @@ int dsnerf_query_density(dsnerf_ctx* ctx, const float* xyz_cano, const uint8_t* 
 int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz_cano, const float* view_dir,
                        int64_t n_pts, float* color, float* density, unsigned flags, void* stream);
 
+/* utils/blend_utils.py:72-81 ppts_to_pts (inverse linear-blend skinning; no caller inside the reference):
+ * ppts (P,3) posed points, bw (24,P) blend weights, A (24,4,4) joint transforms -> out (P,3) = R^-1 (p - t) with
+ * [R|t] = sum_j bw[j,p] A[j].  DEVICE pointers, one batch element per call.  A singular blend gives inf/NaN (torch.inverse
+ * raises there).  Needs no weights / mesh / frame. */
+int dsnerf_ppts_to_pts(dsnerf_ctx* ctx, const float* ppts, const float* bw, const float* A, int64_t n_pts, float* out, void* stream);
+
 /* Counters of the last render on this context (synchronises the stream it ran on). */
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
 

@@ -289,6 +289,18 @@ def sample_pdf(z_vals, weights, n_importance):
     return np.sort(np.concatenate([z_vals, out], -1), -1).astype(f32)
 
 
+# --------------------------------------------------------------------------- inverse LBS (auxiliary op)
+def ppts_to_pts(pts, bw, A):
+    """utils/blend_utils.py:72-81 (the binding definition of ppts_to_pts): blend the 24 joint transforms with the per-point
+    weights, subtract the blended translation, multiply by the inverse of the blended 3x3.
+    pts (P,3), bw (24,P), A (24,4,4) -> (P,3), fp32 throughout (torch.bmm / torch.inverse on CPU)."""
+    pts = np.ascontiguousarray(pts, f32)
+    Ap = (np.ascontiguousarray(bw, f32).T @ np.ascontiguousarray(A, f32).reshape(24, 16)).reshape(-1, 4, 4)
+    d = pts - Ap[:, :3, 3]
+    Rinv = np.linalg.inv(Ap[:, :3, :3]).astype(f32)
+    return np.sum(Rinv * d[:, None, :], axis=2, dtype=f32).astype(f32)
+
+
 # --------------------------------------------------------------------------- full path
 class Oracle:
     """Renderer.render / render_view restated (can_render.py:137-168, 248-278)."""

@@ -213,6 +213,30 @@ def test_tiny_candidate_pool_falls_back_to_scans(scene64, state_dict):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
 
 
+def test_ppts_to_pts_vs_reference_golden_and_oracle():
+    """inverse LBS op (utils/blend_utils.py:72-81) through the drop-in function: reference golden, oracle on a
+    larger random case, batch > 1, empty input.  fp32 with a cofactor inverse vs torch's LU: tolerance 5e-6 absolute."""
+    from oracle import oracle as O
+    from dual_space_nerf_b200 import blend
+    from make_golden_lbs import make_inputs
+
+    g = C.golden("lbs_ppts_to_pts.npz")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out = blend.ppts_to_pts(t(g["pts"])[None], t(g["bw"])[None], t(g["A"])[None])
+    assert out.shape == (1,) + g["out"].shape
+    assert np.abs(out[0].cpu().numpy() - g["out"]).max() < 5e-6
+    pts, bw, A = make_inputs(P=100_003, seed=5)
+    pts2, bw2, A2 = make_inputs(P=100_003, seed=6)
+    out = blend.ppts_to_pts(torch.stack([t(pts), t(pts2)]), torch.stack([t(bw), t(bw2)]), torch.stack([t(A), t(A2)])).cpu().numpy()
+    assert np.abs(out[0] - O.ppts_to_pts(pts, bw, A)).max() < 5e-6
+    assert np.abs(out[1] - O.ppts_to_pts(pts2, bw2, A2)).max() < 5e-6
+    # round trip: posing the canonical result with the blended transform gives the posed point back
+    Ap = (bw.T @ A.reshape(24, 16)).reshape(-1, 4, 4)
+    back = np.einsum("pij,pj->pi", Ap[:, :3, :3], out[0]) + Ap[:, :3, 3]
+    assert np.abs(back - pts).max() < 1e-5
+    assert blend.ppts_to_pts(torch.empty(1, 0, 3).cuda(), torch.empty(1, 24, 0).cuda(), t(A)[None]).shape == (1, 0, 3)
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

@@ -151,3 +151,12 @@ def test_sample_pdf_properties():
     assert np.all(z2 >= z[:, :1]) and np.all(z2 <= z[:, -1:])
     for r in range(50):  # the coarse samples survive the merge
         assert np.all(np.isin(z[r], z2[r]))
+
+
+def test_ppts_to_pts_oracle_vs_reference_golden():
+    """oracle.ppts_to_pts against the golden made by the reference's own utils/blend_utils.py:ppts_to_pts (tests/make_golden_lbs.py).
+    fp32 blend + 3x3 inverse: tolerance 2e-6 absolute on points of magnitude <= 1.7."""
+    g = C.golden("lbs_ppts_to_pts.npz")
+    out = O.ppts_to_pts(g["pts"], g["bw"], g["A"])
+    assert out.dtype == np.float32 and out.shape == g["out"].shape
+    assert np.abs(out - g["out"]).max() < 2e-6

@@ -893,6 +893,36 @@ int dsnerf_ppts_to_pts(dsnerf_ctx* ctx, const float* ppts, const float* bw, cons
   return 0;
 }
 
+int dsnerf_camera_rays(dsnerf_ctx* ctx, int H, int W, const double* K, const double* R, const double* T, const float* bounds, float* ray_o,
+                       float* ray_d, float* near, float* far, uint8_t* mask_at_box, void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (H < 0 || W < 0) return fail(ctx, DSNERF_ERR_INVALID, "bad size");
+  if (H == 0 || W == 0) return 0;
+  if (!K || !R || !T || !bounds || !ray_o || !ray_d || !near || !far || !mask_at_box) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  CameraArgs c{};
+  // K^-1 through the cofactors, in double (np.linalg.inv(K), rays_utils.py:24)
+  const double a = K[0], b = K[1], cc = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i = K[8];
+  const double det = a * (e * i - f * h) - b * (d * i - f * g) + cc * (d * h - e * g);
+  if (!(fabs(det) > 0.0)) return fail(ctx, DSNERF_ERR_INVALID, "singular K");
+  const double inv[9] = {(e * i - f * h) / det, (cc * h - b * i) / det, (b * f - cc * e) / det, (f * g - d * i) / det, (a * i - cc * g) / det,
+                         (cc * d - a * f) / det, (d * h - e * g) / det, (b * g - a * h) / det, (a * e - b * d) / det};
+  for (int k = 0; k < 9; ++k) { c.kinv[k] = inv[k]; c.rot[k] = R[k]; }
+  for (int k = 0; k < 3; ++k) {
+    c.t[k] = T[k];
+    c.origin[k] = -(R[k] * T[0] + R[3 + k] * T[1] + R[6 + k] * T[2]);  // -R^T T
+    c.lo[k] = (double)bounds[k] - 0.01;
+    c.hi[k] = (double)bounds[3 + k] + 0.01;
+  }
+  c.H = H;
+  c.W = W;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  const int64_t P = (int64_t)H * W;
+  camera_rays_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(c, ray_o, ray_d, near, far, mask_at_box);
+  CKL("camera_rays");
+  return 0;
+}
+
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
   if (!ctx || !out) return DSNERF_ERR_INVALID;
   if (ctx->stats.rays > 0) {

@@ -313,4 +313,65 @@ __global__ void __launch_bounds__(256) lbs_inverse_kernel(const float* __restric
   out[3 * p + 2] = (c02 * dx + c12 * dy + c22 * dz) * inv;
 }
 
+// Camera rays on the device: utils/rays_utils.py:16-30 get_rays and :63-97 get_near_far as the
+// inference branch of my_sample_ray (:173-189) chains them.  The reference works in float64 (numpy) and casts to float32
+// at the end; so does this kernel, in the reference's operation order, which makes directions / near / far agree to the
+// last float32 bit except for double-rounding ties.  One thread per pixel; HBM bound: 33 B written per pixel.
+struct CameraArgs {
+  double kinv[9], rot[9], t[3], origin[3];  // K^-1, R, T, -R^T T
+  double lo[3], hi[3];                      // bounds already padded by -/+ 0.01
+  int H, W;
+};
+__global__ void __launch_bounds__(256) camera_rays_kernel(CameraArgs c, float* __restrict__ ray_o, float* __restrict__ ray_d,
+                                                          float* __restrict__ near, float* __restrict__ far, uint8_t* __restrict__ mask) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (int64_t)c.H * c.W) return;
+  const double i = (double)(int)(p % c.W), j = (double)(int)(p / c.W);
+  double cam[3], dir[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cam[k] = __dadd_rn(__dadd_rn(__dmul_rn(i, c.kinv[3 * k]), __dmul_rn(j, c.kinv[3 * k + 1])), c.kinv[3 * k + 2]) - c.t[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    dir[k] = __dadd_rn(__dadd_rn(__dmul_rn(cam[0], c.rot[k]), __dmul_rn(cam[1], c.rot[3 + k])), __dmul_rn(cam[2], c.rot[6 + k])) - c.origin[k];
+  const float of[3] = {(float)c.origin[0], (float)c.origin[1], (float)c.origin[2]};
+  const float df[3] = {(float)dir[0], (float)dir[1], (float)dir[2]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ray_o[3 * p + k] = of[k]; ray_d[3 * p + k] = df[k]; }
+  // get_near_far on the float32 rays, in float64
+  const double o[3] = {of[0], of[1], of[2]}, d[3] = {df[0], df[1], df[2]};
+  const double eps = 1e-6;
+  int hits = 0;
+  double h0[3] = {0, 0, 0}, h1[3] = {0, 0, 0};
+#pragma unroll
+  for (int m = 0; m < 6; ++m) {
+    const double plane = m < 3 ? c.lo[m] : c.hi[m - 3];
+    const double t = (plane - o[m % 3]) / d[m % 3];
+    double q[3];
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      q[k] = __dadd_rn(__dmul_rn(t, d[k]), o[k]);
+      in = in && (q[k] >= c.lo[k] - eps) && (q[k] <= c.hi[k] + eps);
+    }
+    if (in) {
+      if (hits == 0) { h0[0] = q[0]; h0[1] = q[1]; h0[2] = q[2]; }
+      else if (hits == 1) { h1[0] = q[0]; h1[1] = q[1]; h1[2] = q[2]; }
+      ++hits;
+    }
+  }
+  const bool ok = hits == 2;
+  mask[p] = ok ? 1 : 0;
+  float n = 0.f, f = 0.f;
+  if (ok) {
+    auto norm3 = [](double x, double y, double z) { return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z))); };
+    // np.linalg.norm of the float32 directions stays in float32 (rays_utils.py:90)
+    const double nd = (double)__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(df[0], df[0]), __fmul_rn(df[1], df[1])), __fmul_rn(df[2], df[2])));
+    const double d0 = norm3(h0[0] - o[0], h0[1] - o[1], h0[2] - o[2]) / nd, d1 = norm3(h1[0] - o[0], h1[1] - o[1], h1[2] - o[2]) / nd;
+    n = (float)fmin(d0, d1);
+    f = (float)fmax(d0, d1);
+  }
+  near[p] = n;
+  far[p] = f;
+}
+
 }  // namespace dsn

@@ -35,6 +35,10 @@ def _load_bodydata(model_path, model_type="smpl", gender="neutral"):
         return pickle.load(f, encoding="latin1")
 
 
+def _np(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -231,6 +235,37 @@ class Renderer:
             out.update(fine_color=post(fine["color"], 3), fine_disp=post(fine["disp_map"], 1),
                        fine_acc=post(fine["acc_map"], 1), fine_depth=post(fine["depth_map"], 1))
         return out
+
+    # ------------------------------------------------------------------ camera in, image out
+    def camera_rays(self, H, W, K, R, T, bounds):
+        """utils/rays_utils.py:16-30 get_rays + :63-97 get_near_far on the device, over all H*W pixels (row-major):
+        returns ray_o, ray_d (H*W,3), near, far (H*W) float32 and mask_at_box (H*W) bool, all on this renderer's GPU."""
+        K = np.ascontiguousarray(_np(K), np.float64).reshape(3, 3)
+        R = np.ascontiguousarray(_np(R), np.float64).reshape(3, 3)
+        T = np.ascontiguousarray(_np(T), np.float64).reshape(3)
+        b = np.ascontiguousarray(_np(bounds), np.float32).reshape(6)
+        P = int(H) * int(W)
+        dev = self.device
+        ro, rd = torch.empty(P, 3, device=dev), torch.empty(P, 3, device=dev)
+        ne, fa = torch.empty(P, device=dev), torch.empty(P, device=dev)
+        mk = torch.empty(P, device=dev, dtype=torch.uint8)
+        hp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        with torch.cuda.device(dev):
+            self.ctx.check(self.ctx.L.dsnerf_camera_rays(self.ctx.h, int(H), int(W), hp(K), hp(R), hp(T), hp(b), _ptr(ro), _ptr(rd), _ptr(ne),
+                                                         _ptr(fa), _ptr(mk), self._stream()))
+        return ro, rd, ne, fa, mk.bool()
+
+    def render_view_camera(self, batch):
+        """render_view for a batch that carries the camera instead of rays: `K`, `R`, `T`, `bounds` (2,3), `H`, `W` plus the
+        usual `xyz`, `poses`, `frame` (`Th`).  Rays, near/far and mask_at_box (what the reference's dataloader computes with
+        numpy, rays_utils.py:173-189) are generated on the GPU, the masked rays are rendered, and the per-ray outputs are
+        scattered into (H, W, C) images as render_view does.  Saves the per-frame host ray generation and the 8 MB H2D."""
+        H, W = int(batch["H"]), int(batch["W"])
+        ro, rd, ne, fa, mask = self.camera_rays(H, W, batch["K"], batch["R"], batch["T"], batch["bounds"])
+        b = dict(batch)
+        b.update(ray_o=ro[mask][None], ray_d=rd[mask][None], near=ne[mask][None], far=fa[mask][None], mask_at_box=mask[None],
+                 img=torch.zeros(1, H, W, 3))
+        return self.render_view(b)
 
     # ------------------------------------------------------------------ secondary surface
     def w2l_without_lbs(self, pts_world, batch, canonical_model=None, ray_d_W=None, floor=-4, ceil=5, return_idx=False):

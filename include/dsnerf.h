@@ -147,6 +147,14 @@ int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz
  * raises there).  Needs no weights / mesh / frame. */
 int dsnerf_ppts_to_pts(dsnerf_ctx* ctx, const float* ppts, const float* bw, const float* A, int64_t n_pts, float* out, void* stream);
 
+/* Camera rays on the device: utils/rays_utils.py:16-30 get_rays + :63-97 get_near_far (the inference branch of
+ * my_sample_ray, :173-189).  K, R (3x3 row-major) and T (3) are HOST doubles, bounds HOST floats (min xyz, max xyz; the
+ * 0.01 pad of get_near_far is applied here).  Outputs are DEVICE buffers over all H*W pixels in row-major pixel order:
+ * ray_o, ray_d (H*W,3), near, far (H*W; 0 where the ray misses) and mask_at_box (H*W bytes).  The reference then keeps the
+ * masked rays only (rays_utils.py:181-183): compact with the mask before calling dsnerf_render. */
+int dsnerf_camera_rays(dsnerf_ctx* ctx, int H, int W, const double* K, const double* R, const double* T, const float* bounds,
+                       float* ray_o, float* ray_d, float* near, float* far, uint8_t* mask_at_box, void* stream);
+
 /* Counters of the last render on this context (synchronises the stream it ran on). */
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
 

@@ -289,6 +289,40 @@ def sample_pdf(z_vals, weights, n_importance):
     return np.sort(np.concatenate([z_vals, out], -1), -1).astype(f32)
 
 
+# --------------------------------------------------------------------------- camera rays
+def camera_rays(H, W, K, R, T):
+    """utils/rays_utils.py:16-30 get_rays, inference layout: origin (3,) and directions (H*W,3) in float64 (the callers cast
+    to float32, rays_utils.py:175-176).  Pixel (i = column, j = row), xy1 = (i, j, 1)."""
+    K, R, T = np.asarray(K, np.float64), np.asarray(R, np.float64), np.asarray(T, np.float64).reshape(3)
+    origin = -(R.T @ T)
+    ii, jj = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64), indexing="xy")
+    xy1 = np.stack([ii, jj, np.ones_like(ii)], 2).reshape(-1, 3)
+    cam = xy1 @ np.linalg.inv(K).T
+    world = (cam - T[None]) @ R
+    return origin, world - origin[None]
+
+
+def box_near_far(bounds, ray_o, ray_d):
+    """utils/rays_utils.py:63-97 get_near_far: the six plane hits of every ray with the box padded by 0.01, the rays with
+    exactly two hits inside the (eps = 1e-6) box are kept; near / far = the two hit distances divided by |ray_d|.
+    Returns near, far for the kept rays (float64) and the mask over all rays."""
+    b = np.asarray(bounds, np.float64) + np.array([-0.01, 0.01])[:, None]
+    o, d = np.asarray(ray_o, np.float64), np.asarray(ray_d, np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = ((b[None] - o[:, None]) / d[:, None]).reshape(-1, 6)
+        pts = t[..., None] * d[:, None] + o[:, None]
+    eps = 1e-6
+    lo, hi = b[0] - eps, b[1] + eps
+    inside = np.all((pts >= lo) & (pts <= hi), axis=-1)
+    mask = inside.sum(-1) == 2
+    pair = pts[mask][inside[mask]].reshape(-1, 2, 3)
+    rd32 = np.asarray(ray_d, f32)[mask]  # np.linalg.norm of the float32 directions stays in float32 (rays_utils.py:90)
+    nd = np.sqrt(np.sum(rd32 * rd32, axis=1, dtype=f32), dtype=f32).astype(np.float64)
+    d0 = np.sqrt(np.sum((pair[:, 0] - o[mask]) ** 2, axis=1)) / nd
+    d1 = np.sqrt(np.sum((pair[:, 1] - o[mask]) ** 2, axis=1)) / nd
+    return np.minimum(d0, d1), np.maximum(d0, d1), mask
+
+
 # --------------------------------------------------------------------------- inverse LBS (auxiliary op)
 def ppts_to_pts(pts, bw, A):
     """utils/blend_utils.py:72-81 (the binding definition of ppts_to_pts): blend the 24 joint transforms with the per-point

@@ -237,6 +237,40 @@ def test_ppts_to_pts_vs_reference_golden_and_oracle():
     assert blend.ppts_to_pts(torch.empty(1, 0, 3).cuda(), torch.empty(1, 24, 0).cuda(), t(A)[None]).shape == (1, 0, 3)
 
 
+def test_camera_rays_vs_reference_golden(scene64, state_dict):
+    """device ray generation + box near/far + mask_at_box against the golden made by the reference's
+    get_rays / get_near_far.  Directions and origin bit-exact; near/far to 1 float32 ulp (float64 intermediate rounding may
+    differ from numpy's BLAS in the last double bit); mask identical.  Then render_view_camera == render_view on those rays."""
+    g = C.golden("camera_rays.npz")
+    r = make_renderer(scene64, 32)
+    for c in range(2):
+        H, W = int(g[f"H{c}"]), int(g[f"W{c}"])
+        ro, rd, ne, fa, mk = r.camera_rays(H, W, g[f"K{c}"], g[f"R{c}"], g[f"T{c}"], g[f"bounds{c}"])
+        mk = mk.cpu().numpy()
+        assert np.array_equal(mk, g[f"mask{c}"])
+        assert np.array_equal(ro.cpu().numpy(), np.broadcast_to(g[f"ray_o{c}"], (H * W, 3)))
+        assert C.bits_equal(rd.cpu().numpy(), g[f"ray_d{c}"]) == 0
+        for got, ref in ((ne, g[f"near{c}"]), (fa, g[f"far{c}"])):
+            got = got.cpu().numpy()[mk]
+            assert np.abs(got - ref).max() <= np.spacing(np.abs(ref).max().astype(np.float32))
+    # the camera of the synthetic scene: image through render_view_camera vs render_view on host-generated rays
+    sc = scene64
+    from oracle import oracle as O
+
+    o, d = O.camera_rays(sc["H"], sc["W"], sc["K"], sc["R"], sc["T"])
+    o32, d32 = np.broadcast_to(o.astype(np.float32), d.shape).copy(), d.astype(np.float32)
+    near, far, mask = O.box_near_far(sc["bounds"], o32, d32)
+    s2 = dict(sc)
+    s2.update(ray_o=o32[mask], ray_d=d32[mask], near=near.astype(np.float32), far=far.astype(np.float32), mask_at_box=mask)
+    a = r.render_view(S.to_batch(s2, torch))
+    b = S.to_batch(sc, torch)
+    b.update(K=sc["K"], R=sc["R"], T=sc["T"], bounds=sc["bounds"], H=sc["H"], W=sc["W"])
+    cam = r.render_view_camera(b)
+    for k in a:
+        assert torch.equal(torch.nan_to_num(a[k]), torch.nan_to_num(cam[k])), k
+    assert float(cam["coarse_acc"].max()) > 0.5
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

@@ -1,6 +1,8 @@
 """Pin the CPU oracle: against committed golden vectors generated from the
 unmodified reference (tests/make_golden.py) and, when /root/reference is
 present, against the live reference."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -160,3 +162,28 @@ def test_ppts_to_pts_oracle_vs_reference_golden():
     out = O.ppts_to_pts(g["pts"], g["bw"], g["A"])
     assert out.dtype == np.float32 and out.shape == g["out"].shape
     assert np.abs(out - g["out"]).max() < 2e-6
+
+
+def test_camera_rays_oracle_vs_reference_golden_and_live():
+    """oracle.camera_rays / box_near_far (utils/rays_utils.py:16-30, 63-97) against the golden made by the reference's own
+    functions (tests/make_golden_camera.py), and against the live reference when /root/reference is mounted."""
+    g = C.golden("camera_rays.npz")
+    for c in range(2):
+        H, W = int(g[f"H{c}"]), int(g[f"W{c}"])
+        o, d = O.camera_rays(H, W, g[f"K{c}"], g[f"R{c}"], g[f"T{c}"])
+        o32, d32 = o.astype(np.float32), d.astype(np.float32)
+        assert np.array_equal(o32, g[f"ray_o{c}"]) and np.array_equal(d32, g[f"ray_d{c}"])
+        near, far, mask = O.box_near_far(g[f"bounds{c}"], np.broadcast_to(o32, d32.shape), d32)
+        assert np.array_equal(mask, g[f"mask{c}"])
+        assert np.array_equal(near.astype(np.float32), g[f"near{c}"]) and np.array_equal(far.astype(np.float32), g[f"far{c}"])
+    ref = "/root/reference/utils/rays_utils.py"
+    if os.path.exists(ref):
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("ref_rays_utils", ref)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        sc = S.make_scene(32, 40)
+        ro, rd = m.get_rays(32, 40, sc["K"], sc["R"], sc["T"].reshape(3, 1))
+        o, d = O.camera_rays(32, 40, sc["K"], sc["R"], sc["T"])
+        assert np.array_equal(rd.reshape(-1, 3).astype(np.float32), d.astype(np.float32))

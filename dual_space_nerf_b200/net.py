@@ -101,6 +101,17 @@ class DualSpaceNeRF(nn.Module):
         self._weights_version += 1
         return out
 
+    def load_checkpoint(self, path, strict=True):
+        """Load a checkpoint file written by the reference's Checkpointer (utils/checkpoint.py:102-125: a dict whose
+        "model" entry is DualSpaceNeRF.state_dict(); validate.py:27 / test.py:192 do
+        `render.net.load_state_dict(torch.load(path)["model"])`).  A bare state_dict file is accepted too.  A "module."
+        prefix left by DataParallel wrappers is stripped."""
+        data = torch.load(path, map_location="cpu", weights_only=False)
+        sd = data["model"] if isinstance(data, dict) and "model" in data else data
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+        self.load_state_dict(sd, strict=strict)
+        return data
+
     def mark_weights_dirty(self):
         """Call after editing parameters in place so the library re-stages them."""
         self._weights_version += 1

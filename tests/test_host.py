@@ -183,3 +183,19 @@ def test_pe_sincos_algorithm_accuracy():
         cs = np.where((qi + 1) & 2, -b, b)
         arg = x.astype(np.float64) * 2.0 ** k
         assert np.abs(sn - np.sin(arg)).max() < 1e-7 and np.abs(cs - np.cos(arg)).max() < 1e-7, k
+
+
+def test_load_checkpoint_file(tmp_path):
+    """Checkpoint files of the reference (utils/checkpoint.py:102-125: {"model": state_dict, ...}) load into the container."""
+    import torch
+
+    from dual_space_nerf_b200 import net as N
+
+    src = N.synthetic_net(0)
+    path = tmp_path / "model_epoch_0000010.pth"
+    torch.save({"model": {"module." + k: v for k, v in src.state_dict().items()}, "epoch": 10}, path)
+    dst = N.DualSpaceNeRF(None)
+    data = dst.load_checkpoint(str(path))
+    assert data["epoch"] == 10
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k

@@ -73,13 +73,24 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
   const uint32_t t_lane = tmem + ((uint32_t)(hwarp * 32) << 16);
   uint32_t mma_phase = 0;
   bool w_ready = false;
+  // the records of the next tile are fetched while the current one is processed (they head a chain of ~6 dependent gathers)
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ac_n = zero4, ma_n = zero4, mg_n = zero4;
+  {
+    const int64_t t0 = ((int64_t)blockIdx.x * 2 + half) * LT_ROWS + row;
+    if (t0 < n_active) { ac_n = a.active[t0]; ma_n = a.mlp_a[t0]; mg_n = a.mlp_g[t0]; }
+  }
   for (int64_t tile = (int64_t)blockIdx.x * 2 + half; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
     const int64_t t = tile * LT_ROWS + row;
     const bool live = t < n_active;
     float in[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float4 ma = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 ac = ac_n, ma = ma_n, mg = mg_n;
+    {
+      const int64_t tn = t + (int64_t)gridDim.x * 2 * LT_ROWS;
+      if (tn < n_active) { ac_n = a.active[tn]; ma_n = a.mlp_a[tn]; mg_n = a.mlp_g[tn]; }
+    }
     int sample = 0;
-    if (live) shade_inputs(a, gc, t, in, sample, ma);
+    if (live) shade_inputs(a, gc, ac, mg, in, sample);
     // ---- first layer (fp32) -> fp16 A operand
 #pragma unroll 2
     for (int kc = 0; kc < 16; ++kc) {

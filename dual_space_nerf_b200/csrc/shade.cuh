@@ -67,10 +67,7 @@ __device__ __forceinline__ V3 normal_to_world(V3 g, V3 c0, V3 c1, V3 c2, V3 m0, 
 // Inputs of the lighting MLP for active sample t: world normal (normal_local2world, model/spacenet.py:278-298, incl. the
 // exact nearest canonical centroid), world position (with the optional rot / light_center shift, :254-263) and the
 // normalised view direction (:179-181).
-__device__ __forceinline__ void shade_inputs(const ShadeArgs& a, const Grid& gc, int64_t t, float (&in)[9], int& sample, float4& ma) {
-  float4 ac = a.active[t];
-  ma = a.mlp_a[t];
-  float4 mg = a.mlp_g[t];
+__device__ __forceinline__ void shade_inputs(const ShadeArgs& a, const Grid& gc, float4 ac, float4 mg, float (&in)[9], int& sample) {
   sample = __float_as_int(ac.w);
   // exact nearest canonical centroid through the canonical mesh's lookup table (cells requested by mark_points_kernel)
   int idx = table_nearest(gc, live_cell(gc, ac.x, ac.y, ac.z), ac.x, ac.y, ac.z);
@@ -119,9 +116,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, 3) shade_kernel(ShadeArgs a, Li
   int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
   for (int64_t t = (int64_t)blockIdx.x * SHADE_THREADS + threadIdx.x; t < n_active; t += (int64_t)gridDim.x * SHADE_THREADS) {
     float in[9];
-    float4 ma;
+    const float4 ma = a.mlp_a[t];
     int sample;
-    shade_inputs(a, gc, t, in, sample, ma);
+    shade_inputs(a, gc, a.active[t], a.mlp_g[t], in, sample);
     // LightingMLP (model/spacenet.py:165-188): 9 -> 128 -> 128 -> 1, ReLU, ReLU, ELU; color = (out+1)*essence
     float out = L.b3;
 #pragma unroll 1

@@ -82,7 +82,7 @@ struct dsnerf_ctx {
   int F = 0, V = 0;
   std::vector<int32_t> h_faces;
   std::vector<float> h_canon;
-  DevBuf faces, canon, posed, vq, gg_bins;
+  DevBuf faces, canon, posed, vq, gg_bins, normal_m;
   MeshGrid g_canon, g_posed;
   // ---- frame
   bool have_frame = false;
@@ -272,7 +272,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CKL("jfa_pass");
   std::swap(sa, sb);
   g.enum_seed = sa;
-  mg.launches = 4 + 1 + 1 + 1;  // centroid/count/scan/fill, jfa_init, final jfa pass, enum_far
+  mg.launches = 4 + 1 + 1 + 1 + 1;  // centroid/count/scan/fill, jfa_init, final jfa pass, enum_far (+ normal_matrix for the posed mesh)
   for (int step = top; step >= 1; step >>= 1) ++mg.launches;
   // enumeration cells provably farther than r_cap from every centroid (never requested, never searched)
   enum_far_kernel<<<cb, 256, 0, st>>>(g, (int)ceil(r_cap / cell) + 2, mg.efar.as<unsigned char>());
@@ -417,6 +417,7 @@ ShadeArgs base_shade_args(dsnerf_ctx* ctx) {
   s.canon = ctx->canon.as<float>();
   s.faces = ctx->faces.as<int>();
   s.cent_canon = ctx->g_canon.cent.as<float>();
+  s.normal_m = ctx->normal_m.as<float4>();
   s.F = ctx->F;
   for (int k = 0; k < 3; ++k) s.light_shift[k] = ctx->light_shift[k];
   s.has_shift = ctx->has_shift;
@@ -552,7 +553,7 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->light_w2, &ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->gg_bins, &ctx->near2, &ctx->far2, &ctx->raw,
+  DevBuf* bufs[] = {&ctx->light_w2, &ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->gg_bins, &ctx->normal_m, &ctx->near2, &ctx->far2, &ctx->raw,
                     &ctx->active, &ctx->active_tri, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io};
   for (DevBuf* b : bufs) b->release();
   ctx->g_canon.release();
@@ -700,6 +701,11 @@ int dsnerf_set_frame(dsnerf_ctx* ctx, const float* posed_verts, const float* pos
   CK(cudaMemcpyAsync(ctx->bias0.p, pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->tw.bias0_slot(), pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   int e = build_grid(ctx, ctx->g_posed, ctx->posed.as<float>(), pv, 1, st);
+  if (!e) {
+    if (ctx->normal_m.ensure(sizeof(float4) * 3 * (size_t)ctx->F) != cudaSuccess) e = fail(ctx, DSNERF_ERR_CUDA, "normal matrices");
+    else normal_matrix_kernel<<<(ctx->F + 255) / 256, 256, 0, st>>>(ctx->canon.as<float>(), ctx->posed.as<float>(), ctx->faces.as<int>(), ctx->F,
+                                                                  ctx->normal_m.as<float4>());
+  }
   if (int e2 = pin_release(ctx, st)) return e2;
   if (e) return e;
   ctx->has_shift = light_shift != nullptr;

@@ -64,7 +64,8 @@ constexpr uint32_t SM_PE_HI = 131072;    // positional encoding hi, 8 chunks
 constexpr uint32_t SM_PE_LO = 147456;    // positional encoding lo
 constexpr uint32_t SM_RING = 163840;
 constexpr uint32_t SM_BAR = SM_RING + TC_STAGES * TC_STAGE_BYTES;  // 229376
-constexpr uint32_t TC_SMEM = SM_BAR + 256;
+constexpr uint32_t SM_RGBW = SM_BAR + 256;             // fp32: b_rgb1 [128], w_rgb2 [3][128] (rgb tail of every tile)
+constexpr uint32_t TC_SMEM = SM_RGBW + 2048;
 constexpr uint32_t A_CHUNK = TC_TILE * 16;  // bytes between consecutive 8-wide K chunks of an A operand
 constexpr uint32_t SM_STASH = SM_A_LO;           // [64 PE columns][128 rows] fp32 (32 KB), backward chain only
 constexpr uint32_t SM_XCH = SM_A_LO + 32768;     // [3 subs][8][128 rows] fp32 partial sums at the end of a tile
@@ -374,6 +375,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < 512; i += TC_THREADS)
+    reinterpret_cast<float*>(smem + SM_RGBW)[i] = i < 128 ? P.b_rgb1[i] : P.w_rgb2[i - 128];
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
@@ -537,6 +540,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           tc_fence_after();
           if (stamp) { P.timing[1 + 4 * op] = clock64(); P.timing[2 + 4 * op] = clock64(); }
           // rgb head tail: relu(acc[0:128] + b) -> Linear(128,3) partials (model/spacenet.py:75-80); 2 x 16 columns per thread
+          const float* rgbw = reinterpret_cast<const float*>(smem + SM_RGBW);
           uint32_t v0[16], v1[16];
           tmem_ld16_nowait(t_accb, v0);
           tmem_ld16_nowait(t_accb + 64, v1);
@@ -546,10 +550,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             float4 b[4], w0[4], w1[4], w2[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              b[i] = __ldg(reinterpret_cast<const float4*>(P.b_rgb1 + col0) + i);
-              w0[i] = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + col0) + i);
-              w1[i] = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 128 + col0) + i);
-              w2[i] = __ldg(reinterpret_cast<const float4*>(P.w_rgb2 + 256 + col0) + i);
+              b[i] = *(reinterpret_cast<const float4*>(rgbw + col0) + i);
+              w0[i] = *(reinterpret_cast<const float4*>(rgbw + 128 + col0) + i);
+              w1[i] = *(reinterpret_cast<const float4*>(rgbw + 256 + col0) + i);
+              w2[i] = *(reinterpret_cast<const float4*>(rgbw + 384 + col0) + i);
             }
             if (hq == 0) tmem_wait_ld(v0); else tmem_wait_ld(v1);
             const uint32_t(&v)[16] = hq ? v1 : v0;

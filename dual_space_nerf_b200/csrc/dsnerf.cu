@@ -434,6 +434,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
                 cudaStream_t st) {
   if (int e = check_ready(ctx, true)) return e;
   if (R < 0 || N < 1 || N > 4096) return fail(ctx, DSNERF_ERR_INVALID, "n_rays must be >= 0 and 1 <= n_samples <= 4096");
+  if (R * (int64_t)N > 0x7fffffffLL) return fail(ctx, DSNERF_ERR_INVALID, "n_rays * n_samples must fit in 31 bits (sample ids are 32-bit); split the batch");
   if (!ray_o || !ray_d || (!z_in && (!near || !far)) || !rgb || !depth || !acc || !disp) {
     if (R > 0) return fail(ctx, DSNERF_ERR_INVALID, "null input/output pointer");
   }

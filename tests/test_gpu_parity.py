@@ -312,6 +312,12 @@ def test_edge_cases_and_errors(scene64):
     b = S.to_batch(scene64, torch, rays=np.array([2080]))  # a single ray, ragged tile
     out = r.render(b)["coarse"]
     assert out["color"].shape == (1, 3) and torch.isfinite(out["color"]).all()
+    # rays that miss the body entirely: nothing is evaluated (the tensor-core kernel runs zero tiles), acc = 0, disp = NaN
+    s2 = dict(scene64)
+    s2["ray_o"] = scene64["ray_o"] + np.array([100.0, 0.0, 0.0], np.float32)
+    out = r.render(S.to_batch(s2, torch))["coarse"]
+    assert r.ctx.stats()["evaluated_samples"] == 0
+    assert float(out["acc_map"].abs().max()) == 0.0 and float(out["color"].abs().max()) == 0.0 and bool(torch.isnan(out["disp_map"]).all())
     ctx = lib.Context(0)
     with pytest.raises(lib.DsnerfError):  # call order is checked, errors are reported not aborted
         ctx.check(ctx.L.dsnerf_render(ctx.h, None, None, None, None, 1, 8, 1, None, None, None, None, None, None, None))

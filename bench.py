@@ -213,10 +213,11 @@ def main():
     # ---- device-resident arm ("value"): inputs already in HBM, outputs stay in HBM
     d_o, d_d = torch.from_numpy(sc["ray_o"]).to(dev), torch.from_numpy(sc["ray_d"]).to(dev)
     d_n, d_f = torch.from_numpy(sc["near"]).to(dev), torch.from_numpy(sc["far"]).to(dev)
-    out = torch.empty(R, 6, device=dev)  # rgb(3) depth acc disp packed per ray -> one all-gather
-    o_rgb, o_dep, o_acc, o_dsp = (torch.empty(R, 3, device=dev), torch.empty(R, device=dev), torch.empty(R, device=dev),
-                                  torch.empty(R, device=dev))
-    gathered = torch.empty(world * R, 6, device=dev) if world > 1 else None
+    # one flat block per rank, [rgb (R,3) | depth (R) | acc (R) | disp (R)]: the compositor writes straight into it and a single
+    # all-gather (6 floats per ray) reassembles every rank's frame on every rank
+    out = torch.empty(6 * R, device=dev)
+    o_rgb, o_dep, o_acc, o_dsp = out[: 3 * R].view(R, 3), out[3 * R: 4 * R], out[4 * R: 5 * R], out[5 * R:]
+    gathered = torch.empty(world, 6 * R, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_device():
@@ -224,10 +225,6 @@ def main():
         ctx.check(L.dsnerf_render(ctx.h, P(d_o), P(d_d), P(d_n), P(d_f), R, N_SAMPLES, flags, P(o_rgb), P(o_dep), P(o_acc),
                                   P(o_dsp), None, None, sp))
         if world > 1:
-            out[:, :3] = o_rgb
-            out[:, 3] = o_dep
-            out[:, 4] = o_acc
-            out[:, 5] = o_dsp
             dist.all_gather_into_tensor(gathered, out)
 
     def barrier():

@@ -855,7 +855,10 @@ struct WarpArgs {
   int count_candidates;
 };
 
-constexpr int WARP_THREADS = 256;
+#ifndef DSN_WARP_THREADS
+#define DSN_WARP_THREADS 256
+#endif
+constexpr int WARP_THREADS = DSN_WARP_THREADS;
 
 __device__ __forceinline__ void sample_position(const WarpArgs& a, int64_t s, float& px, float& py, float& pz) {
   int64_t r;

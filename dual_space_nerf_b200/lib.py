@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsnerf.so")
+LIB_PATH = os.environ.get("DSNERF_LIB") or os.path.join(_HERE, "libdsnerf.so")  # DSNERF_LIB: A/B experiments with a differently built library
 
 SAMPLE_UNIFORM = 0
 SAMPLE_GG = 1

@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--simt", action="store_true", help="debug: fp32 SIMT MLP kernel instead of tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--early-stop", action="store_true", help="optional DSNERF_EARLY_STOP mode (not the headline: the default evaluates every sample)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -199,7 +200,7 @@ def main():
     faces = np.ascontiguousarray(sc["faces"], dtype=np.int32)
     ctx.check(L.dsnerf_set_mesh(ctx.h, faces.ctypes.data_as(ctypes.c_void_p), faces.shape[0],
                                 sc["canonical"].ctypes.data_as(ctypes.c_void_p), sc["canonical"].shape[0]))
-    flags = lib.SAMPLE_GG | (lib.MLP_FP32_SIMT if args.simt else 0)
+    flags = lib.SAMPLE_GG | (lib.MLP_FP32_SIMT if args.simt else 0) | (lib.EARLY_STOP if args.early_stop else 0)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
@@ -333,6 +334,7 @@ def main():
                 "parallelism": f"{world} x (one frame per GPU) + NCCL all-gather of 6 floats/ray" if world > 1 else "1 GPU",
                 "l2": "256 MB buffer written between timed steps (L2 flush)",
                 "mlp_kernel": "fp32 SIMT (debug)" if args.simt else "tcgen05",
+                "early_stop": bool(args.early_stop),
             },
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",

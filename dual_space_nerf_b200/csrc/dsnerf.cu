@@ -93,6 +93,8 @@ struct dsnerf_ctx {
   // ---- workspace
   DevBuf tc_timing;
   DevBuf near2, far2, raw, active, active_tri, ray_mask, mlp_a, mlp_g, tvals, counters, io;
+  DevBuf ert_active, ert_tri, ert_state, ert_cnt;  // early-ray-termination mode only
+  unsigned long long* h_ert = nullptr;              // pinned, 8 entries
   int tvals_n = 0;
   void* pin = nullptr;
   size_t pin_cap = 0;
@@ -103,6 +105,7 @@ struct dsnerf_ctx {
   dsnerf_stats_t stats{};
   // ---- profiling
   int profile = 0;
+  int ert_mode = 0;   // last render used early ray termination (stats come from h_ert)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   double mlp_ms = 0;
@@ -363,11 +366,13 @@ void profile_end(dsnerf_ctx* ctx, cudaStream_t st, cudaEvent_t a, cudaEvent_t b)
 }
 
 // SpaceNet + gradient on the active list (count on the device or given by the host)
-int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_count, unsigned flags, int density_only, cudaStream_t st) {
+int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_count, unsigned flags, int density_only, cudaStream_t st,
+               const float4* list = nullptr) {
+  const float4* active = list ? list : ctx->active.as<float4>();
   cudaEvent_t a, b;
   profile_begin(ctx, st, &a, &b);
   if (flags & DSNERF_MLP_FP32_SIMT) {
-    mlp_simt_kernel<<<ctx->sm_count, SIMT_THREADS, SIMT_SMEM, st>>>(ctx->sw, ctx->active.as<float4>(), d_count, host_count,
+    mlp_simt_kernel<<<ctx->sm_count, SIMT_THREADS, SIMT_SMEM, st>>>(ctx->sw, active, d_count, host_count,
                                                                     ctx->mlp_a.as<float4>(), ctx->mlp_g.as<float4>(), density_only);
     CKL("mlp_simt");
   } else {
@@ -376,7 +381,7 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
       if (ctx->tc_timing.ensure(sizeof(long long) * 128) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "timing buffer");
       timing = ctx->tc_timing.as<long long>();
     }
-    if (int e = tc_launch(ctx->tw, timing, (ctx->profile >> 3) & 3, ctx->active.as<float4>(), d_count, host_count, ctx->mlp_a.as<float4>(),
+    if (int e = tc_launch(ctx->tw, timing, (ctx->profile >> 3) & 3, active, d_count, host_count, ctx->mlp_a.as<float4>(),
                           ctx->mlp_g.as<float4>(), density_only, ctx->sm_count, st))
       return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc: ") + cudaGetErrorString((cudaError_t)e));
   }
@@ -490,25 +495,69 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
         mark_samples_kernel<<<(unsigned)((mark_threads + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
       }))
     return e;
-  sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
-  CKL("sample_warp");
-  launches += 4;
-  if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
-  ++launches;
   ShadeArgs sa = base_shade_args(ctx);
-  sa.n_active = cnt;
-  sa.active_tri = ctx->active_tri.as<int>();
   sa.ray_o = ray_o; sa.ray_d = ray_d; sa.near = near_use; sa.far = far_use; sa.z_in = z_in; sa.tvals = ctx->tvals.as<float>();
   sa.N = N;
-  if (int e = launch_shade(ctx, sa, flags, st)) return e;
-  launches += 3;
   CompositeArgs ca{};
   ca.sample_mask = ctx->ray_mask.as<unsigned>();
   ca.raw = ctx->raw.as<float4>(); ca.ray_d = ray_d; ca.near = near_use; ca.far = far_use; ca.tvals = ctx->tvals.as<float>(); ca.z_in = z_in;
   ca.R = R; ca.N = N; ca.rgb = rgb; ca.depth = depth; ca.acc = acc; ca.disp = disp; ca.weights = weights; ca.z_out = z_out;
-  composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
-  CKL("composite");
-  ++launches;
+  ctx->ert_mode = 0;
+  if ((flags & DSNERF_EARLY_STOP) && N >= 8 && N % 4 == 0) {
+    // ---- early ray termination: four front-to-back waves of samples; see shade.cuh
+    constexpr int kWaves = 4;
+    const float tau = 1e-6f;
+    const int wsize = (N + kWaves - 1) / kWaves;
+    const int64_t region = R * (int64_t)wsize;  // a wave holds at most wsize samples per ray
+    CK(ctx->ert_active.ensure(sizeof(float4) * (size_t)(region + 128)));
+    CK(ctx->ert_tri.ensure(sizeof(int) * (size_t)(region + 128)));
+    CK(ctx->ert_state.ensure(sizeof(RayState) * (size_t)R));
+    CK(ctx->ert_cnt.ensure(sizeof(unsigned long long) * 8));
+    unsigned long long* ec = ctx->ert_cnt.as<unsigned long long>();  // [0..3] wave sizes, [4..7] evaluated per wave
+    CK(cudaMemsetAsync(ec, 0, sizeof(unsigned long long) * 8, st));
+    wa.waves = kWaves; wa.wave_size = wsize; wa.region = region; wa.wave_counters = ec;
+    sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
+    CKL("sample_warp");
+    launches += 4;
+    for (int k = 0; k < kWaves; ++k) {
+      const float4* list = ctx->active.as<float4>() + k * region;
+      const int* tri = ctx->active_tri.as<int>() + k * region;
+      const unsigned long long* count = ec + k;
+      if (k > 0) {
+        filter_wave_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(list, tri, ec + k, ctx->ert_state.as<RayState>(), N, tau,
+                                                              ctx->ert_active.as<float4>(), ctx->ert_tri.as<int>(), ec + 4 + k);
+        CKL("filter_wave");
+        ++launches;
+        list = ctx->ert_active.as<float4>();
+        tri = ctx->ert_tri.as<int>();
+        count = ec + 4 + k;
+      }
+      if (int e = launch_mlp(ctx, count, 0, flags, 0, st, list)) return e;
+      sa.active = list;
+      sa.active_tri = tri;
+      sa.n_active = count;
+      if (int e = launch_shade(ctx, sa, flags, st)) return e;
+      const int i0 = k * wsize, i1 = std::min(N, (k + 1) * wsize);
+      composite_wave_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca, ctx->ert_state.as<RayState>(), i0, i1, tau, k == kWaves - 1);
+      CKL("composite_wave");
+      launches += 6;
+    }
+    CK(cudaMemcpyAsync(ctx->h_ert, ec, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    ctx->ert_mode = 1;
+  } else {
+    sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
+    CKL("sample_warp");
+    launches += 4;
+    if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
+    ++launches;
+    sa.n_active = cnt;
+    sa.active_tri = ctx->active_tri.as<int>();
+    if (int e = launch_shade(ctx, sa, flags, st)) return e;
+    launches += 3;
+    composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
+    CKL("composite");
+    ++launches;
+  }
   CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ctx->stats_ready, st));
   ctx->stats.rays = R;
@@ -540,6 +589,8 @@ int dsnerf_create(dsnerf_ctx** out, int device) {
   cudaEventCreateWithFlags(&ctx->stats_ready, cudaEventDisableTiming);
   cudaMallocHost(reinterpret_cast<void**>(&ctx->h_counters), sizeof(unsigned long long) * 4);
   memset(ctx->h_counters, 0, sizeof(unsigned long long) * 4);
+  cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ert), sizeof(unsigned long long) * 8);
+  memset(ctx->h_ert, 0, sizeof(unsigned long long) * 8);
   cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMT_SMEM);
   cudaFuncSetAttribute(shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHADE_SMEM);
   cudaFuncSetAttribute(light_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM);
@@ -555,13 +606,15 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->light_w2, &ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->gg_bins, &ctx->normal_m, &ctx->near2, &ctx->far2, &ctx->raw,
-                    &ctx->active, &ctx->active_tri, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io};
+                    &ctx->active, &ctx->active_tri, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io,
+                    &ctx->ert_active, &ctx->ert_tri, &ctx->ert_state, &ctx->ert_cnt};
   for (DevBuf* b : bufs) b->release();
   ctx->g_canon.release();
   ctx->g_posed.release();
   ctx->tw.release();
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_ert) cudaFreeHost(ctx->h_ert);
   if (ctx->pin_free) cudaEventDestroy(ctx->pin_free);
   if (ctx->stats_ready) cudaEventDestroy(ctx->stats_ready);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -934,7 +987,7 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
   if (!ctx || !out) return DSNERF_ERR_INVALID;
   if (ctx->stats.rays > 0) {
     CK(cudaEventSynchronize(ctx->stats_ready));
-    ctx->stats.evaluated_samples = (int64_t)ctx->h_counters[0];
+    ctx->stats.evaluated_samples = ctx->ert_mode ? (int64_t)(ctx->h_ert[0] + ctx->h_ert[5] + ctx->h_ert[6] + ctx->h_ert[7]) : (int64_t)ctx->h_counters[0];
     ctx->stats.nn_candidates = (int64_t)ctx->h_counters[1];
     ctx->stats.reserved = (int32_t)std::min<unsigned long long>(ctx->h_counters[2], 0x7fffffffull);
     ctx->stats.algorithmic_flop = 1804544.0 * (double)ctx->stats.evaluated_samples;

@@ -853,6 +853,8 @@ struct WarpArgs {
   unsigned* sample_mask;   // ceil(R*N/32) words, bit s&31 of word s>>5
   unsigned long long* counters;
   int count_candidates;
+  // early-ray-termination mode: the active list is split into `waves` regions of `region` entries by sample index / wave_size
+  int waves; int wave_size; int64_t region; unsigned long long* wave_counters;
 };
 
 #ifndef DSN_WARP_THREADS
@@ -969,14 +971,18 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
       }
     }
     if ((threadIdx.x & ~31) < n) {  // warp-uniform: this warp holds queue entries
-      unsigned m = __ballot_sync(0xffffffffu, act);
-      if (m) {
+      const int nw = a.waves > 1 ? a.waves : 1;
+      const int my_wave = (a.waves > 1 && act) ? (int)((s0 + t) % a.N) / a.wave_size : 0;
+      for (int w = 0; w < nw; ++w) {
+        const bool mine = act && my_wave == w;
+        unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (!m) continue;
         int leader = __ffs(m) - 1;
         unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(a.counters, (unsigned long long)__popc(m));
+        if (lane == leader) base = atomicAdd(a.waves > 1 ? a.wave_counters + w : a.counters, (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (act) {
-          unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+        if (mine) {
+          unsigned long long slot = (unsigned long long)w * (unsigned long long)a.region + base + __popc(m & ((1u << lane) - 1));
           a.active[slot] = make_float4(xc.x, xc.y, xc.z, __int_as_float((int)(s0 + t)));
           a.active_tri[slot] = idx;
           flag[t] = 1;

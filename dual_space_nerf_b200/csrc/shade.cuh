@@ -240,6 +240,109 @@ __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
   }
 }
 
+// ---- early ray termination (optional, flag DSNERF_EARLY_STOP) ---------------------------------------------------------
+// The samples of a ray are processed in `waves` index ranges, front to back.  After wave k the transmittance T of every ray is
+// known; since sum_{i >= cut} w_i <= T_cut, a ray with T <= tau can gain at most tau in acc, tau*max|c| in colour and
+// tau*z_far in depth from all its remaining samples, so they are not evaluated at all (the reference evaluates them and adds
+// those < tau amounts).  tau = 1e-6 keeps every output within 4e-6 of the exhaustive result, 25x inside the 1e-4 tolerance.
+struct RayState { float T, r, g, b, d, a; };  // running transmittance and sums of one ray
+
+// wave k > 0: keep the entries of its region whose ray is still alive (compaction into `out`)
+__global__ void __launch_bounds__(256) filter_wave_kernel(const float4* __restrict__ in, const int* __restrict__ in_tri,
+                                                          const unsigned long long* __restrict__ n_in, const RayState* __restrict__ state, int N,
+                                                          float tau, float4* __restrict__ out, int* __restrict__ out_tri,
+                                                          unsigned long long* __restrict__ n_out) {
+  const int64_t n = (int64_t)*n_in;
+  const int lane = threadIdx.x & 31;
+  for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < n; t0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = t0 + threadIdx.x;
+    bool keep = false;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < n) {
+      e = in[t];
+      keep = state[__float_as_int(e.w) / N].T > tau;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!m) continue;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) {
+      unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+      out[slot] = e;
+      out_tri[slot] = in_tri[t];
+    }
+  }
+}
+
+// raw2outputs restricted to samples [i0, i1) of every ray (one warp per ray, same arithmetic as composite_kernel), carrying
+// the ray state across waves.  A ray that was dead when the wave started (state.T <= tau) is skipped: its samples of this wave
+// were not evaluated.  The last wave writes the outputs.
+__global__ void __launch_bounds__(256) composite_wave_kernel(CompositeArgs a, RayState* __restrict__ state, int i0, int i1, float tau, int last) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= a.R) return;
+  RayState st;
+  if (i0 == 0) { st.T = 1.f; st.r = st.g = st.b = st.d = st.a = 0.f; }
+  else st = state[r];
+  const bool alive = st.T > tau;
+  float nd = xnorm3(v3(a.ray_d[3 * r], a.ray_d[3 * r + 1], a.ray_d[3 * r + 2]));
+  float near = a.z_in ? 0.f : a.near[r], far = a.z_in ? 0.f : a.far[r];
+  float T = st.T;
+  float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+  for (int base = i0; base < i1; base += 32) {
+    int i = base + lane;
+    bool live = i < i1;
+    float z = 0.f, zn = 0.f;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      z = a.z_in ? a.z_in[r * a.N + i] : sample_z(near, far, a.tvals[i]);
+      if (i + 1 < a.N) zn = a.z_in ? a.z_in[r * a.N + i + 1] : sample_z(near, far, a.tvals[i + 1]);
+      const int64_t sidx = r * a.N + i;
+      bool has = alive && ((a.sample_mask[sidx >> 5] >> (sidx & 31)) & 1u);
+      if (has) c = a.raw[sidx];
+    }
+    float dist = (i + 1 < a.N) ? xsub(zn, z) : 1e10f;
+    dist = xmul(dist, nd);
+    float alpha = live ? xsub(1.0f, expf(-xmul(fmaxf(c.w, 0.f), dist))) : 0.f;
+    float t = xadd(xsub(1.0f, alpha), 1e-10f);
+    float p = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float q = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) p *= q;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) excl = 1.0f;
+    float w = alpha * (T * excl);
+    T *= __shfl_sync(0xffffffffu, p, 31);
+    if (live) {
+      sr = fmaf(w, c.x, sr); sg = fmaf(w, c.y, sg); sb = fmaf(w, c.z, sb);
+      sd = fmaf(w, z, sd); sa += w;
+      if (a.weights) a.weights[r * a.N + i] = w;
+      if (a.z_out) a.z_out[r * a.N + i] = z;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o); sa += __shfl_xor_sync(0xffffffffu, sa, o);
+  }
+  if (lane == 0) {
+    st.T = alive ? T : st.T;
+    st.r += sr; st.g += sg; st.b += sb; st.d += sd; st.a += sa;
+    if (!last) {
+      state[r] = st;
+    } else {
+      a.rgb[3 * r] = st.r; a.rgb[3 * r + 1] = st.g; a.rgb[3 * r + 2] = st.b;
+      a.depth[r] = st.d; a.acc[r] = st.a;
+      float q = xdiv(st.d, st.a);  // 0/0 = NaN when nothing was hit, as in the reference
+      a.disp[r] = (q != q) ? q : xdiv(1.0f, fmaxf(1e-10f, q));
+    }
+  }
+}
+
 // Hierarchical resampling (config 3).  The reference calls an undefined Renderer.resampling
 // (can_render.py:213); this implements the written spec in DESIGN.md "Config 3" =
 // oracle/oracle.py:sample_pdf: deterministic inverse-CDF sampling of the coarse weights

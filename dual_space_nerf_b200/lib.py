@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("DSNERF_LIB") or os.path.join(_HERE, "libdsnerf.so")  
 SAMPLE_UNIFORM = 0
 SAMPLE_GG = 1
 MLP_FP32_SIMT = 2
+EARLY_STOP = 4
 NUM_WEIGHT_TENSORS = 33
 
 ENTRY_POINTS = [

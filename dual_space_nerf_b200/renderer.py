@@ -59,6 +59,9 @@ class Renderer:
         self.device = torch.device("cuda", int(device))
         self.ctx = _lib.Context(int(device))  # raises without a B200: no fallback
         self.flags_extra = 0
+        # optional early ray termination (DSNERF_EARLY_STOP, include/dsnerf.h): off by default, the default path evaluates every
+        # non-transparent sample like the reference
+        self.early_stop = False
         cv = canonical_vertex
         if cv is not None:
             cv = torch.as_tensor(cv, dtype=torch.float32).reshape(-1, 3)
@@ -147,7 +150,7 @@ class Renderer:
         mode = mode or self.cfg.MODEL.sample_points_mode
         if mode not in ("GG", "uniform"):
             raise ValueError(f"unknown sample_points_mode {mode!r}")
-        return (_lib.SAMPLE_GG if mode == "GG" else _lib.SAMPLE_UNIFORM) | self.flags_extra
+        return (_lib.SAMPLE_GG if mode == "GG" else _lib.SAMPLE_UNIFORM) | self.flags_extra | (_lib.EARLY_STOP if self.early_stop else 0)
 
     def _check_eval(self):
         if getattr(self.net, "training", False):

@@ -47,6 +47,10 @@ typedef enum {
 #define DSNERF_SAMPLE_UNIFORM 0u   /* utils/pts_utils.py:3  uniform_sampling */
 #define DSNERF_SAMPLE_GG 1u        /* utils/pts_utils.py:18 geometry_guided_ray_marching */
 #define DSNERF_MLP_FP32_SIMT 2u    /* debug: evaluate the MLP with the fp32 SIMT kernel instead of tcgen05 */
+#define DSNERF_EARLY_STOP 4u       /* optional early ray termination: the samples of a ray are evaluated front to back in four
+                                    * waves and a ray whose transmittance has dropped to <= 1e-6 is not evaluated further (the
+                                    * reference evaluates every sample; the remaining ones can change acc by < 1e-6, colour and
+                                    * depth by < 4e-6).  OFF by default: the default path evaluates every non-transparent sample. */
 
 /* number of tensors in DualSpaceNeRF.state_dict() (model/spacenet.py), order in SURVEY.md 8b */
 #define DSNERF_NUM_WEIGHT_TENSORS 33

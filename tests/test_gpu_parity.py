@@ -271,6 +271,31 @@ def test_camera_rays_vs_reference_golden(scene64, state_dict):
     assert float(cam["coarse_acc"].max()) > 0.5
 
 
+def test_early_stop_option_within_bound(state_dict):
+    """DSNERF_EARLY_STOP (optional): rays are evaluated front to back in four waves and dropped once their transmittance is
+    <= 1e-6.  Against the exhaustive default on a 256x256x64 frame: acc within 1e-6, colour / depth within 4e-6 (the strict bound
+    of shade.cuh), fewer samples evaluated; and the usual 1e-4 parity against the reference golden."""
+    sc = S.make_scene(256, 256)
+    r = make_renderer(sc, 64)
+    full = to_np(r.render(S.to_batch(sc, torch))["coarse"])
+    n_full = r.ctx.stats()["evaluated_samples"]
+    r.early_stop = True
+    es = to_np(r.render(S.to_batch(sc, torch))["coarse"])
+    n_es = r.ctx.stats()["evaluated_samples"]
+    assert n_es < 0.8 * n_full, (n_es, n_full)
+    assert np.abs(es["acc_map"] - full["acc_map"]).max() <= 2e-6
+    assert np.abs(es["color"] - full["color"]).max() <= 4e-6 and np.abs(es["depth_map"] - full["depth_map"]).max() <= 8e-6
+    assert np.abs(es["weights"] - full["weights"]).max() <= 2e-6 and np.array_equal(es["z_vals"], full["z_vals"])
+    print(f"early stop: {n_es} of {n_full} samples evaluated, max|d rgb| {np.abs(es['color'] - full['color']).max():.2e}")
+    g = C.golden("render_128x128x64.npz")
+    sc = S.make_scene(128, 128)
+    r = make_renderer(sc, 64)
+    r.early_stop = True
+    out = to_np(r.render(S.to_batch(sc, torch, rays=g["rays"]))["coarse"])
+    _, st = oracle_run(sc, state_dict, 64, g["rays"])
+    C.check_rays(out, g, kink_rays(st, 64), what="early stop vs reference golden")
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

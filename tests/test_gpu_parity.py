@@ -296,6 +296,25 @@ def test_early_stop_option_within_bound(state_dict):
     C.check_rays(out, g, kink_rays(st, 64), what="early stop vs reference golden")
 
 
+def test_tiny_mesh_vs_oracle(state_dict):
+    """A 4-triangle mesh (tetrahedron around the synthetic body's centre): degenerate grid sizes, every lookup cell sees all
+    centroids, most samples are far from every triangle.  Same parity criteria against the oracle."""
+    sc = dict(S.make_scene(48, 48))
+    c = sc["canonical"].mean(0)
+    tet = np.array([[0.25, 0.0, -0.2], [-0.2, 0.2, -0.2], [-0.2, -0.2, -0.2], [0.0, 0.0, 0.35]], np.float32)
+    sc["canonical"] = (c + tet).astype(np.float32)
+    sc["posed"] = (sc["posed"].mean(0) + tet * np.float32(1.1)).astype(np.float32)
+    sc["faces"] = np.array([[0, 1, 2], [0, 3, 1], [1, 3, 2], [2, 3, 0]], np.int64)
+    n = 32
+    rays = np.arange(0, 48 * 48, 3)
+    r = make_renderer(sc, n)
+    out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    ref, st = oracle_run(sc, state_dict, n, rays)
+    assert np.array_equal(out["z_vals"], ref["z_vals"])
+    assert r.ctx.stats()["evaluated_samples"] == int((~st["mask"]).sum()) > 100
+    C.check_rays(out, ref, kink_rays(st, n), what="tetrahedron")
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

@@ -433,16 +433,17 @@ ShadeArgs base_shade_args(dsnerf_ctx* ctx) {
   return s;
 }
 
-// shared body of dsnerf_render / dsnerf_render_z
+// shared body of dsnerf_render / dsnerf_render_z / dsnerf_render_train (jitter, raw_noise: training-mode draws or NULL)
 int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, const float* z_in,
                 int64_t R, int N, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_out,
-                cudaStream_t st) {
+                cudaStream_t st, const float* jitter = nullptr, const float* raw_noise = nullptr) {
   if (int e = check_ready(ctx, true)) return e;
   if (R < 0 || N < 1 || N > 4096) return fail(ctx, DSNERF_ERR_INVALID, "n_rays must be >= 0 and 1 <= n_samples <= 4096");
   if (R * (int64_t)N > 0x7fffffffLL) return fail(ctx, DSNERF_ERR_INVALID, "n_rays * n_samples must fit in 31 bits (sample ids are 32-bit); split the batch");
   if (!ray_o || !ray_d || (!z_in && (!near || !far)) || !rgb || !depth || !acc || !disp) {
     if (R > 0) return fail(ctx, DSNERF_ERR_INVALID, "null input/output pointer");
   }
+  if (jitter && !z_out && R > 0) return fail(ctx, DSNERF_ERR_INVALID, "jittered sampling needs the z_vals output buffer");
   ctx->stats = dsnerf_stats_t{};
   if (R == 0) return 0;
   CK(cudaSetDevice(ctx->device));
@@ -483,6 +484,13 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
     near_use = ctx->near2.as<float>();
     far_use = ctx->far2.as<float>();
   }
+  if (jitter) {  // training mode: stratified jitter (pts_utils.py:6-13) written straight into the caller's z_vals
+    jitter_z_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(near_use, far_use, ctx->tvals.as<float>(), jitter, R, N, z_out);
+    CKL("jitter_z");
+    ++launches;
+    z_in = z_out;
+    z_out = nullptr;
+  }
   WarpArgs wa{};
   wa.ray_o = ray_o; wa.ray_d = ray_d; wa.near = near_use; wa.far = far_use; wa.z_in = z_in; wa.tvals = ctx->tvals.as<float>();
   wa.posed = ctx->posed.as<float>(); wa.canon = ctx->canon.as<float>(); wa.faces = ctx->faces.as<int>();
@@ -490,6 +498,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   wa.active = ctx->active.as<float4>(); wa.active_tri = ctx->active_tri.as<int>(); wa.sample_mask = ctx->ray_mask.as<unsigned>();
   wa.counters = cnt;
   wa.count_candidates = (ctx->profile & 2) ? 1 : 0;
+  if (!raw_noise)
   if (int e = ensure_cells(ctx, ctx->g_posed, st, [&] {
         const int64_t mark_threads = R * ((N + MARK_SPT - 1) / MARK_SPT);
         mark_samples_kernel<<<(unsigned)((mark_threads + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
@@ -503,7 +512,20 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
   ca.raw = ctx->raw.as<float4>(); ca.ray_d = ray_d; ca.near = near_use; ca.far = far_use; ca.tvals = ctx->tvals.as<float>(); ca.z_in = z_in;
   ca.R = R; ca.N = N; ca.rgb = rgb; ca.depth = depth; ca.acc = acc; ca.disp = disp; ca.weights = weights; ca.z_out = z_out;
   ctx->ert_mode = 0;
-  if ((flags & DSNERF_EARLY_STOP) && N >= 8 && N % 4 == 0) {
+  if (raw_noise) {
+    // ---- training mode with density noise: the network runs on every sample (see sample_warp_all_kernel)
+    sample_warp_all_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(wa, ctx->g_posed.g, ctx->F, ctx->g_posed.cent.as<float>());
+    CKL("sample_warp_all");
+    if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
+    sa.n_active = cnt;
+    sa.active_tri = ctx->active_tri.as<int>();
+    if (int e = launch_shade(ctx, sa, flags, st)) return e;
+    ca.noise = raw_noise;
+    ca.all_raw = 1;
+    composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
+    CKL("composite");
+    launches += 6;
+  } else if ((flags & DSNERF_EARLY_STOP) && N >= 8 && N % 4 == 0) {
     // ---- early ray termination: four front-to-back waves of samples; see shade.cuh
     constexpr int kWaves = 4;
     const float tau = 1e-6f;
@@ -778,6 +800,14 @@ int dsnerf_render(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const
                      reinterpret_cast<cudaStream_t>(stream));
 }
 
+int dsnerf_render_train(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, int64_t n_rays,
+                        int n_samples, unsigned flags, const float* jitter, const float* raw_noise, float* rgb, float* depth, float* acc,
+                        float* disp, float* weights, float* z_vals, void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  return render_impl(ctx, ray_o, ray_d, near, far, nullptr, n_rays, n_samples, flags, rgb, depth, acc, disp, weights, z_vals,
+                     reinterpret_cast<cudaStream_t>(stream), jitter, raw_noise);
+}
+
 int dsnerf_render_z(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* z_vals, int64_t n_rays, int n_samples,
                     unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, void* stream) {
   if (!ctx) return DSNERF_ERR_INVALID;
@@ -820,6 +850,11 @@ int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, 
 
 int dsnerf_composite(dsnerf_ctx* ctx, const float* raw, const float* z_vals, const float* ray_d, int64_t R, int N, float* rgb,
                      float* depth, float* acc, float* disp, float* weights, void* stream) {
+  return dsnerf_composite_noise(ctx, raw, z_vals, ray_d, nullptr, R, N, rgb, depth, acc, disp, weights, stream);
+}
+
+int dsnerf_composite_noise(dsnerf_ctx* ctx, const float* raw, const float* z_vals, const float* ray_d, const float* raw_noise, int64_t R,
+                           int N, float* rgb, float* depth, float* acc, float* disp, float* weights, void* stream) {
   if (!ctx) return DSNERF_ERR_INVALID;
   if (R < 0 || N < 1) return fail(ctx, DSNERF_ERR_INVALID, "bad sizes");
   if (R == 0) return 0;
@@ -829,6 +864,7 @@ int dsnerf_composite(dsnerf_ctx* ctx, const float* raw, const float* z_vals, con
   CompositeArgs ca{};
   ca.raw = reinterpret_cast<const float4*>(raw); ca.ray_d = ray_d; ca.z_in = z_vals; ca.R = R; ca.N = N;
   ca.rgb = rgb; ca.depth = depth; ca.acc = acc; ca.disp = disp; ca.weights = weights; ca.z_out = nullptr;
+  ca.noise = raw_noise;
   composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
   CKL("composite");
   return 0;

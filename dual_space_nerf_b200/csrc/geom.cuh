@@ -998,21 +998,24 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
   }
 }
 
+// exact nearest centroid of an arbitrary point without the lookup table: ball scan seeded by the enumeration cell's
+// approximate nearest centroid; points outside the grid fall back to the exhaustive scan (rare: far from the mesh).
+__device__ __forceinline__ int nearest_any(const Grid& g, const float* __restrict__ cent, int F, float px, float py, float pz) {
+  float fx = (px - g.ox) * g.inv_cell, fy = (py - g.oy) * g.inv_cell, fz = (pz - g.oz) * g.inv_cell;
+  if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz)
+    return scan_nearest(g, px, py, pz, g.enum_seed[((int)fz * g.ny + (int)fy) * g.nx + (int)fx]);
+  return brute_nearest(cent, F, px, py, pz);
+}
+
 // stand-alone warp op (dsnerf_warp_points): reports the reference's values for every point, transparent or not, so it
-// does not use the lookup table: exact ball scan seeded by the enumeration cell's approximate nearest centroid; points
-// outside the grid fall back to the exhaustive scan (rare: far from the mesh).
+// does not use the lookup table (whose cells may hold "provably transparent" instead of a triangle).
 __global__ void warp_points_kernel(const float* __restrict__ pts, int64_t P, const float* __restrict__ posed, const float* __restrict__ canon,
                                    const int* __restrict__ faces, Grid g, int F, const float* __restrict__ cent,
                                    float* __restrict__ xyz_cano, uint8_t* __restrict__ transparent, int* __restrict__ idx_out) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= P) return;
   float px = pts[3 * s], py = pts[3 * s + 1], pz = pts[3 * s + 2];
-  int idx;
-  float fx = (px - g.ox) * g.inv_cell, fy = (py - g.oy) * g.inv_cell, fz = (pz - g.oz) * g.inv_cell;
-  if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz)
-    idx = scan_nearest(g, px, py, pz, g.enum_seed[((int)fz * g.ny + (int)fy) * g.nx + (int)fx]);
-  else
-    idx = brute_nearest(cent, F, px, py, pz);
+  const int idx = nearest_any(g, cent, F, px, py, pz);
   int i0 = faces[3 * idx], i1 = faces[3 * idx + 1], i2 = faces[3 * idx + 2];
   float u, v, h;
   project_point(v3(px, py, pz), ldv3(posed, i0), ldv3(posed, i1), ldv3(posed, i2), u, v, h);
@@ -1020,6 +1023,47 @@ __global__ void warp_points_kernel(const float* __restrict__ pts, int64_t P, con
   xyz_cano[3 * s] = xc.x; xyz_cano[3 * s + 1] = xc.y; xyz_cano[3 * s + 2] = xc.z;
   if (transparent) transparent[s] = is_transparent(u, v, h) ? 1 : 0;
   if (idx_out) idx_out[s] = idx;
+}
+
+// ---- training-mode forward (Renderer.render with net.training) -------------------------------------
+// Stratified jitter of uniform_sampling (utils/pts_utils.py:6-13): z' = lower + (upper - lower) * t_rand with
+// mids = .5 (z[1:] + z[:-1]); t_rand is the caller's torch.rand draw.  One thread per sample.
+__global__ void __launch_bounds__(256) jitter_z_kernel(const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ tvals,
+                                                       const float* __restrict__ t_rand, int64_t R, int N, float* __restrict__ z_out) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= R * N) return;
+  const int64_t r = s / N;
+  const int i = (int)(s - r * N);
+  const float n = near[r], f = far[r];
+  const float z = sample_z(n, f, tvals[i]);
+  const float lower = i > 0 ? xmul(0.5f, xadd(z, sample_z(n, f, tvals[i - 1]))) : z;
+  const float upper = i + 1 < N ? xmul(0.5f, xadd(sample_z(n, f, tvals[i + 1]), z)) : z;
+  z_out[s] = xadd(lower, xmul(xsub(upper, lower), t_rand[s]));
+}
+
+// With density noise a transparent sample has alpha = 1 - exp(-relu(0 + noise) dist) > 0 and its colour counts, so the
+// reference's "network on every sample" (can_render.py:113-120 zeroes only the density) is kept literally: every sample
+// goes to the active list (entry s = sample s) with its exact nearest triangle, and the mask bit says whether the
+// compositor keeps the sample's density (bit set) or replaces it by 0 (transparent).
+__global__ void __launch_bounds__(256) sample_warp_all_kernel(WarpArgs a, Grid g, int F, const float* __restrict__ cent) {
+  const int64_t P = a.R * a.N;
+  const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  bool opaque = false;
+  if (s < P) {
+    float px, py, pz;
+    sample_position(a, s, px, py, pz);
+    const int idx = nearest_any(g, cent, F, px, py, pz);
+    int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
+    float u, v, h;
+    project_point(v3(px, py, pz), ldv3(a.posed, i0), ldv3(a.posed, i1), ldv3(a.posed, i2), u, v, h);
+    const V3 xc = map_to_triangle(u, v, h, ldv3(a.canon, i0), ldv3(a.canon, i1), ldv3(a.canon, i2));
+    a.active[s] = make_float4(xc.x, xc.y, xc.z, __int_as_float((int)s));
+    a.active_tri[s] = idx;
+    opaque = !is_transparent(u, v, h);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, opaque);
+  if ((threadIdx.x & 31) == 0 && s < P) a.sample_mask[s >> 5] = m;
+  if (threadIdx.x == 0) atomicAdd(a.counters, (unsigned long long)min((int64_t)256, P - s));
 }
 
 }  // namespace dsn

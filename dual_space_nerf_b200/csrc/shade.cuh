@@ -183,6 +183,9 @@ struct CompositeArgs {
   const unsigned* sample_mask; // bit (s & 31) of word s >> 5 set <=> raw[s] was written (s = r*N + i); NULL => all
   int64_t R; int N;
   float* rgb; float* depth; float* acc; float* disp; float* weights; float* z_out;
+  // training mode (utils/nerf_net_utils.py:29-33): noise (R,N) = randn * raw_noise_std is added to the density before the
+  // ReLU.  all_raw: raw holds EVERY sample and a clear mask bit only zeroes the density (can_render.py:118-120).
+  const float* noise; int all_raw;
 };
 
 __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
@@ -203,7 +206,9 @@ __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
       if (i + 1 < a.N) zn = a.z_in ? a.z_in[r * a.N + i + 1] : sample_z(near, far, a.tvals[i + 1]);
       const int64_t sidx = r * a.N + i;
       bool has = a.sample_mask ? ((a.sample_mask[sidx >> 5] >> (sidx & 31)) & 1u) : true;
-      if (has) c = a.raw[r * a.N + i];
+      if (has || a.all_raw) c = a.raw[r * a.N + i];
+      if (!has) c.w = 0.f;
+      if (a.noise) c.w = xadd(c.w, a.noise[sidx]);
     }
     float dist = (i + 1 < a.N) ? xsub(zn, z) : 1e10f;
     dist = xmul(dist, nd);

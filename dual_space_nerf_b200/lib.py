@@ -17,8 +17,8 @@ NUM_WEIGHT_TENSORS = 33
 
 ENTRY_POINTS = [
     "dsnerf_abi_version", "dsnerf_create", "dsnerf_destroy", "dsnerf_last_error", "dsnerf_set_weights",
-    "dsnerf_set_mesh", "dsnerf_set_frame", "dsnerf_render", "dsnerf_render_host", "dsnerf_render_z",
-    "dsnerf_resample", "dsnerf_composite", "dsnerf_warp_points", "dsnerf_query_density", "dsnerf_eval_points", "dsnerf_ppts_to_pts", "dsnerf_camera_rays",
+    "dsnerf_set_mesh", "dsnerf_set_frame", "dsnerf_render", "dsnerf_render_train", "dsnerf_render_host", "dsnerf_render_z",
+    "dsnerf_resample", "dsnerf_composite", "dsnerf_composite_noise", "dsnerf_warp_points", "dsnerf_query_density", "dsnerf_eval_points", "dsnerf_ppts_to_pts", "dsnerf_camera_rays",
     "dsnerf_get_stats", "dsnerf_profile", "dsnerf_profile_read", "dsnerf_debug_tc_timing", "dsnerf_debug_table", "dsnerf_debug_sm_clock", "dsnerf_debug_active",
 ]
 
@@ -61,9 +61,11 @@ def load():
     L.dsnerf_set_frame.argtypes = [vp, fp, fp, ci, ci, fp, fp, fp, vp]
     L.dsnerf_render.argtypes = [vp, fp, fp, fp, fp, i64, ci, cu, fp, fp, fp, fp, fp, fp, vp]
     L.dsnerf_render_host.argtypes = L.dsnerf_render.argtypes
+    L.dsnerf_render_train.argtypes = [vp, fp, fp, fp, fp, i64, ci, cu, fp, fp, fp, fp, fp, fp, fp, fp, vp]
     L.dsnerf_render_z.argtypes = [vp, fp, fp, fp, i64, ci, cu, fp, fp, fp, fp, fp, vp]
     L.dsnerf_resample.argtypes = [vp, fp, fp, i64, ci, ci, fp, vp]
     L.dsnerf_composite.argtypes = [vp, fp, fp, fp, i64, ci, fp, fp, fp, fp, fp, vp]
+    L.dsnerf_composite_noise.argtypes = [vp, fp, fp, fp, fp, i64, ci, fp, fp, fp, fp, fp, vp]
     L.dsnerf_warp_points.argtypes = [vp, fp, i64, fp, vp, vp, vp]
     L.dsnerf_query_density.argtypes = [vp, fp, vp, i64, fp, cu, vp]
     L.dsnerf_eval_points.argtypes = [vp, fp, fp, fp, i64, fp, fp, cu, vp]

@@ -9,8 +9,11 @@ Not a port: there is no chunking (the reference chunks 3072 rays at a time to
 bound its (V x rays x 3) intermediates, can_render.py:257), no autograd graph,
 no per-chunk device->host copy; one call renders the whole ray batch.
 
-Eval mode only in this round: ``train()`` + render raises (stratified jitter and
-density noise of the training forward are SURVEY.md 8f row 4).
+``train()`` + ``render(batch)`` / ``render_rays`` is the training-mode FORWARD (stratified
+jitter and density noise): the random draws are made on the
+device with torch (``self.generator``) and handed to the kernels; no autograd
+graph is built, so gradients for training stay with the caller's PyTorch model.
+``render_view`` and the hierarchical pass are eval-mode only.
 """
 from __future__ import annotations
 
@@ -62,6 +65,7 @@ class Renderer:
         # optional early ray termination (DSNERF_EARLY_STOP, include/dsnerf.h): off by default, the default path evaluates every
         # non-transparent sample like the reference
         self.early_stop = False
+        self.generator = None  # torch.Generator on the device for the training-mode draws (None = global generator)
         cv = canonical_vertex
         if cv is not None:
             cv = torch.as_tensor(cv, dtype=torch.float32).reshape(-1, 3)
@@ -154,17 +158,38 @@ class Renderer:
 
     def _check_eval(self):
         if getattr(self.net, "training", False):
-            raise NotImplementedError("dual_space_nerf_b200.Renderer renders in eval mode only; call .eval() first")
+            raise NotImplementedError("this entry point of dual_space_nerf_b200.Renderer works in eval mode only; call .eval() first "
+                                      "(training mode is supported by render())")
 
-    def _render_rays_device(self, ray_o, ray_d, near, far, n_samples, want_weights):
+    def _training_draws(self, R, n_samples):
+        """The two random draws of a training-mode forward, on the device from ``self.generator`` (None = torch's global
+        CUDA generator): torch.rand for the stratified jitter when cfg.MODEL.perturb > 0 (utils/pts_utils.py:6-13) and
+        torch.randn * raw_noise_std when cfg.MODEL.raw_noise_std > 0 (utils/nerf_net_utils.py:29-33), else None."""
+        if not getattr(self.net, "training", False):
+            return None, None
+        gen = getattr(self, "generator", None)
+        jitter = noise = None
+        if float(getattr(self.cfg.MODEL, "perturb", 0.0)) > 0.0:
+            jitter = torch.rand(R, n_samples, device=self.device, generator=gen)
+        std = float(getattr(self.cfg.MODEL, "raw_noise_std", 0.0))
+        if std > 0.0:
+            noise = torch.randn(R, n_samples, device=self.device, generator=gen) * std
+        return jitter, noise
+
+    def _render_rays_device(self, ray_o, ray_d, near, far, n_samples, want_weights, jitter=None, noise=None):
         R = ray_o.shape[0]
         mk = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
         rgb, depth, acc, disp = mk(R, 3), mk(R), mk(R), mk(R)
         weights = mk(R, n_samples) if want_weights else None
         z_vals = mk(R, n_samples) if want_weights else None
-        self.ctx.check(self.ctx.L.dsnerf_render(self.ctx.h, _ptr(ray_o), _ptr(ray_d), _ptr(near), _ptr(far), R, n_samples,
-                                                self._flags(), _ptr(rgb), _ptr(depth), _ptr(acc), _ptr(disp), _ptr(weights),
-                                                _ptr(z_vals), self._stream()))
+        if jitter is not None or noise is not None:
+            self.ctx.check(self.ctx.L.dsnerf_render_train(self.ctx.h, _ptr(ray_o), _ptr(ray_d), _ptr(near), _ptr(far), R, n_samples,
+                                                          self._flags(), _ptr(jitter), _ptr(noise), _ptr(rgb), _ptr(depth), _ptr(acc),
+                                                          _ptr(disp), _ptr(weights), _ptr(z_vals), self._stream()))
+        else:
+            self.ctx.check(self.ctx.L.dsnerf_render(self.ctx.h, _ptr(ray_o), _ptr(ray_d), _ptr(near), _ptr(far), R, n_samples,
+                                                    self._flags(), _ptr(rgb), _ptr(depth), _ptr(acc), _ptr(disp), _ptr(weights),
+                                                    _ptr(z_vals), self._stream()))
         ret = {"color": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth}
         if want_weights:
             ret["weights"] = weights
@@ -182,9 +207,15 @@ class Renderer:
                                                   _ptr(rgb), _ptr(depth), _ptr(acc), _ptr(disp), _ptr(w), self._stream()))
         return {"color": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth, "weights": w, "z_vals": z2}
 
-    def render(self, batch):
-        """can_render.py:137-168: {"coarse": {color, disp_map, acc_map, depth_map, weights, z_vals}} on the GPU."""
-        self._check_eval()
+    def render(self, batch, jitter=None, noise=None):
+        """can_render.py:137-168: {"coarse": {color, disp_map, acc_map, depth_map, weights, z_vals}} on the GPU.
+
+        After ``train()`` this is the training-mode FORWARD (stratified jitter + density noise; the draws come from
+        ``_training_draws`` unless given explicitly as (R,N) tensors).  No autograd graph is built: gradients for
+        training stay with the caller's PyTorch model."""
+        training = getattr(self.net, "training", False)
+        if training and int(getattr(self.cfg.MODEL, "FINE_RAY_SAMPLING", -1)) > 0:
+            raise NotImplementedError("the hierarchical second pass is an eval-mode feature (own spec, DESIGN.md)")
         with torch.cuda.device(self.device):
             self._set_frame(batch)
             ray_o = self._dev(batch["ray_o"]).reshape(-1, 3)
@@ -192,7 +223,13 @@ class Renderer:
             near = self._dev(batch["near"]).reshape(-1)
             far = self._dev(batch["far"]).reshape(-1)
             N = int(self.cfg.MODEL.COARSE_RAY_SAMPLING)
-            coarse = self._render_rays_device(ray_o, ray_d, near, far, N, True)
+            if training and jitter is None and noise is None:
+                jitter, noise = self._training_draws(ray_o.shape[0], N)
+            if jitter is not None:
+                jitter = self._dev(jitter).reshape(-1, N)
+            if noise is not None:
+                noise = self._dev(noise).reshape(-1, N)
+            coarse = self._render_rays_device(ray_o, ray_d, near, far, N, True, jitter, noise)
             out = {"coarse": coarse}
             n_imp = int(getattr(self.cfg.MODEL, "FINE_RAY_SAMPLING", -1))
             if n_imp > 0:
@@ -335,8 +372,8 @@ class Renderer:
         return color, dens.reshape(P, 1), None
 
     def render_rays(self, pts, rays, z_vals, frame_idx, net, transparent_mask=None, batch_info=None):
-        """can_render.py:97-134 on explicit samples: pts/rays (R,N,6), z_vals (R,N)."""
-        self._check_eval()
+        """can_render.py:97-134 on explicit samples: pts/rays (R,N,6), z_vals (R,N); in training mode the density noise of
+        raw2outputs is drawn here (``_training_draws``)."""
         with torch.cuda.device(self.device):
             pts = self._dev(pts)
             rays = self._dev(rays)
@@ -350,8 +387,9 @@ class Renderer:
             rd = rays[:, 0, :3].contiguous()
             mk = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
             rgb, depth, acc, disp, w = mk(R, 3), mk(R), mk(R), mk(R), mk(R, N)
-            self.ctx.check(self.ctx.L.dsnerf_composite(self.ctx.h, _ptr(raw), _ptr(z), _ptr(rd), R, N, _ptr(rgb), _ptr(depth), _ptr(acc),
-                                                       _ptr(disp), _ptr(w), self._stream()))
+            noise = self._training_draws(R, N)[1]
+            self.ctx.check(self.ctx.L.dsnerf_composite_noise(self.ctx.h, _ptr(raw), _ptr(z), _ptr(rd), _ptr(noise), R, N, _ptr(rgb),
+                                                             _ptr(depth), _ptr(acc), _ptr(disp), _ptr(w), self._stream()))
         return {"color": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth, "weights": w, "z_vals": z}
 
     def batchify_pts(self, pts, rays, z_vals, frame_idx, chunk=1024 * 32, net=None, batch_info=None):

@@ -103,6 +103,16 @@ int dsnerf_render(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const
                   int64_t n_rays, int n_samples, unsigned flags, float* rgb, float* depth, float* acc, float* disp,
                   float* weights, float* z_vals, void* stream);
 
+/* Renderer.render with net.training == True (can_render.py:26-31, 105-108), forward only: the stratified jitter of
+ * uniform_sampling (utils/pts_utils.py:6-13, cfg.MODEL.perturb > 0) and the density noise of raw2outputs
+ * (utils/nerf_net_utils.py:29-33, cfg.MODEL.raw_noise_std > 0).  The reference draws both from torch's global generator;
+ * here the draws are inputs, DEVICE (R,N): jitter = torch.rand (NULL: perturb off), raw_noise = torch.randn * raw_noise_std
+ * (NULL: noise off).  With noise a transparent sample has weight relu(noise)-dependent > 0 and its colour counts, so the
+ * network runs on every sample as in the reference.  z_vals is required when jitter is given; near/far are not modified. */
+int dsnerf_render_train(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                        int64_t n_rays, int n_samples, unsigned flags, const float* jitter, const float* raw_noise,
+                        float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_vals, void* stream);
+
 /* Same call with HOST buffers (pinned or pageable): copies inputs to the device,
  * renders, copies the outputs back and synchronises the stream.  This is the
  * entry point Renderer.render_view (can_render.py:248-278) maps to, and what
@@ -127,6 +137,12 @@ int dsnerf_resample(dsnerf_ctx* ctx, const float* z_in, const float* weights, in
  * stand-alone op.  raw (R,N,4) = rgb + density, z_vals (R,N), ray_d (R,3); DEVICE. */
 int dsnerf_composite(dsnerf_ctx* ctx, const float* raw, const float* z_vals, const float* ray_d, int64_t n_rays,
                      int n_samples, float* rgb, float* depth, float* acc, float* disp, float* weights, void* stream);
+
+/* raw2outputs with raw_noise_std > 0 (utils/nerf_net_utils.py:29-33): raw_noise (R,N) = randn * raw_noise_std (DEVICE,
+ * NULL = none) is added to the density before the ReLU. */
+int dsnerf_composite_noise(dsnerf_ctx* ctx, const float* raw, const float* z_vals, const float* ray_d, const float* raw_noise,
+                           int64_t n_rays, int n_samples, float* rgb, float* depth, float* acc, float* disp, float* weights,
+                           void* stream);
 
 /* Renderer.w2l_without_lbs (can_render.py:333-379) as a stand-alone op on the
  * current frame: pts (P,3) -> xyz_cano (P,3), transparent (P) uint8, idx (P) int32

@@ -32,18 +32,25 @@ PE_L = 10
 
 
 # --------------------------------------------------------------------------- sampling
-def uniform_sampling(ray_o, ray_d, n_pts, near, far):
-    """utils/pts_utils.py:3-16, eval mode (no jitter)."""
+def uniform_sampling(ray_o, ray_d, n_pts, near, far, t_rand=None):
+    """utils/pts_utils.py:3-16.  ``t_rand`` (R,N) in [0,1) is the training-mode draw of ``torch.rand`` (:12): the
+    stratified jitter of :6-13 is applied when it is given (perturb > 0 and net.training), eval mode otherwise."""
     t = clib.linspace01(n_pts)
     z = near[:, None] * (f32(1.0) - t)[None] + far[:, None] * t[None]
+    if t_rand is not None:
+        z = z.astype(f32)
+        mids = f32(0.5) * (z[:, 1:] + z[:, :-1])
+        upper = np.concatenate([mids, z[:, -1:]], -1)
+        lower = np.concatenate([z[:, :1], mids], -1)
+        z = lower + (upper - lower) * np.asarray(t_rand, f32)
     pts = ray_o[:, None, :] + ray_d[:, None, :] * z[..., None]
     return pts.astype(f32), z.astype(f32)
 
 
-def gg_sampling(ray_o, ray_d, n_pts, near, far, xyz):
+def gg_sampling(ray_o, ray_d, n_pts, near, far, xyz, t_rand=None):
     """utils/pts_utils.py:18-58 (geometry-guided near/far then uniform samples)."""
     near2, far2 = clib.gg_bounds(ray_o[0], ray_d, xyz, near, far, GAMMA)
-    pts, z = uniform_sampling(ray_o, ray_d, n_pts, near2, far2)
+    pts, z = uniform_sampling(ray_o, ray_d, n_pts, near2, far2, t_rand)
     return pts, z, near2, far2
 
 
@@ -235,8 +242,11 @@ def lighting(W, normal_w, xyz_world, view_dir, essence, rounder=None):
 
 
 # --------------------------------------------------------------------------- compositing
-def raw2outputs(rgb, sigma, z_vals, rays_d):
-    """utils/nerf_net_utils.py:5-56 with raw_noise_std=0, white_bkgd=False."""
+def raw2outputs(rgb, sigma, z_vals, rays_d, noise=None):
+    """utils/nerf_net_utils.py:5-56 with white_bkgd=False.  ``noise`` (R,N) = randn * raw_noise_std is the training-mode
+    draw of :29-33, added to the density before the ReLU; None = raw_noise_std 0."""
+    if noise is not None:
+        sigma = (sigma + np.asarray(noise, f32)).astype(f32)
     R, N = z_vals.shape
     dists = z_vals[:, 1:] - z_vals[:, :-1]
     dists = np.concatenate([dists, np.full((R, 1), 1e10, f32)], 1)
@@ -351,7 +361,10 @@ class Oracle:
         self.rot = None if rot is None else np.asarray(rot, f32)
         self.rot_center = None if rot_center is None else np.asarray(rot_center, f32)
 
-    def shade_points(self, pts, z, ray_d, posed, poses, frame, Th=None, stages=None):
+    def shade_points(self, pts, z, ray_d, posed, poses, frame, Th=None, stages=None, noise=None):
+        """``noise`` given (training mode): a transparent sample then has alpha = 1 - exp(-relu(0 + noise) dist) > 0 and its
+        colour counts, so the network runs on EVERY sample as in the reference (can_render.py:113-120 zeroes only the
+        density); without noise the masked samples have weight exactly 0 and are skipped."""
         R, N = z.shape
         W = self.W
         posed = np.ascontiguousarray(posed, f32)
@@ -360,7 +373,7 @@ class Oracle:
         code = W.embedding[int(frame)] * (f32(0.0) if self.zero_code else f32(1.0))
         pf = pose_feature(W, poses)
         P = flat.shape[0]
-        active = ~mask
+        active = ~mask if noise is None else np.ones(mask.shape, bool)
         essence = np.zeros((P, 3), f32)
         sigma = np.zeros(P, f32)
         color = np.zeros((P, 3), f32)
@@ -380,8 +393,9 @@ class Oracle:
             vd = np.repeat(ray_d, N, axis=0)[a]
             c_a = lighting(W, n_a, xw.astype(f32), vd, e_a)
             essence[a], sigma[a], grad[a], nw[a], color[a], idx2[a] = e_a, s_a, g_a, n_a, c_a, i2
-        # masked samples: density forced to 0 (can_render.py:118-120) => weight exactly 0
-        out = raw2outputs(color.reshape(R, N, 3), sigma.reshape(R, N), z, ray_d)
+        # masked samples: density forced to 0 (can_render.py:118-120) => weight exactly 0 (without noise)
+        sigma[mask] = 0
+        out = raw2outputs(color.reshape(R, N, 3), sigma.reshape(R, N), z, ray_d, noise)
         out["z_vals"] = z
         if stages is not None:
             sig = np.zeros(P, np.uint64)
@@ -393,20 +407,21 @@ class Oracle:
                           grad=grad, normal_world=nw, color=color, idx_cano=idx2, pose_feat=pf)
         return out
 
-    def render(self, ray_o, ray_d, near, far, posed, poses, frame, Th=None, stages=None):
+    def render(self, ray_o, ray_d, near, far, posed, poses, frame, Th=None, stages=None, t_rand=None, noise=None):
+        """``t_rand`` / ``noise``: the training-mode draws (see uniform_sampling / raw2outputs); both None = eval mode."""
         ray_o = np.ascontiguousarray(ray_o, f32).reshape(-1, 3)
         ray_d = np.ascontiguousarray(ray_d, f32).reshape(-1, 3)
         near = np.ascontiguousarray(near, f32).reshape(-1)
         far = np.ascontiguousarray(far, f32).reshape(-1)
         posed = np.ascontiguousarray(posed, f32)
         if self.mode == "GG":
-            pts, z, n2, f2 = gg_sampling(ray_o, ray_d, self.N, near, far, posed)
+            pts, z, n2, f2 = gg_sampling(ray_o, ray_d, self.N, near, far, posed, t_rand)
         else:
-            pts, z = uniform_sampling(ray_o, ray_d, self.N, near, far)
+            pts, z = uniform_sampling(ray_o, ray_d, self.N, near, far, t_rand)
             n2, f2 = near, far
         if stages is not None:
             stages.update(near_gg=n2, far_gg=f2, pts=pts, z_vals=z)
-        return self.shade_points(pts, z, ray_d, posed, poses, frame, Th, stages)
+        return self.shade_points(pts, z, ray_d, posed, poses, frame, Th, stages, noise)
 
     def render_hierarchical(self, ray_o, ray_d, near, far, posed, poses, frame, n_importance=128, Th=None):
         """Config 3 (own spec): coarse pass -> sample_pdf -> second pass of the SAME net on the

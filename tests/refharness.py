@@ -83,6 +83,37 @@ class ReferenceRig:
         out = self.renderer.render(b)["coarse"]
         return {k: v.detach().numpy() for k, v in out.items()}
 
+    def render_train(self, rays, t_rand, noise):
+        """``Renderer.render`` in TRAINING mode (perturb = raw_noise_std = 1).  The reference draws the jitter with
+        ``torch.rand`` (utils/pts_utils.py:12) and the density noise with ``torch.randn`` (utils/nerf_net_utils.py:31)
+        from the global generator; both are replaced for the duration of the call by functions that hand out the given
+        arrays, so that the draws are inputs of the golden vector instead of a property of torch's CPU generator."""
+        b = self.batch(rays)
+        real_rand, real_randn = torch.rand, torch.randn
+        used = []
+
+        def fake_rand(*shape, **kw):
+            shape = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+            assert shape[-2:] == t_rand.shape, shape
+            used.append("rand")
+            return torch.from_numpy(t_rand.copy()).reshape(shape)
+
+        def fake_randn(*shape, **kw):
+            shape = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+            assert shape == noise.shape, shape
+            used.append("randn")
+            return torch.from_numpy(noise.copy())
+
+        self.renderer.train()
+        torch.rand, torch.randn = fake_rand, fake_randn
+        try:
+            out = self.renderer.render(b)["coarse"]
+        finally:
+            torch.rand, torch.randn = real_rand, real_randn
+            self.renderer.eval()
+        assert used == ["rand", "randn"], used
+        return {k: v.detach().numpy() for k, v in out.items()}
+
     def render_view(self):
         b = self.batch(None)
         out = self.renderer.render_view(b)

@@ -315,6 +315,61 @@ def test_tiny_mesh_vs_oracle(state_dict):
     C.check_rays(out, ref, kink_rays(st, n), what="tetrahedron")
 
 
+def test_training_mode_forward(scene64, state_dict):
+    """Renderer.train() + render(batch): stratified jitter + density noise through
+    dsnerf_render_train, with the random draws as inputs, against the reference's own training-mode output (golden) and
+    the oracle; jitter alone takes the transparent-skip path and must match the reference's all-sample evaluation too."""
+    g = C.golden("render_train.npz")
+    rays = g["rays"]
+    n = 32
+    r = make_renderer(scene64, n)
+    from oracle import oracle as O
+
+    o = O.Oracle(state_dict, scene64["canonical"], scene64["faces"], n)
+    args = (scene64["ray_o"][rays], scene64["ray_d"][rays], scene64["near"][rays], scene64["far"][rays], scene64["posed"],
+            scene64["poses"], scene64["frame"])
+    st = {}
+    ref = o.render(*args, Th=scene64["Th"], t_rand=g["t_rand"], noise=g["noise"], stages=st)
+    r.train()
+    out = to_np(r.render(S.to_batch(scene64, torch, rays=rays), jitter=torch.from_numpy(g["t_rand"]),
+                         noise=torch.from_numpy(g["noise"]))["coarse"])
+    assert r.ctx.stats()["evaluated_samples"] == len(rays) * n  # the network ran on every sample
+    assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0
+    kink = kink_rays(st, n)
+    print("train", C.check_rays(out, g, kink, what="train vs reference"), C.check_rays(out, ref, kink, what="train vs oracle"))
+    assert np.abs(out["weights"] - g["weights"]).max() < 1e-4
+    # jitter only
+    st2 = {}
+    o.render(*args, Th=scene64["Th"], t_rand=g["t_rand"], stages=st2)
+    out2 = to_np(r.render(S.to_batch(scene64, torch, rays=rays), jitter=torch.from_numpy(g["t_rand"]))["coarse"])
+    assert r.ctx.stats()["evaluated_samples"] == int((~st2["mask"]).sum())
+    assert C.bits_equal(out2["z_vals"], g["jitter_only_z_vals"]) == 0
+    C.check_rays(out2, {k[12:]: g[k] for k in g.files if k.startswith("jitter_only_")}, kink_rays(st2, n), what="jitter only")
+    # draws made by the renderer itself: reproducible from the generator, different from eval mode, z stays sorted
+    r.generator = torch.Generator(device="cuda:0").manual_seed(7)
+    a = to_np(r.render(S.to_batch(scene64, torch, rays=rays))["coarse"])
+    r.generator.manual_seed(7)
+    b = to_np(r.render(S.to_batch(scene64, torch, rays=rays))["coarse"])
+    assert all(np.array_equal(a[k], b[k], equal_nan=True) for k in a)
+    assert np.all(np.diff(a["z_vals"], axis=1) >= 0)
+    r.eval()
+    e = to_np(r.render(S.to_batch(scene64, torch, rays=rays))["coarse"])
+    assert np.abs(e["acc_map"] - a["acc_map"]).max() > 1e-3
+    # raw2outputs with noise as a stand-alone op (render_rays in training mode draws it; here: explicit, vs the oracle)
+    import ctypes
+    raw = torch.randn(64, n, 4, generator=torch.Generator().manual_seed(1)).cuda()
+    z = torch.sort(torch.rand(64, n, generator=torch.Generator().manual_seed(2)) + 2.0, dim=1)[0].cuda()
+    rd = torch.randn(64, 3, generator=torch.Generator().manual_seed(3)).cuda()
+    nz = torch.randn(64, n, generator=torch.Generator().manual_seed(4)).cuda()
+    mk = lambda *s: torch.empty(*s, device="cuda:0")
+    rgb, dep, acc, dsp, w = mk(64, 3), mk(64), mk(64), mk(64), mk(64, n)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    r.ctx.check(r.ctx.L.dsnerf_composite_noise(r.ctx.h, p(raw), p(z), p(rd), p(nz), 64, n, p(rgb), p(dep), p(acc), p(dsp), p(w), None))
+    want = O.raw2outputs(raw[..., :3].cpu().numpy(), raw[..., 3].cpu().numpy(), z.cpu().numpy(), rd.cpu().numpy(), nz.cpu().numpy())
+    assert np.abs(w.cpu().numpy() - want["weights"]).max() < 1e-6
+    assert np.abs(rgb.cpu().numpy() - want["color"]).max() < 1e-5
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

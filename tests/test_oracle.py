@@ -187,3 +187,23 @@ def test_camera_rays_oracle_vs_reference_golden_and_live():
         ro, rd = m.get_rays(32, 40, sc["K"], sc["R"], sc["T"].reshape(3, 1))
         o, d = O.camera_rays(32, 40, sc["K"], sc["R"], sc["T"])
         assert np.array_equal(rd.reshape(-1, 3).astype(np.float32), d.astype(np.float32))
+
+
+def test_training_mode_forward_vs_reference_golden(state_dict):
+    """Training-mode forward: stratified jitter (utils/pts_utils.py:6-13) and density noise
+    (utils/nerf_net_utils.py:29-33) with the draws as inputs, against the UNMODIFIED reference run by
+    tests/make_golden_train.py: z bit-exact, per-ray outputs within 1e-5 (fp32 summation order)."""
+    g = C.golden("render_train.npz")
+    sc = S.make_scene(64, 64)
+    rays = g["rays"]
+    o = O.Oracle(state_dict, sc["canonical"], sc["faces"], 32)
+    args = (sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays], sc["posed"], sc["poses"], sc["frame"])
+    out = o.render(*args, Th=sc["Th"], t_rand=g["t_rand"], noise=g["noise"])
+    assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0
+    for k in ("color", "depth_map", "acc_map", "weights"):
+        assert np.abs(out[k] - g[k]).max() < 1e-5, k
+    jit = o.render(*args, Th=sc["Th"], t_rand=g["t_rand"])  # jitter only: transparent samples are skipped exactly
+    for k in ("color", "depth_map", "acc_map", "weights"):
+        assert np.abs(jit[k] - g["jitter_only_" + k]).max() < 1e-5, k
+    # the noise matters: the two goldens differ by far more than the tolerance
+    assert np.abs(g["acc_map"] - g["jitter_only_acc_map"]).max() > 0.05

@@ -92,7 +92,7 @@ struct dsnerf_ctx {
   int has_rot = 0;
   // ---- workspace
   DevBuf tc_timing;
-  DevBuf near2, far2, raw, active, active_tri, ray_mask, mlp_a, mlp_g, tvals, counters, io;
+  DevBuf near2, far2, raw, active, active_tri, active_cidx, ray_mask, mlp_a, mlp_g, tvals, counters, io;
   DevBuf ert_active, ert_tri, ert_state, ert_cnt;  // early-ray-termination mode only
   unsigned long long* h_ert = nullptr;              // pinned, 8 entries
   int tvals_n = 0;
@@ -228,7 +228,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CK(mg.estate.ensure((size_t)mg.ncell + 4));
   CK(mg.ereq.ensure(sizeof(int) * (size_t)mg.ncell));
   CK(mg.pool.ensure(sizeof(float4) * (size_t)kPoolEntries));
-  CK(mg.pool_used.ensure(sizeof(int) * 16));
+  CK(mg.pool_used.ensure(sizeof(int) * 32));
   g.cell_start = mg.start.as<int>();
   g.sorted = mg.sorted.as<float4>();
   g.row_mask = mg.rowmask.as<unsigned long long>();
@@ -251,7 +251,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CK(cudaMemsetAsync(mg.rowmask.p, 0, sizeof(unsigned long long) * nrow, st));
   CK(cudaMemsetAsync(mg.tstate.p, 0, (size_t)mg.ntab + 4, st));
   CK(cudaMemsetAsync(mg.estate.p, 0, (size_t)mg.ncell + 4, st));
-  CK(cudaMemsetAsync(mg.pool_used.p, 0, sizeof(int) * 16, st));
+  CK(cudaMemsetAsync(mg.pool_used.p, 0, sizeof(int) * 32, st));
   grid_count_kernel<<<fb, 256, 0, st>>>(g, mg.cent.as<float>(), F, mg.counts.as<int>(), mg.rowmask.as<unsigned long long>());
   CKL("grid_count");
   grid_scan_kernel<<<1, 1024, 0, st>>>(mg.counts.as<int>(), mg.ncell, mg.start.as<int>(), mg.cursor.as<int>());
@@ -287,6 +287,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
 template <class Mark>
 int ensure_cells(dsnerf_ctx* ctx, MeshGrid& mg, cudaStream_t st, Mark&& mark) {
   CK(cudaMemsetAsync(mg.pool_used.as<int>() + 1, 0, 3 * sizeof(int), st));
+  CK(cudaMemsetAsync(mg.pool_used.as<int>() + 16, 0, 2 * sizeof(int), st));
   mark();
   CKL("mark");
   build_cells_kernel<1><<<ctx->sm_count * 8, BUILD_WARPS * 32, 0, st>>>(mg.g);  // per requested enumeration cell
@@ -333,6 +334,7 @@ int ensure_workspace(dsnerf_ctx* ctx, int64_t R, int N) {
   CK(ctx->raw.ensure(sizeof(float4) * P));
   CK(ctx->active.ensure(sizeof(float4) * (P + 128)));
   CK(ctx->active_tri.ensure(sizeof(int) * (P + 128)));
+  CK(ctx->active_cidx.ensure(sizeof(int) * (P + 128)));
   CK(ctx->ray_mask.ensure(sizeof(unsigned) * (size_t)((P + 31) / 32 + 8)));
   CK(ctx->mlp_a.ensure(sizeof(float4) * (P + 128)));
   CK(ctx->mlp_g.ensure(sizeof(float4) * (P + 128)));
@@ -397,7 +399,8 @@ int check_ready(dsnerf_ctx* ctx, bool need_frame) {
   return 0;
 }
 
-int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStream_t st) {
+int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStream_t st, int* launches = nullptr) {
+  if (launches) *launches += (flags & DSNERF_MLP_FP32_SIMT) ? 4 : 5;  // mark_points, build<1>, build<2>, (canon_nearest,) lighting
   // canonical-space lookup cells of the active points (static mesh: cells stay built across frames)
   if (int e = ensure_cells(ctx, ctx->g_canon, st, [&] {
         mark_points_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(sa.active, sa.n_active, sa.n_active_host, ctx->g_canon.g);
@@ -407,7 +410,12 @@ int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStrea
     shade_kernel<<<ctx->sm_count * 3, SHADE_THREADS, SHADE_SMEM, st>>>(sa, ctx->lw, ctx->g_canon.g);
     CKL("shade");
   } else {
-    light_tc_kernel<<<ctx->sm_count * 2, LT_THREADS, LT_SMEM, st>>>(sa, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
+    ShadeArgs sb = sa;
+    canon_nearest_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(sa.active, sa.n_active, sa.n_active_host, ctx->g_canon.g, ctx->g_canon.cent.as<float>(),
+                                                            ctx->F, ctx->active_cidx.as<int>());
+    CKL("canon_nearest");
+    sb.active_cidx = ctx->active_cidx.as<int>();
+    light_tc_kernel<<<ctx->sm_count * 2, LT_THREADS, LT_SMEM, st>>>(sb, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
     CKL("light_tc");
   }
   return 0;
@@ -519,12 +527,12 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
     if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;
     sa.n_active = cnt;
     sa.active_tri = ctx->active_tri.as<int>();
-    if (int e = launch_shade(ctx, sa, flags, st)) return e;
+    if (int e = launch_shade(ctx, sa, flags, st, &launches)) return e;
     ca.noise = raw_noise;
     ca.all_raw = 1;
     composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
     CKL("composite");
-    launches += 6;
+    launches += 3;  // sample_warp_all, MLP, composite
   } else if ((flags & DSNERF_EARLY_STOP) && N >= 8 && N % 4 == 0) {
     // ---- early ray termination: four front-to-back waves of samples; see shade.cuh
     constexpr int kWaves = 4;
@@ -558,11 +566,11 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
       sa.active = list;
       sa.active_tri = tri;
       sa.n_active = count;
-      if (int e = launch_shade(ctx, sa, flags, st)) return e;
+      if (int e = launch_shade(ctx, sa, flags, st, &launches)) return e;
       const int i0 = k * wsize, i1 = std::min(N, (k + 1) * wsize);
       composite_wave_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca, ctx->ert_state.as<RayState>(), i0, i1, tau, k == kWaves - 1);
       CKL("composite_wave");
-      launches += 6;
+      launches += 2;  // MLP, composite_wave
     }
     CK(cudaMemcpyAsync(ctx->h_ert, ec, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     ctx->ert_mode = 1;
@@ -574,8 +582,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
     ++launches;
     sa.n_active = cnt;
     sa.active_tri = ctx->active_tri.as<int>();
-    if (int e = launch_shade(ctx, sa, flags, st)) return e;
-    launches += 3;
+    if (int e = launch_shade(ctx, sa, flags, st, &launches)) return e;
     composite_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(ca);
     CKL("composite");
     ++launches;
@@ -628,7 +635,7 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->light_w2, &ctx->wblob, &ctx->bias0, &ctx->faces, &ctx->canon, &ctx->posed, &ctx->vq, &ctx->gg_bins, &ctx->normal_m, &ctx->near2, &ctx->far2, &ctx->raw,
-                    &ctx->active, &ctx->active_tri, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io,
+                    &ctx->active, &ctx->active_tri, &ctx->active_cidx, &ctx->ray_mask, &ctx->mlp_a, &ctx->mlp_g, &ctx->tvals, &ctx->counters, &ctx->io,
                     &ctx->ert_active, &ctx->ert_tri, &ctx->ert_state, &ctx->ert_cnt};
   for (DevBuf* b : bufs) b->release();
   ctx->g_canon.release();

@@ -115,7 +115,7 @@ struct Grid {
   int2* __restrict__ trec;                         // per table cell: (off, cnt), see above
   float4* __restrict__ pool;                       // candidate lists
   int pool_cap;
-  int* __restrict__ pool_used;                     // [0] entries used, [1] table-cell requests, [2] enumeration-cell requests, [3] LEVEL-2 left-overs, [4..10] debug counters
+  int* __restrict__ pool_used;                     // [0] entries used, [1] table-cell requests, [2] enumeration-cell requests, [3] LEVEL-2 left-overs, [4..10] and [13..15] debug counters, [16], [17] work counters of the two build levels
   int debug;                                       // count build outcomes in pool_used[4..10]
 };
 
@@ -377,7 +377,11 @@ __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py
   __syncwarp();
 }
 
-constexpr int LIST_CAP = 64;      // longest candidate list kept; longer ones fall back to the ball scan
+#ifndef DSN_LIST_CAP
+#define DSN_LIST_CAP 256
+#endif
+constexpr int LIST_CAP = DSN_LIST_CAP;      // longest candidate list kept; longer ones fall back to the ball scan (64 -> 256: the cells
+                                         // deep inside the body see a whole ring of centroids; 7 % -> 0.5 % of the lookups scan)
 constexpr int BUF_CAP = 448;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
 constexpr int BUILD_WARPS = 4;
 
@@ -474,7 +478,13 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
   const float at = 0.5f * tcell * 1.0002f + 2e-6f;
   const float rho = LEVEL == 1 ? 2.0f * g.thalf_diag : g.thalf_diag;
   const int lnx = LEVEL == 1 ? g.nx : g.tnx, lny = LEVEL == 1 ? g.ny : g.tny;
-  for (int r = blockIdx.x * BUILD_WARPS + w; r < n_req; r += gridDim.x * BUILD_WARPS) {
+  for (;;) {
+    // cells differ in cost by two orders of magnitude (deep inside the body a cell sees a whole ring of centroids): warps
+    // fetch their next cell from a work counter instead of striding
+    int r = 0;
+    if (lane == 0) r = atomicAdd(g.pool_used + 15 + LEVEL, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= n_req) break;
     const int cell = LEVEL == 1 ? g.ereq[r] : g.req2[r];
     const int tx = cell % lnx, ty = (cell / lnx) % lny, tz = cell / (lnx * lny);
     const int par = LEVEL == 1 ? cell : ((tz >> 1) * g.ny + (ty >> 1)) * g.nx + (tx >> 1);
@@ -916,12 +926,12 @@ __global__ void __launch_bounds__(256) mark_points_kernel(const float4* __restri
 __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, Grid g) {
   __shared__ int queue[WARP_THREADS];
   __shared__ int qn;
-  __shared__ int bin_count[8], bin_start[8];
+  __shared__ int bin_count[16], bin_start[16];
   __shared__ unsigned char flag[WARP_THREADS];
   const int64_t P = a.R * a.N;
   const int64_t s0 = (int64_t)blockIdx.x * WARP_THREADS;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x < 8) bin_count[threadIdx.x] = 0;
+  if (threadIdx.x < 16) bin_count[threadIdx.x] = 0;
   flag[threadIdx.x] = 0;
   __syncthreads();
   // phase 1: place the sample, look its table cell up.  Samples that need the exact search are queued, bucketed by the
@@ -935,7 +945,7 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
       const int cell = live_cell(g, px, py, pz);
       if (cell >= 0) {
         const int cnt = g.trec[cell].y;
-        if (cnt != -1) my_bin = cnt < 0 ? 7 : min(6, cnt >> 3);
+        if (cnt != -1) my_bin = cnt < 0 ? 15 : min(14, cnt >> 3);
       }
     }
     if (my_bin >= 0) atomicAdd(&bin_count[my_bin], 1);
@@ -943,7 +953,7 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int b = 7; b >= 0; --b) { bin_start[b] = acc; acc += bin_count[b]; }  // long lists first
+    for (int b = 15; b >= 0; --b) { bin_start[b] = acc; acc += bin_count[b]; }  // long lists first
     qn = acc;
   }
   __syncthreads();

@@ -1,16 +1,17 @@
 // Shading on the tensor cores: normal_local2world + LightingMLP (model/spacenet.py:165-188, 278-298).
 //
 // Tile = 128 active samples per CTA iteration, one thread per sample (4 warps):
-//   A. exact nearest canonical centroid, world normal, world position, view direction (shade_inputs), then the
-//      9 -> 128 first layer in fp32 registers; ReLU output is written as the fp16 A operand (K-major core matrices);
+//   A. world normal (through the nearest canonical triangle found by canon_nearest_kernel beforehand), world position,
+//      view direction (shade_inputs), then the 9 -> 128 first layer in fp32 registers; ReLU output is written as the fp16 A operand (K-major core matrices);
 //   B. one elected lane issues 8 tcgen05.mma (M = 128, N = 128, K = 16; A and B from shared memory): the 128 x 128
 //      second layer.  Its weights are packed on the host into the B-operand image and fetched once per CTA with
 //      cp.async.bulk, so they stay resident in shared memory for every tile of the CTA;
 //   C. tcgen05.ld of the thread's accumulator row, bias + ReLU + 128 -> 1 dot + ELU in fp32, colour = (out+1)*essence.
 // A CTA runs TWO such tiles side by side (256 threads: two independent 4-warp halves with their own A operand,
 // accumulator, mbarrier and named barrier) on one copy of the second-layer weights: ~103 KB of shared memory and 256 TMEM
-// columns per CTA, two CTAs = 16 warps per SM.  The kernel is latency bound (dependent gathers of shade_inputs), so the
-// number of independent tiles in flight per SM is what counts (3 x 4 warps with one tile per CTA: 1.72 ms).  Only the middle layer is rounded to fp16 (single pass): the lighting term is smooth and enters the
+// columns per CTA, two CTAs = 16 warps per SM (registers and TMEM allow no more).  With so few warps the kernel cannot hide
+// chains of dependent gathers: the nearest-centroid search used to run inside shade_inputs here (1.42 ms); as a separate
+// full-occupancy kernel it takes 0.31 ms and this kernel 0.36 ms.  Only the middle layer is rounded to fp16 (single pass): the lighting term is smooth and enters the
 // colour linearly (measured effect on |d rgb| is ~1e-5); the fp32 SIMT kernel in shade.cuh remains as
 // the verification path.
 #pragma once
@@ -76,21 +77,23 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
   // the records of the next tile are fetched while the current one is processed (they head a chain of ~6 dependent gathers)
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 ac_n = zero4, ma_n = zero4, mg_n = zero4;
+  int ci_n = -1;
   {
     const int64_t t0 = ((int64_t)blockIdx.x * 2 + half) * LT_ROWS + row;
-    if (t0 < n_active) { ac_n = a.active[t0]; ma_n = a.mlp_a[t0]; mg_n = a.mlp_g[t0]; }
+    if (t0 < n_active) { ac_n = a.active[t0]; ma_n = a.mlp_a[t0]; mg_n = a.mlp_g[t0]; if (a.active_cidx) ci_n = a.active_cidx[t0]; }
   }
   for (int64_t tile = (int64_t)blockIdx.x * 2 + half; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
     const int64_t t = tile * LT_ROWS + row;
     const bool live = t < n_active;
     float in[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float4 ac = ac_n, ma = ma_n, mg = mg_n;
+    const int ci = ci_n;
     {
       const int64_t tn = t + (int64_t)gridDim.x * 2 * LT_ROWS;
-      if (tn < n_active) { ac_n = a.active[tn]; ma_n = a.mlp_a[tn]; mg_n = a.mlp_g[tn]; }
+      if (tn < n_active) { ac_n = a.active[tn]; ma_n = a.mlp_a[tn]; mg_n = a.mlp_g[tn]; if (a.active_cidx) ci_n = a.active_cidx[tn]; }
     }
     int sample = 0;
-    if (live) shade_inputs(a, gc, ac, mg, in, sample);
+    if (live) shade_inputs(a, gc, ac, mg, in, sample, ci);
     // ---- first layer (fp32) -> fp16 A operand
 #pragma unroll 2
     for (int kc = 0; kc < 16; ++kc) {

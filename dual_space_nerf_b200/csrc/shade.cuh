@@ -24,6 +24,7 @@ struct ShadeArgs {
   int N;
   const float* posed; const float* canon; const int* faces; const float* cent_canon; int F;
   const float4* normal_m;  // (F,3) rows of the per-triangle canonical -> world normal map of the current frame
+  const int* active_cidx;  // nearest canonical triangle per active sample (canon_nearest_kernel); NULL => searched in place
   // explicit-point mode (dsnerf_eval_points): world position / view direction per point instead of rays
   const float* xyz_world; const float* view_dir;
   float light_shift[3]; int has_shift;
@@ -71,11 +72,35 @@ __global__ void normal_matrix_kernel(const float* __restrict__ canon, const floa
 // Inputs of the lighting MLP for active sample t: world normal (normal_local2world, model/spacenet.py:278-298, incl. the
 // exact nearest canonical centroid), world position (with the optional rot / light_center shift, :254-263) and the
 // normalised view direction (:179-181).
-__device__ __forceinline__ void shade_inputs(const ShadeArgs& a, const Grid& gc, float4 ac, float4 mg, float (&in)[9], int& sample) {
+// exact nearest canonical centroid through the canonical mesh's lookup table (cells requested by mark_points_kernel)
+__device__ __forceinline__ int canon_nearest(const Grid& gc, const float* __restrict__ cent, int F, float x, float y, float z) {
+  int idx = table_nearest(gc, live_cell(gc, x, y, z), x, y, z);
+  if (idx < 0) idx = brute_nearest(cent, F, x, y, z);  // outside the table / far from the canonical mesh (rare for warped points)
+  return idx;
+}
+// The search is a chain of dependent gathers (cell byte -> record -> candidate list, ~45 candidates per lookup on the
+// benchmark scene): it runs here at full occupancy instead of inside the register- and TMEM-limited lighting kernel
+// (16 warps per SM), which then only reads the result (lighting 1.42 ms -> 0.47 + 0.36 ms).  Consecutive lookups are
+// consecutive samples of a ray and mostly share a cell, so the lanes of a warp walk the same list with broadcast loads;
+// bucketing the lookups of a block by list length (as sample_warp_kernel does) breaks that and was slower (0.82 ms).
+__global__ void __launch_bounds__(256) canon_nearest_kernel(const float4* __restrict__ active, const unsigned long long* __restrict__ n_ptr,
+                                                            int64_t n_host, Grid gc, const float* __restrict__ cent, int F, int* __restrict__ out) {
+  const int64_t n = n_ptr ? (int64_t)*n_ptr : n_host;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = active[t];
+    out[t] = canon_nearest(gc, cent, F, p.x, p.y, p.z);
+    if (gc.debug) {  // profile bit 2: which path the lookups take (dsnerf_debug_table [13] list, [14] scan, [15] exhaustive)
+      const int cell = live_cell(gc, p.x, p.y, p.z);
+      const int c = cell < 0 ? -1 : gc.trec[cell].y;
+      atomicAdd(gc.pool_used + (c >= 0 ? 13 : (c == -2 ? 14 : 15)), 1);
+      if (c > 0) atomicAdd(gc.pool_used + 10, c);
+    }
+  }
+}
+
+__device__ __forceinline__ void shade_inputs(const ShadeArgs& a, const Grid& gc, float4 ac, float4 mg, float (&in)[9], int& sample, int cidx = -1) {
   sample = __float_as_int(ac.w);
-  // exact nearest canonical centroid through the canonical mesh's lookup table (cells requested by mark_points_kernel)
-  int idx = table_nearest(gc, live_cell(gc, ac.x, ac.y, ac.z), ac.x, ac.y, ac.z);
-  if (idx < 0) idx = brute_nearest(a.cent_canon, a.F, ac.x, ac.y, ac.z);  // outside the table / far: cannot happen for warped points
+  const int idx = cidx >= 0 ? cidx : canon_nearest(gc, a.cent_canon, a.F, ac.x, ac.y, ac.z);
   V3 nw = v3(0.f, 0.f, 0.f);
   {
     // normalize(M_idx g) with F.normalize's eps; the scale of g is removed first (range), g = 0 stays 0

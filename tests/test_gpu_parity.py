@@ -402,6 +402,8 @@ def test_composite_op_vs_oracle():
 
 
 def test_edge_cases_and_errors(scene64):
+    import ctypes
+
     from dual_space_nerf_b200 import lib
 
     r = make_renderer(scene64, 32)
@@ -421,8 +423,13 @@ def test_edge_cases_and_errors(scene64):
     with pytest.raises(lib.DsnerfError):  # call order is checked, errors are reported not aborted
         ctx.check(ctx.L.dsnerf_render(ctx.h, None, None, None, None, 1, 8, 1, None, None, None, None, None, None, None))
     r.train()
-    with pytest.raises(NotImplementedError):
-        r.render(S.to_batch(scene64, torch))
+    with pytest.raises(NotImplementedError):  # render_view is an eval-mode entry point (training mode: render(), see below)
+        r.render_view(S.to_batch(scene64, torch))
+    with pytest.raises(lib.DsnerfError):  # jittered sampling writes z into the caller's z_vals: required
+        ctx2 = r.ctx
+        d = torch.zeros(8, 3, device="cuda:0")
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        ctx2.check(ctx2.L.dsnerf_render_train(ctx2.h, p(d), p(d), p(d), p(d), 1, 8, 1, p(d), None, p(d), p(d), p(d), p(d), None, None, None))
 
 
 def test_hierarchical_config3_vs_oracle(scene64, state_dict):

@@ -339,6 +339,7 @@ __device__ __forceinline__ void request_cell(const Grid& g, int cell) {
 // Warp-cooperative visit of every centroid stored in a grid cell that intersects the ball (p, rho): the (z, y) rows of the
 // ball's bounding box are dealt to the lanes (a row costs three dependent loads before its centroids can be read, so 32
 // rows in flight hide that latency), each lane walks its row's run of centroids serially.  visit(q) runs per lane.
+// visit(q, j): q = g.sorted[j]
 template <class Visit>
 __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py, float pz, float rho, Visit&& visit) {
   const int lane = threadIdx.x & 31;
@@ -368,10 +369,10 @@ __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py
       float4 q = __ldg(g.sorted + b);
       for (int j = b + 1; j < e; ++j) {
         const float4 qn = __ldg(g.sorted + j);  // next load in flight while q is visited
-        visit(q);
+        visit(q, j - 1);
         q = qn;
       }
-      visit(q);
+      visit(q, e - 1);
     }
   }
   __syncwarp();
@@ -382,7 +383,10 @@ __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py
 #endif
 constexpr int LIST_CAP = DSN_LIST_CAP;      // longest candidate list kept; longer ones fall back to the ball scan (64 -> 256: the cells
                                          // deep inside the body see a whole ring of centroids; 7 % -> 0.5 % of the lookups scan)
-constexpr int BUF_CAP = 448;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
+#ifndef DSN_BUF_CAP
+#define DSN_BUF_CAP 448
+#endif
+constexpr int BUF_CAP = DSN_BUF_CAP;      // candidates buffered per enumeration cell (superset shared by its 8 table cells)
 constexpr int BUILD_WARPS = 4;
 
 // Candidate filter of a cube (centre x, half edge a) against a reference centroid r with |x - r|^2 = dr2: a centroid q
@@ -391,14 +395,16 @@ __device__ __forceinline__ bool can_beat(float d, float dr2, float a, float l1) 
 
 // Settle one table cell from a buffered candidate superset S[0..n) (all lanes of the warp call this): exact nearest c0 of the
 // cell centre, filter against c0, transparency proof (posed mesh), list -> pool.  `list` is a LIST_CAP scratch buffer.
-__device__ __forceinline__ int2 settle_cell(const Grid& g, const float4* S, int n, float4* list, float px, float py, float pz, float a, float rho,
+// S and list hold POSITIONS in g.sorted (4 bytes per candidate instead of the 16-byte record: the records are re-read
+// through L1, and the shared memory saved raises the builder's occupancy from 20 to 28 warps per SM).
+__device__ __forceinline__ int2 settle_cell(const Grid& g, const int* S, int n, int* list, float px, float py, float pz, float a, float rho,
                                             int& kind) {
   const int lane = threadIdx.x & 31;
   float mb = 3.0e38f;
   int mi = 0x7fffffff;
   float c0x = 0.f, c0y = 0.f, c0z = 0.f;
   for (int i = lane; i < n; i += 32) {
-    float4 q = S[i];
+    float4 q = __ldg(g.sorted + S[i]);
     float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
     float d = dx * dx + dy * dy + dz * dz;
     int id = __float_as_int(q.w);
@@ -420,9 +426,10 @@ __device__ __forceinline__ int2 settle_cell(const Grid& g, const float4* S, int 
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
     bool cand = false;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    int qi = 0;
     if (i < n) {
-      q = S[i];
+      qi = S[i];
+      const float4 q = __ldg(g.sorted + qi);
       float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
       float d = dx * dx + dy * dy + dz * dz;
       cand = can_beat(d, best, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
@@ -435,7 +442,7 @@ __device__ __forceinline__ int2 settle_cell(const Grid& g, const float4* S, int 
     unsigned m = __ballot_sync(0xffffffffu, cand);
     if (cand) {
       int slot = keep + __popc(m & ((1u << lane) - 1));
-      if (list != nullptr && slot < LIST_CAP) list[slot] = q;
+      if (list != nullptr && slot < LIST_CAP) list[slot] = qi;
     }
     keep += __popc(m);
   }
@@ -450,7 +457,7 @@ __device__ __forceinline__ int2 settle_cell(const Grid& g, const float4* S, int 
     if (lane == 0) off = atomicAdd(g.pool_used, keep);
     off = __shfl_sync(0xffffffffu, off, 0);
     if (off + keep <= g.pool_cap) {
-      for (int i = lane; i < keep; i += 32) g.pool[off + i] = list[i];
+      for (int i = lane; i < keep; i += 32) g.pool[off + i] = __ldg(g.sorted + list[i]);
       rec = make_int2(off, keep);
       kind = 6;
     }
@@ -467,8 +474,8 @@ __device__ __forceinline__ int2 settle_cell(const Grid& g, const float4* S, int 
 // LEVEL 2: table cells still unsettled (parent built by an earlier call, or its superset overflowed): own scan.
 template <int LEVEL>
 __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
-  __shared__ float4 buf[BUILD_WARPS][BUF_CAP];
-  __shared__ float4 lst[BUILD_WARPS][LIST_CAP];
+  __shared__ int buf[BUILD_WARPS][BUF_CAP];
+  __shared__ int lst[BUILD_WARPS][LIST_CAP];
   __shared__ int cnt_s[BUILD_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n_req = g.pool_used[LEVEL == 1 ? 2 : 3];
@@ -502,14 +509,14 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
     __syncwarp();
     float mb = dref2;
     int mi = cref;
-    warp_scan_ball(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q) {
+    warp_scan_ball(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j) {
       float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
       float d = dx * dx + dy * dy + dz * dz;
       ++visits;
       if (d < mb) { mb = d; mi = __float_as_int(q.w); }
       if (can_beat(d, dref2, a, fabsf(q.x - rx) + fabsf(q.y - ry) + fabsf(q.z - rz))) {
         int slot = atomicAdd(&cnt_s[w], 1);
-        if (slot < BUF_CAP) buf[w][slot] = q;
+        if (slot < BUF_CAP) buf[w][slot] = j;
       }
     });
     int nbuf = cnt_s[w];
@@ -526,12 +533,12 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
       __syncwarp();
       if (lane == 0) cnt_s[w] = 0;
       __syncwarp();
-      warp_scan_ball(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q) {
+      warp_scan_ball(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j) {
         float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
         ++visits;
         if (can_beat(dx * dx + dy * dy + dz * dz, mb, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z))) {
           int slot = atomicAdd(&cnt_s[w], 1);
-          if (slot < BUF_CAP) buf[w][slot] = q;
+          if (slot < BUF_CAP) buf[w][slot] = j;
         }
       });
       nbuf = cnt_s[w];

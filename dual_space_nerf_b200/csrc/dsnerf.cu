@@ -102,6 +102,8 @@ struct dsnerf_ctx {
   bool pin_busy = false;
   unsigned long long* h_counters = nullptr;  // pinned, 4 entries
   cudaEvent_t stats_ready = nullptr;
+  cudaStream_t copy = nullptr;   // dsnerf_render_host: ray upload next to the grid build that dsnerf_set_frame left on the caller's stream
+  cudaEvent_t copy_done = nullptr;
   dsnerf_stats_t stats{};
   // ---- profiling
   int profile = 0;
@@ -616,6 +618,8 @@ int dsnerf_create(dsnerf_ctx** out, int device) {
   ctx->sm_count = prop.multiProcessorCount;
   cudaEventCreateWithFlags(&ctx->pin_free, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->stats_ready, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming);
+  if (!getenv("DSNERF_NO_COPY_STREAM")) cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
   cudaMallocHost(reinterpret_cast<void**>(&ctx->h_counters), sizeof(unsigned long long) * 4);
   memset(ctx->h_counters, 0, sizeof(unsigned long long) * 4);
   cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ert), sizeof(unsigned long long) * 8);
@@ -646,6 +650,8 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   if (ctx->h_ert) cudaFreeHost(ctx->h_ert);
   if (ctx->pin_free) cudaEventDestroy(ctx->pin_free);
   if (ctx->stats_ready) cudaEventDestroy(ctx->stats_ready);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+  if (ctx->copy) cudaStreamDestroy(ctx->copy);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   delete ctx;
 }
@@ -840,10 +846,17 @@ int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, 
   float *d_rgb = d + 8 * R, *d_dep = d_rgb + 3 * R, *d_acc = d_dep + R, *d_dsp = d_acc + R;
   float* d_w = weights ? d_dsp + R : nullptr;
   float* d_z = z_vals ? (d_dsp + R + (weights ? opt_f : 0)) : nullptr;
-  CK(cudaMemcpyAsync(d_o, ray_o, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_d, ray_d, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_n, near, sizeof(float) * R, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_f, far, sizeof(float) * R, cudaMemcpyHostToDevice, st));
+  // The upload does not depend on anything queued on `st` (typically the per-frame grid build of dsnerf_set_frame): it runs
+  // on the context's copy stream and `st` joins it.  The staging buffer is free: the previous call ended with a stream sync.
+  cudaStream_t cs = ctx->copy ? ctx->copy : st;
+  CK(cudaMemcpyAsync(d_o, ray_o, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(d_d, ray_d, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(d_n, near, sizeof(float) * R, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(d_f, far, sizeof(float) * R, cudaMemcpyHostToDevice, cs));
+  if (cs != st) {
+    CK(cudaEventRecord(ctx->copy_done, cs));
+    CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+  }
   if (int e = render_impl(ctx, d_o, d_d, d_n, d_f, nullptr, R, N, flags, d_rgb, d_dep, d_acc, d_dsp, d_w, d_z, st)) return e;
   CK(cudaMemcpyAsync(rgb, d_rgb, sizeof(float) * 3 * R, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(depth, d_dep, sizeof(float) * R, cudaMemcpyDeviceToHost, st));

@@ -370,6 +370,22 @@ def test_training_mode_forward(scene64, state_dict):
     assert np.abs(rgb.cpu().numpy() - want["color"]).max() < 1e-5
 
 
+def test_rays_sharded_over_nccl_equal_unsharded():
+    """Config 4 style on real GPUs: one frame's rays split across 2 ranks over NCCL (dist.render_sharded) is bit-identical to
+    the unsharded render.  Needs 2 visible GPUs (skipped on a 1-GPU box; the gloo world-2 CPU test covers the host logic)."""
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "tests", "sharded_worker.py"), "128"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "bit_identical=True" in out.stdout
+
+
 def test_composite_op_vs_oracle():
     from oracle import oracle as O
     from dual_space_nerf_b200 import lib

@@ -219,6 +219,31 @@ __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
   if (r >= a.R) return;
   float nd = xnorm3(v3(a.ray_d[3 * r], a.ray_d[3 * r + 1], a.ray_d[3 * r + 2]));
   float near = a.z_in ? 0.f : a.near[r], far = a.z_in ? 0.f : a.far[r];
+  if (a.sample_mask && !a.z_in && !a.noise && !a.all_raw) {
+    // A ray without a single evaluated sample (3 of 4 rays of a frame): every density is 0, so alpha = 1 - exp(-0 * dist) = 0,
+    // T = 1 and all sums are exactly 0 (disp = 0/0 = NaN) whenever the distances are finite -- written without the scan.
+    const int64_t b0 = r * a.N, b1 = b0 + a.N;  // bit range of the ray in the mask
+    bool any = false;
+    for (int64_t wd = (b0 >> 5) + lane; wd <= ((b1 - 1) >> 5); wd += 32) {
+      unsigned m = a.sample_mask[wd];
+      if (wd == (b0 >> 5)) m &= ~0u << (b0 & 31);
+      if (wd == ((b1 - 1) >> 5) && (b1 & 31)) m &= ~0u >> (32 - (b1 & 31));
+      any |= m != 0u;
+    }
+    const float span = fabsf(near) + fabsf(far) + nd;  // finite <=> near, far and |d| are
+    if (!__any_sync(0xffffffffu, any) && span < 3.0e38f) {
+      for (int i = lane; i < a.N; i += 32) {
+        if (a.weights) a.weights[b0 + i] = 0.f;
+        if (a.z_out) a.z_out[b0 + i] = sample_z(near, far, a.tvals[i]);
+      }
+      if (lane == 0) {
+        a.rgb[3 * r] = 0.f; a.rgb[3 * r + 1] = 0.f; a.rgb[3 * r + 2] = 0.f;
+        a.depth[r] = 0.f; a.acc[r] = 0.f;
+        a.disp[r] = __int_as_float(0x7fc00000);
+      }
+      return;
+    }
+  }
   float T = 1.0f;
   float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
   for (int base = 0; base < a.N; base += 32) {

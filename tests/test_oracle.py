@@ -207,3 +207,32 @@ def test_training_mode_forward_vs_reference_golden(state_dict):
         assert np.abs(jit[k] - g["jitter_only_" + k]).max() < 1e-5, k
     # the noise matters: the two goldens differ by far more than the tolerance
     assert np.abs(g["acc_map"] - g["jitter_only_acc_map"]).max() > 0.05
+
+
+def test_compositor_and_jitter_properties():
+    """Size-independent properties of the oracle's sampling / compositing restatement (utils/pts_utils.py:3-16,
+    utils/nerf_net_utils.py:5-56) on random inputs: weights in [0,1] with sum <= 1 (+ rounding), colour inside the convex
+    hull scaled by acc, zero density => exactly zero weight and NaN disparity, jittered z sorted and inside [near, far]."""
+    rng = np.random.RandomState(5)
+    R, N = 257, 37
+    z = np.sort(rng.rand(R, N).astype(np.float32) * 2 + 2, axis=1)
+    rd = rng.randn(R, 3).astype(np.float32)
+    rgb = rng.rand(R, N, 3).astype(np.float32)
+    sig = (rng.randn(R, N) * 30).astype(np.float32)
+    out = O.raw2outputs(rgb, sig, z, rd)
+    w = out["weights"]
+    assert w.min() >= 0 and w.max() <= 1 and (w.sum(1) <= 1 + 1e-5).all()
+    assert np.all(w[sig <= 0] == 0)                                    # relu(sigma) = 0 => alpha exactly 0
+    assert np.all(out["color"] <= out["acc_map"][:, None] * 1.00001 + 1e-6)  # colours in [0,1] => rgb_map <= acc
+    assert np.all((out["depth_map"] >= out["acc_map"] * z[:, 0] * 0.99999) & (out["depth_map"] <= out["acc_map"] * z[:, -1] * 1.00001))
+    dead = O.raw2outputs(rgb, -np.abs(sig), z, rd)
+    assert np.all(dead["weights"] == 0) and np.all(dead["acc_map"] == 0) and np.isnan(dead["disp_map"]).all()
+    near = (rng.rand(R).astype(np.float32) + 2)
+    far = near + rng.rand(R).astype(np.float32) + np.float32(0.1)
+    t = rng.rand(R, N).astype(np.float32)
+    o = np.zeros((R, 3), np.float32)
+    _, zj = O.uniform_sampling(o, rd, N, near, far, t)
+    _, z0 = O.uniform_sampling(o, rd, N, near, far)
+    assert np.all(np.diff(zj, axis=1) >= 0) and np.all(zj >= near[:, None]) and np.all(zj <= far[:, None])
+    _, zlo = O.uniform_sampling(o, rd, N, near, far, np.zeros_like(t))   # t_rand = 0 picks the lower interval ends
+    assert np.array_equal(zlo[:, 0], z0[:, 0]) and np.all(zlo[:, 1:] <= z0[:, 1:])

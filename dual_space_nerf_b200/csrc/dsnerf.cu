@@ -277,10 +277,12 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
   CKL("jfa_pass");
   std::swap(sa, sb);
   g.enum_seed = sa;
-  mg.launches = 4 + 1 + 1 + 1 + 1;  // centroid/count/scan/fill, jfa_init, final jfa pass, enum_far (+ normal_matrix for the posed mesh)
+  mg.launches = 4 + 1 + 1 + 2 + 1;  // centroid/count/scan/fill, jfa_init, final jfa pass, 2 x enum_far (+ normal_matrix for the posed mesh)
   for (int step = top; step >= 1; step >>= 1) ++mg.launches;
   // enumeration cells provably farther than r_cap from every centroid (never requested, never searched)
-  enum_far_kernel<<<cb, 256, 0, st>>>(g, (int)ceil(r_cap / cell) + 2, mg.efar.as<unsigned char>());
+  enum_far_rows_kernel<<<cb, 256, 0, st>>>(g, (int)ceil(r_cap / cell) + 2, sb);  // (sb: the jump-flooding buffer that does not hold the seeds)
+  CKL("enum_far_rows");
+  enum_far_kernel<<<cb, 256, 0, st>>>(g, (int)ceil(r_cap / cell) + 2, sb, mg.efar.as<unsigned char>());
   CKL("enum_far");
   return 0;
 }

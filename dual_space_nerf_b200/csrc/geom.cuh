@@ -261,29 +261,40 @@ __global__ void jfa_pass_kernel(Grid g, int step, const int* __restrict__ in, in
 // least max(0, |A_k - B_k| - 1) cells, so cell^2 * min_B sum_k max(0, |A_k - B_k| - 1)^2 > r_cap^2 proves that every point of
 // A is farther than r_cap from all centroids (=> transparent, see transparency_radius).  Rows are searched through the
 // occupancy words (nearest set bit on either side of the cell's x).
-__global__ void enum_far_kernel(Grid g, int window, unsigned char* __restrict__ out) {
+// The minimum separates: pass 1 takes, per cell, the minimum over the rows y' of its z slab of gx^2 + gy^2 (window rows), pass
+// 2 the minimum over the slabs z' of that plus gz^2 -- 2 x 13 steps per cell instead of 13 x 13, same integers.
+__global__ void enum_far_rows_kernel(Grid g, int window, int* __restrict__ tmp) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= g.nx * g.ny * g.nz) return;
   int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+  int best = 1 << 28;
+  for (int y = max(0, cy - window); y <= min(g.ny - 1, cy + window); ++y) {
+    unsigned long long m = __ldg(g.row_mask + cz * g.ny + y);
+    if (!m) continue;
+    int gy = max(0, abs(y - cy) - 1);
+    // nearest set bit at or below cx, and at or above cx
+    unsigned long long lo = m & (cx >= 63 ? ~0ull : ((2ull << cx) - 1ull)), hi = m & (~0ull << cx);
+    int dx = 1 << 12;
+    if (lo) dx = min(dx, cx - (63 - __clzll((long long)lo)));
+    if (hi) dx = min(dx, (__ffsll((long long)hi) - 1) - cx);
+    int gx = max(0, dx - 1);
+    best = min(best, gx * gx + gy * gy);
+  }
+  tmp[c] = best;
+}
+__global__ void enum_far_kernel(Grid g, int window, const int* __restrict__ tmp, unsigned char* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.nx * g.ny * g.nz) return;
+  int cz = c / (g.nx * g.ny);
+  const int plane = g.nx * g.ny;
   const float need = (g.r_cap * 1.0002f + 1e-5f) * g.inv_cell;
   const float need2 = need * need;
-  bool far = true;
-  for (int z = max(0, cz - window); z <= min(g.nz - 1, cz + window) && far; ++z) {
+  int best = 1 << 28;
+  for (int z = max(0, cz - window); z <= min(g.nz - 1, cz + window); ++z) {
     int gz = max(0, abs(z - cz) - 1);
-    for (int y = max(0, cy - window); y <= min(g.ny - 1, cy + window); ++y) {
-      unsigned long long m = __ldg(g.row_mask + z * g.ny + y);
-      if (!m) continue;
-      int gy = max(0, abs(y - cy) - 1);
-      // nearest set bit at or below cx, and at or above cx
-      unsigned long long lo = m & (cx >= 63 ? ~0ull : ((2ull << cx) - 1ull)), hi = m & (~0ull << cx);
-      int dx = 1 << 20;
-      if (lo) dx = min(dx, cx - (63 - __clzll((long long)lo)));
-      if (hi) dx = min(dx, (__ffsll((long long)hi) - 1) - cx);
-      int gx = max(0, dx - 1);
-      if ((float)(gx * gx + gy * gy + gz * gz) <= need2) { far = false; break; }
-    }
+    best = min(best, __ldg(tmp + c + (z - cz) * plane) + gz * gz);
   }
-  out[c] = far ? 1 : 0;
+  out[c] = ((float)best <= need2) ? 0 : 1;
 }
 
 // ---- lazy lookup table -----------------------------------------------------------------------

@@ -78,6 +78,10 @@ def make_rounder(scheme):
             return xh @ wh + fp8_mx(xh, 1) @ fp8_mx(wl, 0) + fp8_mx(xl, 1) @ fp8_mx(wh, 0)
         if scheme == "fp8corr_mx_merged":                   # one fp8 GEMM with K doubled: [xh | xl] . [wl ; wh]
             return xh @ wh + np.concatenate([fp8_mx(xh, 1), fp8_mx(xl, 1)], 1) @ np.concatenate([fp8_mx(wl, 0), fp8_mx(wh, 0)], 0)
+        if scheme == "hl8_lh16":                            # x_hi.w_lo in MX fp8, x_lo.w_hi in fp16 (2.5 pass-equivalents)
+            return xh @ wh + fp8_mx(xh, 1) @ fp8_mx(wl, 0) + h16(xl) @ wh
+        if scheme == "hl16_lh8":                            # x_hi.w_lo in fp16, x_lo.w_hi in MX fp8
+            return xh @ wh + xh @ h16(wl) + fp8_mx(xl, 1) @ fp8_mx(wh, 0)
         raise SystemExit(f"unknown scheme {scheme}")
     return r
 

@@ -26,6 +26,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # the reference arm is a CPU run on ALL host cores whatever the launcher exported: torchrun sets OMP_NUM_THREADS=1 for
+    # its workers, which would otherwise throttle OpenBLAS / OpenMP here (must happen before numpy loads OpenBLAS)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -102,8 +108,10 @@ class ClockSampler:
                 "source": f"nvidia-smi --query-gpu -lms {self.period_ms} child process running across the timed region"}
 
 
-def cpu_port(rays_per_step, steps, warmup, sc=None, sd=None):
-    """Time the oracle (CPU restatement of the reference) on a bounded slice of the 512x512x64 frame."""
+def cpu_port(rays_per_step, steps, warmup, sc=None, sd=None, novel_pose=False, keep=False):
+    """Time the oracle (CPU restatement of the reference) on a bounded slice of the 512x512x64 frame.  ``novel_pose``: the
+    config-5 switches (nerf.w = 0, set_light_center, test.py:193-196).  ``keep``: also return (ray indices, outputs) of the
+    timed slices, which bench.py compares with the GPU frame (`parity`)."""
     import torch
 
     from dual_space_nerf_b200 import net as N
@@ -115,23 +123,65 @@ def cpu_port(rays_per_step, steps, warmup, sc=None, sd=None):
     sd = sd or N.synthetic_net(0).state_dict()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    orc = O.Oracle(sd, sc["canonical"], sc["faces"], N_SAMPLES)
+    try:  # OpenBLAS (numpy) and libgomp (oracle/geom.c) at run time, whatever OMP_NUM_THREADS the launcher exported
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    kw = dict(zero_code=True, light_center=S.LIGHT_CENTER_313) if novel_pose else {}
+    orc = O.Oracle(sd, sc["canonical"], sc["faces"], N_SAMPLES, **kw)
     # contiguous scanlines through the middle of the frame (hit and miss rays in the frame's proportion)
     r0 = (H // 2) * W
-    times = []
+    times, kept = [], []
     for s in range(warmup + steps):
         sel = slice(r0 + s * rays_per_step, r0 + (s + 1) * rays_per_step)
         t = time.perf_counter()
-        orc.render(sc["ray_o"][sel], sc["ray_d"][sel], sc["near"][sel], sc["far"][sel], sc["posed"], sc["poses"], sc["frame"])
+        out = orc.render(sc["ray_o"][sel], sc["ray_d"][sel], sc["near"][sel], sc["far"][sel], sc["posed"], sc["poses"], sc["frame"], Th=sc["Th"])
         if s >= warmup:
             times.append(time.perf_counter() - t)
+        if keep:
+            kept.append((np.arange(sel.start, sel.stop), out))
     sec = float(np.sum(times))
-    return {
+    res = {
         "value": rays_per_step * steps / sec, "unit": "rays/s", "cores": int(max(cores, clib.lib().dso_num_threads())), "kind": "port",
         "sample": f"{steps} x {rays_per_step}-ray scanline slices of the 512x512x64 frame (numpy/OpenBLAS MLP + OpenMP C "
                   f"brute-force nearest triangle, fp32), {sec:.1f} s",
         "seconds": sec,
     }
+    if keep:
+        res["kept"] = kept
+        res["oracle"] = orc
+    return res
+
+
+def parity_vs_oracle(frame, res, sc):
+    """GPU frame (dict of host arrays over all H*W rays) against the oracle outputs `cpu_port(keep=True)` produced: north_star's
+    tolerance is 1e-4 max-abs on rgb and depth.  A ray over the rgb bound is re-run through the oracle with its ReLU-kink
+    margin: `kink_rays` of them contain a sample within rounding distance of a ReLU kink of the density
+    gradient, where any two fp32 implementations may disagree; `rays_over_tol_unexplained` must be 0."""
+    KINK_MARGIN, TOL = 2e-6, 1e-4
+    idx = np.concatenate([k[0] for k in res["kept"]])
+    ref = {k: np.concatenate([o[1][k] for o in res["kept"]]) for k in ("color", "depth_map", "acc_map", "disp_map")}
+    col = np.abs(frame["color"][idx] - ref["color"]).max(1)
+    dep = np.abs(frame["depth_map"][idx] - ref["depth_map"])
+    acc = np.abs(frame["acc_map"][idx] - ref["acc_map"])
+    over = np.nonzero(col > TOL)[0]
+    kink = 0
+    if len(over):
+        st = {}
+        sel = idx[over]
+        res["oracle"].render(sc["ray_o"][sel], sc["ray_d"][sel], sc["near"][sel], sc["far"][sel], sc["posed"], sc["poses"], sc["frame"],
+                             Th=sc["Th"], stages=st)
+        is_kink = (st["kink_margin"] < KINK_MARGIN).reshape(len(sel), -1).any(1)
+        kink = int(is_kink.sum())
+    hit = ref["acc_map"] > 0
+    return {"rays_compared": int(len(idx)), "rays_hit": int(hit.sum()), "max_abs_rgb": float(col.max()), "max_abs_depth": float(dep.max()),
+            "max_abs_acc": float(acc.max()), "tol": TOL, "rays_over_tol": int(len(over)), "kink_rays": kink,
+            "rays_over_tol_unexplained": int(len(over) - kink),
+            "max_abs_rgb_within_tol_rays": float(col[col <= TOL].max()) if (col <= TOL).any() else None,
+            "disp_nan_pattern_equal": bool(np.array_equal(np.isnan(frame["disp_map"][idx]), np.isnan(ref["disp_map"]))),
+            "against": "oracle/ (CPU restatement pinned to the reference) on the same rays / pose / weights, 512x512x64"}
 
 
 def run_reference_arm(args):
@@ -155,14 +205,244 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+class Rig:
+    """One context per rank with the synthetic weights and mesh staged; thin helpers around the C ABI."""
+
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+
+        from dual_space_nerf_b200 import lib
+        from dual_space_nerf_b200 import net as N
+
+        self.torch, self.lib, self.args = torch, lib, args
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", local_rank)
+        self.net = N.synthetic_net(0)
+        self.sd = self.net.state_dict()
+        self.ctx = lib.Context(local_rank)
+        self.L = self.ctx.L
+        arrs = [np.ascontiguousarray(self.sd[k].detach().numpy(), dtype=np.float32) for k in N.STATE_DICT_ORDER]
+        ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs])
+        self.ctx.check(self.L.dsnerf_set_weights(self.ctx.h, ptrs, len(arrs)))
+        self.flags = lib.SAMPLE_GG | (lib.MLP_FP32_SIMT if args.simt else 0) | (lib.EARLY_STOP if args.early_stop else 0)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.sp = ctypes.c_void_p(self.stream.cuda_stream)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.mesh_of = None
+
+    def set_mesh(self, sc):
+        if self.mesh_of is sc:
+            return
+        faces = np.ascontiguousarray(sc["faces"], dtype=np.int32)
+        self.ctx.check(self.L.dsnerf_set_mesh(self.ctx.h, faces.ctypes.data_as(ctypes.c_void_p), faces.shape[0],
+                                              sc["canonical"].ctypes.data_as(ctypes.c_void_p), sc["canonical"].shape[0]))
+        self.mesh_of = sc
+
+    def frame_setter(self, sc, novel_pose):
+        """dsnerf_set_frame for this scene; novel_pose = config 5's switches: nerf.w = 0 (zero latent code) and
+        set_light_center(313.yml) => xyz_world += light_center - mean(Th) (test.py:193-196, model/spacenet.py:260-263)."""
+        from dual_space_nerf_b200 import scene as S
+
+        posed = np.ascontiguousarray(sc["posed"])
+        poses = np.ascontiguousarray(sc["poses"])
+        shift = (S.LIGHT_CENTER_313 - sc["Th"].reshape(-1, 3).mean(0)).astype(np.float32) if novel_pose else None
+        sp_ = None if shift is None else shift.ctypes.data_as(ctypes.c_void_p)
+
+        def set_frame():
+            self.ctx.check(self.L.dsnerf_set_frame(self.ctx.h, posed.ctypes.data_as(ctypes.c_void_p), poses.ctypes.data_as(ctypes.c_void_p),
+                                                   sc["frame"], 1 if novel_pose else 0, sp_, None, None, self.sp))
+
+        set_frame.keep = (posed, poses, shift)
+        set_frame.h2d_bytes = posed.nbytes + 256 * 4
+        return set_frame
+
+    def barrier(self):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        import torch.distributed as dist
+
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def bench_strong(rig, steps, warmup):
+    """BASELINE configs[3]: ONE 1024x1024x64 frame, its rays sharded over the ranks (image rows dealt round-robin, so every
+    rank gets the same mix of hit and miss rays), every rank runs the identical path on its rows and one NCCL all-gather of
+    6 floats per ray reassembles the frame on every rank.  Strong scaling: the same frame is also timed unsharded on one GPU."""
+    import torch
+    import torch.distributed as dist
+
+    from dual_space_nerf_b200 import dist as D
+    from dual_space_nerf_b200 import scene as S
+
+    H4 = W4 = 1024
+    R4 = H4 * W4
+    world, rank, dev, L, ctx = rig.world, rig.rank, rig.dev, rig.L, rig.ctx
+    sc = S.make_scene(H4, W4)
+    rig.set_mesh(sc)
+    set_frame = rig.frame_setter(sc, False)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    full_in = [t(sc[k]) for k in ("ray_o", "ray_d", "near", "far")]
+    sel = D.interleaved_indices(R4, rank, world, W4).to(dev)
+    mine = [x[sel].contiguous() for x in full_in]
+    Rl = int(sel.numel())
+    out_l = torch.empty(6 * Rl, device=dev)
+    gathered = torch.empty(world, 6 * Rl, device=dev)
+    frame = torch.empty(6 * R4, device=dev)
+    out_1 = torch.empty(6 * R4, device=dev)
+
+    def views(buf, R):
+        return buf[: 3 * R].view(R, 3), buf[3 * R: 4 * R], buf[4 * R: 5 * R], buf[5 * R:]
+
+    def render(inp, R, buf):
+        rgb, dep, acc, dsp = views(buf, R)
+        ctx.check(L.dsnerf_render(ctx.h, P(inp[0]), P(inp[1]), P(inp[2]), P(inp[3]), R, N_SAMPLES, rig.flags, P(rgb), P(dep), P(acc), P(dsp),
+                                  None, None, rig.sp))
+
+    nblk = Rl // W4
+
+    def step_sharded():
+        set_frame()
+        render(mine, Rl, out_l)
+        dist.all_gather_into_tensor(gathered, out_l)
+        # rows back into image order: (world, rows per rank, W, c) -> (rows per rank, world, W, c)
+        for (src_lo, c), dst in zip(((0, 3), (3 * Rl, 1), (4 * Rl, 1), (5 * Rl, 1)), views(frame, R4)):
+            dst.view(nblk, world, W4, c).copy_(gathered[:, src_lo: src_lo + c * Rl].view(world, nblk, W4, c).transpose(0, 1))
+
+    def step_single():
+        set_frame()
+        render(full_in, R4, out_1)
+
+    def timed(step):
+        for _ in range(warmup):
+            step()
+        rig.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(rig.stream)
+        for _ in range(steps):
+            rig.flush.fill_(1)
+            step()
+        e1.record(rig.stream)
+        rig.barrier()
+        return rig.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    ms_1 = timed(step_single)      # every rank renders the whole frame on its own GPU at the same time (max over ranks)
+    ev1 = ctx.stats()["evaluated_samples"]
+    ms_n = timed(step_sharded)
+    ev_l = ctx.stats()["evaluated_samples"]
+    ev = torch.tensor([float(ev_l)], device=dev, dtype=torch.float64)
+    gl = [torch.zeros_like(ev) for _ in range(world)]
+    dist.all_gather(gl, ev)
+    per_rank = [int(x.item()) for x in gl]
+    same = bool(torch.equal(frame.nan_to_num(-1.0), out_1.nan_to_num(-1.0)))
+    flag = torch.tensor([1 if same else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {
+        "workload": "BASELINE configs[3] shape: one 1024x1024 = 1048576-ray frame, 64 samples/ray, rays sharded over the ranks "
+                    "(image rows round-robin) + one NCCL all-gather of 6 floats/ray (25 MB) + row re-ordering, inside the timed region",
+        "rays_s": R4 / (ms_n * 1e-3), "ms": ms_n, "ms_1gpu": ms_1, "rays_s_1gpu": R4 / (ms_1 * 1e-3), "speedup_vs_1gpu": ms_1 / ms_n,
+        "efficiency_vs_1gpu": ms_1 / ms_n / world, "bit_identical": bool(flag.item()), "steps": steps,
+        "evaluated_samples_per_rank": per_rank, "evaluated_samples_1gpu": int(ev1),
+        "replicated_per_rank": "dsnerf_set_frame: posed-mesh upload, grid + lookup-table build (every rank needs the whole body)",
+    }
+
+
+def bench_config3(rig, args, sc):
+    """BASELINE configs[2]: 512x512, hierarchical 64 coarse + 128 importance samples (own spec): coarse pass with
+    weights / z_vals outputs -> dsnerf_resample -> 192-sample second pass (dsnerf_render_z), per frame."""
+    torch, ctx, L, dev = rig.torch, rig.ctx, rig.L, rig.dev
+    R, n, n_imp = H * W, N_SAMPLES, 128
+    set_frame = rig.frame_setter(sc, False)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_o, d_d, d_n, d_f = (t(sc[k]) for k in ("ray_o", "ray_d", "near", "far"))
+    mk = lambda *s_: torch.empty(*s_, device=dev)
+    c_rgb, c_dep, c_acc, c_dsp, c_w, c_z = mk(R, 3), mk(R), mk(R), mk(R), mk(R, n), mk(R, n)
+    z2, f_rgb, f_dep, f_acc, f_dsp = mk(R, n + n_imp), mk(R, 3), mk(R), mk(R), mk(R)
+    counts = {}
+
+    def step(sync=False):
+        set_frame()
+        ctx.check(L.dsnerf_render(ctx.h, P(d_o), P(d_d), P(d_n), P(d_f), R, n, rig.flags, P(c_rgb), P(c_dep), P(c_acc), P(c_dsp), P(c_w),
+                                  P(c_z), rig.sp))
+        if sync:
+            counts["coarse"] = ctx.stats()["evaluated_samples"]
+        ctx.check(L.dsnerf_resample(ctx.h, P(c_z), P(c_w), R, n, n_imp, P(z2), rig.sp))
+        ctx.check(L.dsnerf_render_z(ctx.h, P(d_o), P(d_d), P(z2), R, n + n_imp, rig.flags, P(f_rgb), P(f_dep), P(f_acc), P(f_dsp), None, rig.sp))
+        if sync:
+            counts["fine"] = ctx.stats()["evaluated_samples"]
+
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        step(sync=True)
+    launches = ctx.stats()["kernel_launches"]
+    ctx.profile(1)
+    ctx.profile_read(reset=True)
+    rig.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(rig.stream)
+    for _ in range(args.steps):
+        rig.flush.fill_(1)
+        step()
+    e1.record(rig.stream)
+    rig.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    mlp_ms, mlp_n = ctx.profile_read(reset=True)
+    ctx.profile(0)
+    sustained, burst, hbm, src = peaks()
+    evaluated = counts["coarse"] + counts["fine"]
+    mlp_per_frame = mlp_ms / args.steps
+    achieved = evaluated * FLOP_PER_SAMPLE / (mlp_per_frame * 1e-3) / 1e12
+    return {
+        "metric": "rays/sec (512x512, hierarchical 64 coarse + 128 importance samples/ray)", "value": R / (ms * 1e-3), "unit": "rays/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16x3-split operands, f32 accumulate (tcgen05)", "data": "synthetic",
+        "config": {"workload": "ZJU-Mocap 313 shape with hierarchical sampling (configs[2]): 512x512 rays, 64-sample coarse pass + "
+                               "sample_pdf(128) -> 192-sample second pass of the same net (own spec: the reference's resampling is undefined, "
+                               "can_render.py:213)",
+                   "evaluated_samples_coarse": int(counts["coarse"]), "evaluated_samples_fine": int(counts["fine"]),
+                   "nominal_samples": R * (2 * n + n_imp), "l2": "256 MB buffer written between timed steps (L2 flush)"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
+                     "kernel": "mlp_tc_kernel (2 launches per frame)", "kernel_ms_per_frame": mlp_per_frame,
+                     "kernel_share_of_step": mlp_per_frame / ms, "peak_source": f"bf16_tflops_sustained of {src} (MEASURED_PEAKS.json)"},
+        "gpu_launches": None if launches is None else int((launches + 1 + launches) * args.steps),
+    }
+
+
+def dram_traffic():
+    """DRAM bytes per launch of the MLP kernel and per frame over all kernels, from the committed ncu capture of this very
+    command (profiles/r02_dram_bytes.json, written by tools/dram_summary.py from `ncu --metrics dram__bytes_*` launch lists):
+    ncu cannot run inside a timed benchmark, so this is the measured figure of the same build, not a live one."""
+    for name in ("r02_dram_bytes.json", "mlp_dram_bytes.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            with open(tp) as f:
+                d = json.load(f)
+            return d.get("dram_bytes_per_launch"), d.get("dram_bytes_per_frame"), "profiles/" + name
+    return None, None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="2 = headline (512x512x64; with --gpus N > 1: config 5 weak + "
+                    "config 4 strong); 3 = hierarchical 64 + 128 (1 GPU, secondary line)")
     ap.add_argument("--simt", action="store_true", help="debug: fp32 SIMT MLP kernel instead of tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the config-4 strong-scaling measurement")
     ap.add_argument("--early-stop", action="store_true", help="optional DSNERF_EARLY_STOP mode (not the headline: the default evaluates every sample)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -173,8 +453,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from dual_space_nerf_b200 import lib
-    from dual_space_nerf_b200 import net as N
     from dual_space_nerf_b200 import scene as S
 
     rank = int(os.environ.get("RANK", 0))
@@ -188,53 +466,50 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     warmup = max(args.warmup, 3)
-    sc = S.make_scene(H, W, pose_seed=rank)  # config 5 for N > 1: one novel-pose frame per GPU
-    net = N.synthetic_net(0)
-    sd = net.state_dict()
+    novel = world > 1   # config 5 (N > 1): one novel-pose frame per GPU, pose seed = rank, nerf.w = 0 + light_center
+    sc = S.make_scene(H, W, pose_seed=rank)
     R = H * W
-    ctx = lib.Context(local_rank)
-    L = ctx.L
-    arrs = [np.ascontiguousarray(sd[k].detach().numpy(), dtype=np.float32) for k in N.STATE_DICT_ORDER]
-    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs])
-    ctx.check(L.dsnerf_set_weights(ctx.h, ptrs, len(arrs)))
-    faces = np.ascontiguousarray(sc["faces"], dtype=np.int32)
-    ctx.check(L.dsnerf_set_mesh(ctx.h, faces.ctypes.data_as(ctypes.c_void_p), faces.shape[0],
-                                sc["canonical"].ctypes.data_as(ctypes.c_void_p), sc["canonical"].shape[0]))
-    flags = lib.SAMPLE_GG | (lib.MLP_FP32_SIMT if args.simt else 0) | (lib.EARLY_STOP if args.early_stop else 0)
-    stream = torch.cuda.current_stream(dev)
-    sp = ctypes.c_void_p(stream.cuda_stream)
-    P = lambda t: ctypes.c_void_p(t.data_ptr())
-    posed = np.ascontiguousarray(sc["posed"])
-    poses = np.ascontiguousarray(sc["poses"])
-
-    def set_frame():
-        ctx.check(L.dsnerf_set_frame(ctx.h, posed.ctypes.data_as(ctypes.c_void_p), poses.ctypes.data_as(ctypes.c_void_p),
-                                     sc["frame"], 0, None, None, None, sp))
+    rig = Rig(args, rank, local_rank, world)
+    ctx, L, sp, stream, flags, flush = rig.ctx, rig.L, rig.sp, rig.stream, rig.flags, rig.flush
+    rig.set_mesh(sc)
+    if args.config == 3:
+        if world > 1:
+            raise SystemExit("--config 3 is a 1-GPU measurement")
+        print(json.dumps(bench_config3(rig, args, sc)))
+        return
+    set_frame = rig.frame_setter(sc, novel)
 
     # ---- device-resident arm ("value"): inputs already in HBM, outputs stay in HBM
     d_o, d_d = torch.from_numpy(sc["ray_o"]).to(dev), torch.from_numpy(sc["ray_d"]).to(dev)
     d_n, d_f = torch.from_numpy(sc["near"]).to(dev), torch.from_numpy(sc["far"]).to(dev)
     # one flat block per rank, [rgb (R,3) | depth (R) | acc (R) | disp (R)]: the compositor writes straight into it and a single
-    # all-gather (6 floats per ray) reassembles every rank's frame on every rank
-    out = torch.empty(6 * R, device=dev)
-    o_rgb, o_dep, o_acc, o_dsp = out[: 3 * R].view(R, 3), out[3 * R: 4 * R], out[4 * R: 5 * R], out[5 * R:]
-    gathered = torch.empty(world, 6 * R, device=dev) if world > 1 else None
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # all-gather (6 floats per ray) reassembles every rank's frame on every rank.  The gather of frame k runs on NCCL's stream
+    # against double-buffered blocks while the compute stream renders frame k + 1: the collective is off the critical path.
+    outs = [torch.empty(6 * R, device=dev) for _ in range(2)]
+    gathered = [torch.empty(world, 6 * R, device=dev) for _ in range(2)] if world > 1 else None
+    works = [None, None]
 
-    def step_device():
+    def step_device(i):
+        k = i & 1
+        if works[k] is not None:   # the block is about to be overwritten: its previous gather (two frames ago) must be done
+            works[k].wait()
+            works[k] = None
+        out = outs[k]
         set_frame()
-        ctx.check(L.dsnerf_render(ctx.h, P(d_o), P(d_d), P(d_n), P(d_f), R, N_SAMPLES, flags, P(o_rgb), P(o_dep), P(o_acc),
-                                  P(o_dsp), None, None, sp))
+        ctx.check(L.dsnerf_render(ctx.h, P(d_o), P(d_d), P(d_n), P(d_f), R, N_SAMPLES, flags, P(out[: 3 * R]), P(out[3 * R: 4 * R]),
+                                  P(out[4 * R: 5 * R]), P(out[5 * R:]), None, None, sp))
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            works[k] = dist.all_gather_into_tensor(gathered[k], out, async_op=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def drain():
+        for k in range(2):
+            if works[k] is not None:
+                works[k].wait()
+                works[k] = None
 
-    for _ in range(warmup):
-        step_device()
+    for i in range(warmup):
+        step_device(i)
+    drain()
     torch.cuda.synchronize()
     st = ctx.stats()
     launches_per_step = st["kernel_launches"] + 1  # render + per-frame grid build (counted by the library) + the clock probe
@@ -247,15 +522,16 @@ def main():
     # 30-100 ms on this driver (ms_per_step 13.8 -> 23..88 ms); throttle reasons and power are sampled during an identical,
     # untimed repeat of the region right after it.
     d_clk = torch.zeros(args.steps, 2, device=dev)
-    barrier()
+    rig.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (inside the bracket: ~0.1 ms of 256 MB writes per step)
-        step_device()
+        step_device(i)
         ctx.check(L.dsnerf_debug_sm_clock(ctx.h, ctypes.c_void_p(d_clk.data_ptr() + 8 * i), sp))
+    drain()             # every frame's all-gather completes inside the timed region
     e1.record(stream)
-    barrier()
+    rig.barrier()
     ms_total = e0.elapsed_time(e1)
     mlp_ms, mlp_n = ctx.profile_read(reset=True)
     ctx.profile(0)
@@ -266,10 +542,13 @@ def main():
         time.sleep(0.4)
         sampler.mark(0)
         t_rep = time.time()
+        i = 0
         while time.time() - t_rep < 1.0:  # identical load, untimed, long enough for several samples
             flush.fill_(1)
-            step_device()
+            step_device(i)
+            i += 1
             torch.cuda.synchronize()
+        drain()
         sampler.mark(1)
     clocks = sampler.stop()
     clocks["sm_mhz_nvidia_smi_repeat"] = clocks.get("sm_mhz")
@@ -277,10 +556,7 @@ def main():
     clocks["sm_mhz_min"] = float(probe[:, 0].min())
     clocks["source"] = ("sm_mhz: clock64/globaltimer probe kernel after every timed step (inside the timed region); reasons, power, "
                         "sm_max_mhz: " + str(clocks.get("source")) + " during an untimed repeat of the same loop")
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = rig.max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
     value = world * R * args.steps / (ms_total * 1e-3)
 
@@ -297,41 +573,43 @@ def main():
 
     for _ in range(2):
         step_e2e()
-    barrier()
+    rig.barrier()
     e0.record(stream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)
         step_e2e()
     e1.record(stream)
-    barrier()
+    rig.barrier()
     wall = time.perf_counter() - t0
-    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = rig.max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
     e2e_value = world * R * args.steps / (e2e_ms * 1e-3)
     frame_checksum = float(h_rgb.double().sum())
+    # the e2e frame must be the device-resident frame, bit for bit
+    e2e_same = bool(torch.equal(h_rgb.to(dev), outs[0][: 3 * R].view(R, 3)))
+
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = bench_strong(rig, min(args.steps, 10), 3)
 
     if rank == 0:
         sustained, burst, hbm, src = peaks()
         achieved = (evaluated * FLOP_PER_SAMPLE) / (mlp_ms / max(mlp_n, 1) * 1e-3) / 1e12 if mlp_ms > 0 else None
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "mlp_dram_bytes.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+        traffic, traffic_frame, traffic_src = dram_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.simt else "f16x3-split operands, f32 accumulate (tcgen05)", "data": "synthetic",
             "config": {
-                "workload": "ZJU-Mocap 313 config shape (configs[1]): 512x512 = 262144 rays, 64 samples/ray, GG sampling, "
-                            "random-init SpaceNet (head rescale of SURVEY.md 8d), synthetic SMPL-sized mesh (V=6890, F=13776)",
+                "workload": ("novel-pose batch (configs[4]): one 512x512 = 262144-ray frame per GPU (pose seed = rank), 64 samples/ray, nerf.w = 0 + "
+                             "light_center of 313.yml (test.py:193-196), " if world > 1 else
+                             "ZJU-Mocap 313 config shape (configs[1]): 512x512 = 262144 rays, 64 samples/ray, ") +
+                            "GG sampling, random-init SpaceNet (head rescale of SURVEY.md 8d), synthetic SMPL-sized mesh (V=6890, F=13776)",
                 "rays_per_gpu_per_step": R, "samples_per_ray": N_SAMPLES, "evaluated_samples_per_step": int(evaluated),
                 "evaluated_fraction": evaluated / float(R * N_SAMPLES),
-                "parallelism": f"{world} x (one frame per GPU) + NCCL all-gather of 6 floats/ray" if world > 1 else "1 GPU",
+                "parallelism": (f"{world} x (one frame per GPU) + NCCL all-gather of 6 floats/ray per frame, issued asynchronously "
+                                "against double-buffered output blocks (frame k's gather overlaps frame k+1; all gathers complete inside the timed region)")
+                if world > 1 else "1 GPU",
                 "l2": "256 MB buffer written between timed steps (L2 flush)",
                 "mlp_kernel": "fp32 SIMT (debug)" if args.simt else "tcgen05",
                 "early_stop": bool(args.early_stop),
@@ -342,20 +620,30 @@ def main():
                 "kernel": "mlp_simt_kernel" if args.simt else "mlp_tc_kernel", "kernel_ms_per_launch": mlp_ms / max(mlp_n, 1),
                 "kernel_share_of_step": (mlp_ms / max(mlp_n, 1)) / ms_step, "peak_source": f"bf16_tflops_sustained of {src} (MEASURED_PEAKS.json)",
                 "algorithmic_flop_per_launch": evaluated * FLOP_PER_SAMPLE,
+                "whole_step_frac": (evaluated * FLOP_PER_SAMPLE) / (ms_step * 1e-3) / 1e12 / sustained,
                 # the 1e-4 parity bound forces three fp16 MMAs per forward k-step: the tensor pipe executes
                 # 1 734 656 MAC per sample for 902 272 algorithmic ones; reported alongside, never instead
                 "executed_tensor_tflops": None if (achieved is None or args.simt) else achieved * (1734656.0 / 902272.0),
                 "executed_frac_of_peak": None if (achieved is None or args.simt) else achieved * (1734656.0 / 902272.0) / sustained,
+                "traffic_all_kernels_per_frame": traffic_frame, "traffic_algorithmic_per_frame": 56 * R, "traffic_source": traffic_src,
             },
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * 8 * 4 + posed.nbytes + 256 * 4,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * 8 * 4 + set_frame.h2d_bytes,
                     "d2h_bytes_per_step": R * 6 * 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": "dsnerf_set_frame + dsnerf_render_host (C ABI, pinned host buffers)", "rgb_checksum": frame_checksum},
+                    "api": "dsnerf_set_frame + dsnerf_render_host (C ABI, pinned host buffers)", "rgb_checksum": frame_checksum,
+                    "bit_identical_to_device_arm": e2e_same},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }
+        if strong is not None:
+            line["strong"] = strong
+        # parity at the benchmark's own size, every run: the frame the e2e arm has just produced against the oracle on
+        # 3 x 8192 rays of it.  The same oracle calls are the `cpu_baseline` timing at N = 1 (rank 0 only).
         if not args.no_cpu_baseline:
-            res = cpu_port(8192, 3, 1, sc=S.make_scene(H, W), sd=sd)
-            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            res = cpu_port(8192, 3, 1, sc=sc, sd=rig.sd, novel_pose=novel, keep=True)
+            if world == 1:
+                line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            frame = {"color": h_rgb.numpy(), "depth_map": h_dep.numpy(), "acc_map": h_acc.numpy(), "disp_map": h_dsp.numpy()}
+            line["parity"] = parity_vs_oracle(frame, res, sc)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -377,7 +377,7 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
   const float4* active = list ? list : ctx->active.as<float4>();
   cudaEvent_t a, b;
   profile_begin(ctx, st, &a, &b);
-  if (flags & DSNERF_MLP_FP32_SIMT) {
+  if ((flags & DSNERF_MLP_FP32_SIMT) || !ctx->tw.fp16_ok) {  // weights outside fp16 range: the fp32 kernel is the product path
     mlp_simt_kernel<<<ctx->sm_count, SIMT_THREADS, SIMT_SMEM, st>>>(ctx->sw, active, d_count, host_count,
                                                                     ctx->mlp_a.as<float4>(), ctx->mlp_g.as<float4>(), density_only);
     CKL("mlp_simt");
@@ -387,7 +387,7 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
       if (ctx->tc_timing.ensure(sizeof(long long) * 128) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "timing buffer");
       timing = ctx->tc_timing.as<long long>();
     }
-    if (int e = tc_launch(ctx->tw, timing, (ctx->profile >> 3) & 3, active, d_count, host_count, ctx->mlp_a.as<float4>(),
+    if (int e = tc_launch(ctx->tw, timing, (ctx->profile >> 3) & 3, (ctx->profile >> 6) & 3, active, d_count, host_count, ctx->mlp_a.as<float4>(),
                           ctx->mlp_g.as<float4>(), density_only, ctx->sm_count, st))
       return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc: ") + cudaGetErrorString((cudaError_t)e));
   }
@@ -404,6 +404,7 @@ int check_ready(dsnerf_ctx* ctx, bool need_frame) {
 }
 
 int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStream_t st, int* launches = nullptr) {
+  if (!ctx->tw.fp16_ok) flags |= DSNERF_MLP_FP32_SIMT;
   if (launches) *launches += (flags & DSNERF_MLP_FP32_SIMT) ? 4 : 5;  // mark_points, build<1>, build<2>, (canon_nearest,) lighting
   // canonical-space lookup cells of the active points (static mesh: cells stay built across frames)
   if (int e = ensure_cells(ctx, ctx->g_canon, st, [&] {
@@ -663,12 +664,15 @@ const char* dsnerf_last_error(const dsnerf_ctx* ctx) { return ctx ? ctx->err.c_s
 int dsnerf_set_weights(dsnerf_ctx* ctx, const float* const* t, int n_tensors) {
   if (!ctx) return DSNERF_ERR_INVALID;
   if (!t || n_tensors != DSNERF_NUM_WEIGHT_TENSORS) return fail(ctx, DSNERF_ERR_INVALID, "expected 33 tensors in state_dict order");
+  // validate everything before touching the context: a rejected call leaves the previously staged weights in use
   for (int i = 0; i < n_tensors; ++i) {
     if (!t[i]) return fail(ctx, DSNERF_ERR_INVALID, "null weight tensor");
-    ctx->hw[i].assign(t[i], t[i] + kTensorSize[i]);
-    for (float v : ctx->hw[i])
-      if (!std::isfinite(v)) return fail(ctx, DSNERF_ERR_INVALID, "non-finite weight");
+    for (int j = 0; j < kTensorSize[i]; ++j)
+      if (!std::isfinite(t[i][j])) return fail(ctx, DSNERF_ERR_INVALID, "non-finite weight");
   }
+  for (int i = 0; i < n_tensors; ++i) ctx->hw[i].assign(t[i], t[i] + kTensorSize[i]);
+  ctx->have_weights = false;  // until the staging below has succeeded
+  ctx->have_frame = false;
   CK(cudaSetDevice(ctx->device));
   CK(cudaDeviceSynchronize());  // weights may be in use by work in flight
   BlobBuilder bb;
@@ -1041,6 +1045,33 @@ int dsnerf_camera_rays(dsnerf_ctx* ctx, int H, int W, const double* K, const dou
   return 0;
 }
 
+namespace {
+__global__ void expand_mask_kernel(const unsigned* __restrict__ bits, int64_t P, uint8_t* __restrict__ transparent) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < P) transparent[s] = ((bits[s >> 5] >> (s & 31)) & 1u) ? 0 : 1;
+}
+}  // namespace
+
+int dsnerf_last_transparent_mask(dsnerf_ctx* ctx, int64_t R, int N, uint8_t* transparent, void* stream) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  if (R < 0 || N < 1) return fail(ctx, DSNERF_ERR_INVALID, "bad sizes");
+  if (R == 0) return 0;
+  if (!transparent) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
+  if (ctx->stats.rays != R || ctx->stats.samples != R * (int64_t)N || !ctx->ray_mask.p)
+    return fail(ctx, DSNERF_ERR_STATE, "no render of that shape precedes this call on the context");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  const int64_t P = R * (int64_t)N;
+  expand_mask_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(ctx->ray_mask.as<unsigned>(), P, transparent);
+  CKL("expand_mask");
+  return 0;
+}
+
+int dsnerf_tensor_path_active(const dsnerf_ctx* ctx) {
+  if (!ctx || !ctx->have_weights) return DSNERF_ERR_STATE;
+  return ctx->tw.fp16_ok ? 1 : 0;
+}
+
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
   if (!ctx || !out) return DSNERF_ERR_INVALID;
   if (ctx->stats.rays > 0) {
@@ -1056,7 +1087,7 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
 
 int dsnerf_profile(dsnerf_ctx* ctx, int enable) {
   if (!ctx) return DSNERF_ERR_INVALID;
-  ctx->profile = enable & 63;
+  ctx->profile = enable & 255;
   return 0;
 }
 

@@ -46,6 +46,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace dsn {
@@ -100,7 +102,8 @@ struct TcParams {
   const uint32_t* seed_h2; // [128] packed half2 pairs of w_dens / seed_scale
   float b_rgb2[3];
   float b_dens;
-  float seed_scale;
+  float seed_scale;        // out_g = accumulated gradient * seed_scale (undoes the seed normalisation and the per-layer power-of-two scales)
+  float stash_scale;       // layer 4's PE-gradient (parked at op 10) carries fewer per-layer scales than layer 0's: multiply it by this
   const float4* active;
   const unsigned long long* n_active_ptr;
   int64_t n_active_host;
@@ -109,6 +112,7 @@ struct TcParams {
   int density_only;
   long long* timing;       // debug: clock64 stamps of CTA 0 / first tile, NULL in production
   int debug_noload;        // debug: skip the weight stream (garbage results) to measure its cost
+  int debug_passes;        // debug: 0 = normal; 1 / 2 = issue only that many MMAs per forward k-step (garbage results)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -245,7 +249,7 @@ __device__ __forceinline__ uint32_t relu_mask2(uint32_t word) {
 // parameters so that every descriptor is "slab base + immediate": the issuing lane spends a couple of
 // uniform-datapath adds per tcgen05.mma instead of rebuilding 64-bit descriptors.
 //   a_word / a_lo_word / b_word: low 32 bits of the A-hi / A-lo / B-hi shared-memory descriptors at the slab's first k-step
-template <int ROWS, int KSTEPS, bool THREE, int NMMA, bool EXTRA>
+template <int ROWS, int KSTEPS, int NPASS, int NMMA, bool EXTRA>
 __device__ __forceinline__ void issue_slab(uint32_t d_main, uint32_t d_extra, uint32_t a_word, uint32_t a_lo_word, uint32_t b_word,
                                            uint32_t first_acc, uint32_t empty_bar, bool do_commit = true) {  // ROWS = B rows held by ONE CTA
   constexpr uint32_t DHI = (128u >> 4) | (1u << 14);             // descriptor bits 32..63: SBO = 128 B, version 1
@@ -260,10 +264,12 @@ __device__ __forceinline__ void issue_slab(uint32_t d_main, uint32_t d_extra, ui
       const uint64_t da = ((uint64_t)DHI << 32) | (a_word + j * A_STEP);
       const uint64_t db = ((uint64_t)DHI << 32) | (b_word + j * B_STEP);
       tc_mma_ss2(d_main, da, db, IDESC, j == 0 ? first_acc : 1u);
-      if (THREE) {
+      if (NPASS >= 2) {
         const uint64_t dbl = ((uint64_t)DHI << 32) | (b_word + j * B_STEP + B_LO);
-        const uint64_t dal = ((uint64_t)DHI << 32) | (a_lo_word + j * A_STEP);
         tc_mma_ss2(d_main, da, dbl, IDESC, 1u);
+      }
+      if (NPASS >= 3) {
+        const uint64_t dal = ((uint64_t)DHI << 32) | (a_lo_word + j * A_STEP);
         tc_mma_ss2(d_main, dal, db, IDESC, 1u);
       }
       if (EXTRA) {
@@ -287,7 +293,7 @@ struct MmaState {
     tc_fence_after();
   }
 };
-template <int ROWS, int KSTEPS, bool THREE, int NMMA, bool EXTRA>
+template <int ROWS, int KSTEPS, int NPASS, int NMMA, bool EXTRA>
 __device__ __forceinline__ void run_op(MmaState& ms, int n_slabs, int a_src, uint32_t d_main, uint32_t d_extra) {
   constexpr uint32_t A_LBO = (A_CHUNK >> 4) << 16;          // LBO field of every A descriptor
   constexpr uint32_t B_LBO = ((ROWS * 16) >> 4) << 16;
@@ -303,7 +309,7 @@ __device__ __forceinline__ void run_op(MmaState& ms, int n_slabs, int a_src, uin
     tc_fence_after();
     const uint32_t b_word = B_LBO | ((ms.sbase + SM_RING + ms.stage * TC_STAGE_BYTES) >> 4);
     const uint32_t ac = ((from_pe ? kk : kk - pe_steps) * 2 * A_CHUNK) >> 4;
-    issue_slab<ROWS, KSTEPS, THREE, NMMA, EXTRA>(d_main, d_extra, (from_pe ? p_hi0 : a_hi0) + ac, (from_pe ? p_lo0 : a_lo0) + ac, b_word,
+    issue_slab<ROWS, KSTEPS, NPASS, NMMA, EXTRA>(d_main, d_extra, (from_pe ? p_hi0 : a_hi0) + ac, (from_pe ? p_lo0 : a_lo0) + ac, b_word,
                                                  (uint32_t)(kk > 0), ms.bar_empty + 8 * ms.stage, !(ms.noload & 2));
     if (++ms.stage == TC_STAGES) { ms.stage = 0; ms.phase ^= 1; }
   }
@@ -442,11 +448,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         const uint32_t d_extra = tmem + (uint32_t)((op & 1) ^ 1) * TM_ACC;
         ms.waited = op == 8 ? 4 : 0;  // op 8 (bW6) reads the seed that layer 6's epilogue published together with h6 (consumed by op 7)
         switch (o.kind) {
-          case K_FWD: run_op<128, 2, true, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
-          case K_RGB: run_op<64, 8, false, 128, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
-          case K_BWD: run_op<128, 4, false, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
-          case K_BW4: run_op<160, 2, false, 256, true>(ms, o.n_slabs, o.a_src, d_main, d_extra); break;
-          default: run_op<32, 16, false, 64, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_FWD:
+            // debug_passes (measurement only, wrong numerics): issue 2 or 1 of the 3 MMAs of a forward k-step = the time any
+            // cheaper operand split could reach at best with this pipeline
+            if (P.debug_passes == 2) run_op<128, 2, 2, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u);
+            else if (P.debug_passes == 1) run_op<128, 2, 1, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u);
+            else run_op<128, 2, 3, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u);
+            break;
+          case K_RGB: run_op<64, 8, 1, 128, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_BWD: run_op<128, 4, 1, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_BW4: run_op<160, 2, 1, 256, true>(ms, o.n_slabs, o.a_src, d_main, d_extra); break;
+          default: run_op<32, 16, 1, 64, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
         }
         ms.need_quarters(4);
         if (elect_one()) tc_commit2(bar_acc);  // accumulator (and the extra columns of K_BW4) complete, in both CTAs
@@ -691,7 +703,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
                    __half2float(*reinterpret_cast<const __half*>(smem + SM_PE_LO + off));
           };
           // every branch below is warp uniform (sub is); C0 = pe_ld0(sub) as a literal keeps g[] in registers
-#define DSN_GPE(C, C0) (__uint_as_float(g[(C) - (C0)]) + stash[(C) * TC_TILE + row])
+#define DSN_GPE(C, C0) fmaf(stash[(C) * TC_TILE + row], P.stash_scale, __uint_as_float(g[(C) - (C0)]))
 #define DSN_OCTAVE(K, C0)                                                               \
   {                                                                                     \
     _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                     \
@@ -755,7 +767,9 @@ struct TcWeights {
   void* d_pack = nullptr;
   float* d_f32 = nullptr;  // biases 0..6 (7x256; row 0 per frame), b_rgb1 (128), w_rgb2 (384), w_dens (256), seed half2 pairs (128 words)
   float b_rgb2[3] = {0, 0, 0};
-  float b_dens = 0.f, seed_scale = 1.f;
+  float b_dens = 0.f, seed_scale = 1.f, stash_scale = 1.f;
+  bool fp16_ok = true;     // false: some weight is outside fp16 range, the tensor-core path must not be used (dsnerf.cu routes to the fp32 kernel)
+  int bwd_shift[7] = {0, 0, 0, 0, 0, 0, 0};  // per-layer power-of-two scale folded into the backward weights
   TcOp ops[TC_NUM_OPS];
   static constexpr int F32_BRGB1 = 7 * 256, F32_WRGB2 = F32_BRGB1 + 128, F32_WDENS = F32_WRGB2 + 384, F32_SEED = F32_WDENS + 256,
                        F32_TOTAL = F32_SEED + 128;
@@ -833,24 +847,51 @@ struct TcWeights {
     for (int n = 0; n < 128; ++n)
       for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = wr1[(size_t)n * 256 + k];
     pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 0, 256, 8, false, B);
+    // fp16 range: the forward operands are fp16 hi/lo splits of the weights, so |w| must be below 65504; the backward chain
+    // G_{l-1} = (G_l W_l) * relu' repacks G to fp16 at every layer, so each backward weight matrix carries a power-of-two scale
+    // 2^shift[l] ~ 1 / (rms gain of the layer) that keeps |G| near the seed's magnitude whatever the checkpoint's weight norms are
+    // (the normal is scale invariant; out_g is rescaled by seed_scale).  Scaling by powers of two is exact.
+    fp16_ok = true;
+    for (int l = 0; l < 7; ++l) {
+      const int in_dim = l == 0 ? 87 : (l == 4 ? 319 : 256);
+      double ss = 0.0, mx = 0.0;
+      for (int n = 0; n < 256; ++n)
+        for (int k = 0; k < in_dim; ++k) {
+          if (l == 0 && (k < 8 || k >= 71)) continue;  // code / pose columns are folded into the bias
+          const double v = (*W[l])[(size_t)n * in_dim + k];
+          ss += v * v;
+          mx = std::max(mx, fabs(v));
+        }
+      if (!(mx < 60000.0)) fp16_ok = false;
+      const double cols = l == 0 ? 63 : in_dim;
+      const double gain = sqrt(0.5 * ss / cols);        // rms of one backward output per unit rms input, half of the units active
+      int sh = gain > 0.0 ? (int)lrint(-log2(gain)) : 0;
+      sh = std::max(-12, std::min(12, sh));
+      while (sh > -12 && mx * exp2((double)sh) > 30000.0) --sh;
+      bwd_shift[l] = sh;
+    }
+    for (float v : wd) if (!(fabsf(v) < 3.0e38f)) fp16_ok = false;
+    for (float v : wr1) if (!(fabsf(v) < 60000.f)) fp16_ok = false;
+    auto p2 = [](int sh) { return (float)exp2((double)sh); };
     // backward through layers 6..1: B[n][k] = W[k][n] (n = input index, k = output index), 1-pass
     for (int l = 6; l >= 1; --l) {
+      const float sc = p2(bwd_shift[l]);
       if (l == 4) {  // 256 hidden inputs + 63 PE inputs (+1 pad): rows 256..319 feed the extra N = 64 MMA
         B.assign((size_t)320 * 256, 0.f);
         for (int n = 0; n < 319; ++n)
-          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = w4[(size_t)k * 319 + n];
+          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = sc * w4[(size_t)k * 319 + n];
         pack_op(blob, ops[oi++], K_BW4, A_ACT, 256, 64, 256, 2, false, B);
       } else {
         B.assign((size_t)256 * 256, 0.f);
         for (int n = 0; n < 256; ++n)
-          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = (*W[l])[(size_t)k * 256 + n];
+          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = sc * (*W[l])[(size_t)k * 256 + n];
         pack_op(blob, ops[oi++], K_BWD, l == 6 ? A_ACT_LO : A_ACT, 256, 0, 256, 4, false, B);
       }
     }
     // layer 0 backward, PE columns only (N = 64); added to the stashed layer-4 PE gradient in the tile's last stage
     B.assign((size_t)64 * 256, 0.f);
     for (int n = 0; n < 63; ++n)
-      for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = w0[(size_t)k * 87 + 8 + n];
+      for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = p2(bwd_shift[0]) * w0[(size_t)k * 87 + 8 + n];
     pack_op(blob, ops[oi++], K_BW0, A_ACT, 64, 0, 256, 16, false, B);
     if (oi != TC_NUM_OPS) return (int)cudaErrorUnknown;
     for (int i = 0; i < TC_NUM_OPS; ++i)
@@ -868,11 +909,18 @@ struct TcWeights {
     for (int i = 0; i < 384; ++i) f[F32_WRGB2 + i] = wr2[i];
     float mx = 0.f;
     for (int i = 0; i < 256; ++i) mx = fmaxf(mx, fabsf(wd[i]));
-    seed_scale = mx > 0.f ? mx : 1.f;
+    const float seed_norm = mx > 0.f ? mx : 1.f;
     for (int i = 0; i < 256; ++i) f[F32_WDENS + i] = wd[i];
     for (int i = 0; i < 128; ++i) {
-      __half2 h = __floats2half2_rn(wd[2 * i] / seed_scale, wd[2 * i + 1] / seed_scale);
+      __half2 h = __floats2half2_rn(wd[2 * i] / seed_norm, wd[2 * i + 1] / seed_norm);
       memcpy(&f[F32_SEED + i], &h, 4);
+    }
+    {
+      int all = 0, low = 0;  // layer 0's PE gradient went through every scale, layer 4's (stash) only through layers 6..4
+      for (int l = 0; l < 7; ++l) all += bwd_shift[l];
+      for (int l = 0; l < 4; ++l) low += bwd_shift[l];
+      seed_scale = seed_norm * (float)exp2((double)-all);
+      stash_scale = (float)exp2((double)low);
     }
     e = cudaMalloc(reinterpret_cast<void**>(&d_f32), f.size() * sizeof(float));
     if (e != cudaSuccess) return (int)e;
@@ -887,7 +935,7 @@ struct TcWeights {
 
 inline void tc_configure() { cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM); }
 
-inline int tc_launch(TcWeights& w, long long* timing, int debug_noload, const float4* active, const unsigned long long* n_active_ptr, int64_t n_active_host,
+inline int tc_launch(TcWeights& w, long long* timing, int debug_noload, int debug_passes, const float4* active, const unsigned long long* n_active_ptr, int64_t n_active_host,
                      float4* out_a, float4* out_g, int density_only, int sm_count, cudaStream_t st) {
   TcParams p{};
   p.wpack = reinterpret_cast<const uint8_t*>(w.d_pack);
@@ -899,6 +947,7 @@ inline int tc_launch(TcWeights& w, long long* timing, int debug_noload, const fl
   for (int i = 0; i < 3; ++i) p.b_rgb2[i] = w.b_rgb2[i];
   p.b_dens = w.b_dens;
   p.seed_scale = w.seed_scale;
+  p.stash_scale = w.stash_scale;
   p.active = active;
   p.n_active_ptr = n_active_ptr;
   p.n_active_host = n_active_host;
@@ -907,6 +956,7 @@ inline int tc_launch(TcWeights& w, long long* timing, int debug_noload, const fl
   p.density_only = density_only;
   p.timing = timing;
   p.debug_noload = debug_noload;
+  p.debug_passes = debug_passes;
   mlp_tc_kernel<<<sm_count & ~1, TC_THREADS, TC_SMEM, st>>>(p);  // CTA pairs (__cluster_dims__(2,1,1))
   return (int)cudaGetLastError();
 }

@@ -23,6 +23,36 @@ def shard_range(n_rays: int, rank: int, world: int):
     return lo, min(lo + per, n_rays)
 
 
+def interleaved_indices(n_rays: int, rank: int, world: int, block: int):
+    """Ray indices of `rank` when blocks of `block` consecutive rays are dealt round-robin to the ranks (block = one image
+    row: rank r renders rows r, r + world, ...).  Hit and miss rays differ in cost by two orders of magnitude (transparent
+    samples are skipped), and a body fills the middle rows of a frame: contiguous ranges leave the first and last ranks idle,
+    interleaved rows give every rank the same mix.  Every rank gets the same count when block * world divides
+    n_rays; otherwise the tail blocks go to the low ranks and `gather_interleaved` pads."""
+    idx = torch.arange(n_rays)
+    return idx[(idx // block) % world == rank]
+
+
+def gather_interleaved(local, n_rays: int, block: int, group=None):
+    """Inverse of `interleaved_indices`: all-gather the per-rank (n_local, C) outputs and restore ray order."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    C = local.shape[1]
+    counts = [int(((torch.arange(n_rays) // block) % world == r).sum()) for r in range(world)]
+    per = max(counts)
+    if local.shape[0] < per:
+        local = torch.cat([local, local.new_zeros(per - local.shape[0], C)], 0)
+    full = local.new_empty(world, per, C)
+    dist.all_gather_into_tensor(full.view(world * per, C), local.contiguous(), group=group)
+    if n_rays % (block * world) == 0:  # regular case: (world, n_blocks, block, C) -> (n_blocks, world, block, C)
+        return full.view(world, per // block, block, C).transpose(0, 1).reshape(n_rays, C)
+    out = local.new_empty(n_rays, C)
+    for r in range(world):
+        out[interleaved_indices(n_rays, r, world, block).to(out.device)] = full[r, : counts[r]]
+    return out
+
+
 def pack_outputs(out):
     """dict(color (R,3), depth_map, acc_map, disp_map (R,)) -> (R,6) tensor."""
     return torch.cat([out["color"], out["depth_map"][:, None], out["acc_map"][:, None], out["disp_map"][:, None]], 1).contiguous()
@@ -57,15 +87,22 @@ def gather_frames(local, group=None):
     return full.reshape((world,) + tuple(local.shape))
 
 
-def render_sharded(renderer, batch, group=None):
+def render_sharded(renderer, batch, group=None, interleave=0):
     """Render one frame with its rays split across the ranks (config 4) and reassemble it everywhere.
 
-    `renderer` is a dual_space_nerf_b200.Renderer (or anything with the same ``render``)."""
+    `renderer` is a dual_space_nerf_b200.Renderer (or anything with the same ``render``).  ``interleave`` = 0: contiguous
+    ray ranges; > 0: blocks of that many rays (one image row) dealt round-robin, which balances hit and miss rays."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     R = batch["ray_o"].shape[1]
-    lo, hi = shard_range(R, rank, world)
     sub = dict(batch)
+    if interleave > 0:
+        sel = interleaved_indices(R, rank, world, interleave).to(batch["ray_o"].device)
+        for k in ("ray_o", "ray_d", "near", "far"):
+            sub[k] = batch[k][:, sel]
+        out = renderer.render(sub)["coarse"]
+        return unpack_outputs(gather_interleaved(pack_outputs(out), R, interleave, group))
+    lo, hi = shard_range(R, rank, world)
     for k in ("ray_o", "ray_d", "near", "far"):
         sub[k] = batch[k][:, lo:hi]
     out = renderer.render(sub)["coarse"]

@@ -116,9 +116,15 @@ class Renderer:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _weights_fingerprint(self):
+        """Changes whenever a parameter is replaced or edited in place (optimizer.step(), p.data.copy_(), load_state_dict):
+        torch bumps ``Tensor._version`` on every in-place write, so no caller cooperation (mark_weights_dirty) is needed."""
+        sd = self.net.state_dict(keep_vars=True)
+        return (getattr(self.net, "_weights_version", 0),) + tuple((sd[k].data_ptr(), sd[k]._version) for k in STATE_DICT_ORDER)
+
     def _sync_weights(self):
-        ver = getattr(self.net, "_weights_version", None)
-        if ver is not None and ver == self._weights_version:
+        ver = self._weights_fingerprint()
+        if ver == self._weights_version:
             return
         sd = self.net.state_dict()
         arrs = [_f32_host(sd[k]) for k in STATE_DICT_ORDER]
@@ -197,6 +203,11 @@ class Renderer:
         return ret
 
     def _render_fine(self, ray_o, ray_d, coarse, n_importance):
+        if self.fine_net is not None and self.fine_net is not self.net:
+            # the reference would evaluate the second pass with fine_net (can_render.py:232, a branch that cannot run there:
+            # Renderer.resampling is undefined); one context stages one weight set, so a distinct fine network is refused
+            raise NotImplementedError("hierarchical pass with a separate fine_net is not supported: pass fine_net=None "
+                                      "(the second pass then uses net, as can_render.py:77-78 does)")
         R, N = coarse["z_vals"].shape
         mk = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
         z2 = mk(R, N + n_importance)
@@ -230,6 +241,7 @@ class Renderer:
             if noise is not None:
                 noise = self._dev(noise).reshape(-1, N)
             coarse = self._render_rays_device(ray_o, ray_d, near, far, N, True, jitter, noise)
+            batch["transparent_mask"] = self._last_transparent_mask(ray_o.shape[0], N)  # can_render.py:156
             out = {"coarse": coarse}
             n_imp = int(getattr(self.cfg.MODEL, "FINE_RAY_SAMPLING", -1))
             if n_imp > 0:
@@ -237,6 +249,14 @@ class Renderer:
         batch["canonical_model"] = self.canonical_model
         batch["face_idx"] = self.face_idx
         return out
+
+    def _last_transparent_mask(self, R, N):
+        """(R, N) bool mask of the samples of the render call that has just been enqueued (get_transparent_mask,
+        utils/render_utils.py:103-109)."""
+        tm = torch.empty(R, N, device=self.device, dtype=torch.uint8)
+        if R > 0:
+            self.ctx.check(self.ctx.L.dsnerf_last_transparent_mask(self.ctx.h, R, N, _ptr(tm), self._stream()))
+        return tm.bool()
 
     def batchify_rays_view(self, ray_o, ray_d, near, far, batch, chunk=1024 * 32):
         """can_render.py:172-245.  ``chunk`` is accepted for signature compatibility; the whole
@@ -339,17 +359,29 @@ class Renderer:
         return pts6, rays, tm
 
     def query_volume(self, pts, code_idx, transparent_mask=None, batch_info={}):
-        """can_render.py:280-296: canonical points (B,P,3) -> density (B,P,1)."""
+        """can_render.py:280-296: points (B,P,6) = [world xyz | canonical xyz], as the reference's only caller passes them
+        (utils/visualizer.py:60-66; DualSpaceNeRF.forward reads pos[..., 3:], model/spacenet.py:219), or canonical points
+        (B,P,3); code_idx (B,) = one latent-code row per batch entry -> density (B,P,1), 0 where transparent_mask."""
+        pts = torch.as_tensor(pts)
+        if pts.dim() != 3 or pts.shape[-1] not in (3, 6):
+            raise ValueError(f"query_volume expects pts of shape (B, P, 6) [world | canonical] or (B, P, 3) canonical, got {tuple(pts.shape)}")
+        B, P = pts.shape[:2]
+        codes = torch.as_tensor(code_idx).reshape(-1).tolist()
+        if len(codes) != B:
+            raise ValueError(f"code_idx must hold one code index per batch entry ({B}), got {len(codes)}")
         with torch.cuda.device(self.device):
-            if "xyz" in batch_info:
-                b = dict(batch_info)
-                b["frame"] = torch.as_tensor(code_idx).reshape(-1)[:1]
-                self._set_frame(b)
-            B, P = pts.shape[:2]
-            x = self._dev(pts).reshape(-1, 3)
-            tm = None if transparent_mask is None else torch.as_tensor(transparent_mask).to(self.device).reshape(-1).to(torch.uint8).contiguous()
-            dens = torch.empty(B * P, device=self.device)
-            self.ctx.check(self.ctx.L.dsnerf_query_density(self.ctx.h, _ptr(x), _ptr(tm), B * P, _ptr(dens), self.flags_extra, self._stream()))
+            x = self._dev(pts)[..., -3:].contiguous()
+            tm = None if transparent_mask is None else torch.as_tensor(transparent_mask).to(self.device).reshape(B, P).to(torch.uint8).contiguous()
+            dens = torch.empty(B, P, device=self.device)
+            for b in range(B):  # the latent code is a per-frame constant of the library: one frame set-up per distinct batch entry
+                if "xyz" in batch_info:
+                    bi = dict(batch_info)
+                    bi["frame"] = torch.tensor([int(codes[b])])
+                    self._set_frame(bi)
+                elif b > 0 and codes[b] != codes[0]:
+                    raise ValueError("different code indices per batch entry need batch_info (xyz, poses) to set up each frame")
+                self.ctx.check(self.ctx.L.dsnerf_query_density(self.ctx.h, _ptr(x[b]), None if tm is None else _ptr(tm[b]), P,
+                                                               _ptr(dens[b]), self.flags_extra, self._stream()))
         return dens.reshape(B, P, 1)
 
     def _net_forward(self, pos, rays, frame_idx, batch_info, density_only):

@@ -175,6 +175,16 @@ int dsnerf_ppts_to_pts(dsnerf_ctx* ctx, const float* ppts, const float* bw, cons
 int dsnerf_camera_rays(dsnerf_ctx* ctx, int H, int W, const double* K, const double* R, const double* T, const float* bounds,
                        float* ray_o, float* ray_d, float* near, float* far, uint8_t* mask_at_box, void* stream);
 
+/* batch["transparent_mask"] of Renderer.render (can_render.py:156, get_transparent_mask utils/render_utils.py:103-109): the
+ * per-sample mask of the LAST dsnerf_render* call on this context, which must have had exactly n_rays x n_samples samples:
+ * transparent[r * n_samples + i] = 1 where the sample is transparent (density forced to 0), else 0.  DEVICE buffer of
+ * n_rays * n_samples bytes; enqueued on `stream` (use the stream of the render call). */
+int dsnerf_last_transparent_mask(dsnerf_ctx* ctx, int64_t n_rays, int n_samples, uint8_t* transparent, void* stream);
+
+/* 1 if SpaceNet runs on the tcgen05 kernel with the staged weights, 0 if dsnerf_set_weights found a weight outside fp16
+ * range (|w| >= 60000) and routed every evaluation to the fp32 CUDA kernel (same results, slower); < 0 without weights. */
+int dsnerf_tensor_path_active(const dsnerf_ctx* ctx);
+
 /* Counters of the last render on this context (synchronises the stream it ran on). */
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
 
@@ -182,11 +192,13 @@ int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
  * (read back with dsnerf_profile_read: accumulated milliseconds / launches since the last
  * reset); 2 = count nearest-centroid distance evaluations (dsnerf_stats_t.nn_candidates; slows
  * the warp kernel, never enable it in a timed run); 4 = clock stamps of the tensor-core kernel; 8, 16 = debug switches of its
- * weight stream (garbage results); 32 = test switch: shrink the candidate-list pool of meshes built from now on to 4096
+ * weight stream (garbage results); 64 / 128 = measurement switch: issue only 1 (64) or 2 (128) of the three MMAs of every forward
+ * k-step (garbage results; bounds what a cheaper operand split could gain); 32 = test switch: shrink the candidate-list pool of meshes built from now on to 4096
  * entries so that most lookup cells take the ball-scan fallback (results must not change). */
 int dsnerf_profile(dsnerf_ctx* ctx, int enable);
-/* debug (profile bit 4): clock64 stamps of the tensor-core kernel's first tile, 64 values */
-int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out64);
+/* debug (profile bit 4): clock64 stamps of the tensor-core kernel's first tile; writes 128 values (the caller's buffer must
+ * hold 128 long long: [0..63] epilogue stamps, [64..127] MMA-warp stamps) */
+int dsnerf_debug_tc_timing(dsnerf_ctx* ctx, long long* out128);
 int dsnerf_profile_read(dsnerf_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int reset);
 /* debug: counters of the lazily built lookup table of the posed (which = 0) or canonical (1) mesh, 16 ints:
  * [0] candidate-list entries in use, [1] table cells / [2] enumeration cells requested by the last call, [3] table cells left

@@ -32,8 +32,40 @@ def bits_equal(a, b):
     return int(np.sum(a.view(np.int32) != b.view(np.int32)))
 
 
-def check_rays(out, ref, kink_ray=None, tol=TOL, what=""):
-    """Assert the per-ray outputs match; returns a dict of error statistics."""
+def record(name, stats):
+    """Append the achieved error statistics of a parity test to gpurun_out/r02_parity.json (copied to profiles/ by hand
+    after a GPU run: the numbers a test merely prints are lost)."""
+    import json
+
+    try:
+        import torch
+
+        if not torch.cuda.is_available():  # CPU runs pin the oracle; only the GPU path's achieved errors are recorded
+            return
+    except ImportError:
+        return
+    root = os.environ.get("GRAFT_REPO_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, "r02_parity.json")
+        data = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                data = json.load(f)
+        data[name] = stats
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def check_rays(out, ref, kink_ray=None, tol=TOL, what="", strict=False):
+    """Assert the per-ray outputs match; returns a dict of error statistics.  ``strict``: every ray within ``tol`` on rgb, no
+    ReLU-kink exemption (used wherever the committed golden is known to be met on every ray)."""
+    if strict:
+        n_kink = int(np.sum(kink_ray)) if kink_ray is not None else 0
+        kink_ray = None
     col = np.abs(np.asarray(out["color"]) - np.asarray(ref["color"])).reshape(len(ref["color"]), -1).max(1)
     dep = np.abs(np.asarray(out["depth_map"]).ravel() - np.asarray(ref["depth_map"]).ravel())
     acc = np.abs(np.asarray(out["acc_map"]).ravel() - np.asarray(ref["acc_map"]).ravel())
@@ -50,7 +82,14 @@ def check_rays(out, ref, kink_ray=None, tol=TOL, what=""):
         assert col.max() <= KINK_RGB_BOUND, f"{what} rgb err {col.max():.3e} exceeds the kink bound"
         assert bad.sum() <= max(3, 0.02 * len(col)), f"{what} too many kink rays over tolerance: {bad.sum()}"
         stats["rgb_max_nokink"] = float(col[~kink_ray].max()) if (~kink_ray).any() else 0.0
+    if strict:
+        stats["kink_rays"] = n_kink
+        stats["strict"] = True
+    elif kink_ray is not None:
+        stats["kink_rays"] = int(np.sum(kink_ray))
     d0 = np.asarray(ref["disp_map"]).ravel()
     d1 = np.asarray(out["disp_map"]).ravel()
     assert np.array_equal(np.isnan(d0), np.isnan(d1)), f"{what} disp NaN pattern (acc==0 rays) differs"
+    if what:
+        record(what, stats)
     return stats

@@ -63,7 +63,7 @@ def test_render_view_config1_vs_reference_golden(mlp, scene64, state_dict):
            "acc_map": out["coarse_acc"].numpy().ravel(), "disp_map": out["coarse_disp"].numpy().ravel()}
     ref = {"color": g["coarse_color"].reshape(-1, 3), "depth_map": g["coarse_depth"].ravel(),
            "acc_map": g["coarse_acc"].ravel(), "disp_map": g["coarse_disp"].ravel()}
-    stats = C.check_rays(got, ref, kink_rays(st, 32), what=f"render_view[{mlp}]")
+    stats = C.check_rays(got, ref, kink_rays(st, 32), what=f"render_view 64x64x32 vs reference golden [{mlp}]", strict=True)
     print(mlp, stats)
     # discrete decisions are bit-identical to the oracle: same set of evaluated samples
     assert r.ctx.stats()["evaluated_samples"] == int((~st["mask"]).sum())
@@ -77,7 +77,7 @@ def test_render_128x128x64_vs_reference_golden(mlp, state_dict):
     r = make_renderer(sc, 64, mlp=mlp)
     out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
     _, st = oracle_run(sc, state_dict, 64, rays)
-    stats = C.check_rays(out, g, kink_rays(st, 64), what=f"render 128[{mlp}]")
+    stats = C.check_rays(out, g, kink_rays(st, 64), what=f"render 128x128x64 vs reference golden [{mlp}]", strict=True)
     print(mlp, stats)
     assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0  # GG near/far and sample placement are bit-exact
     assert np.abs(out["weights"] - g["weights"]).max() < 1e-4
@@ -89,7 +89,7 @@ def test_uniform_and_novel_pose_vs_reference_golden(scene64, state_dict):
     r = make_renderer(scene64, 16, mode="uniform")
     out = to_np(r.render(S.to_batch(scene64, torch, rays=rays))["coarse"])
     _, st = oracle_run(scene64, state_dict, 16, rays, mode="uniform")
-    C.check_rays(out, g, kink_rays(st, 16), what="uniform")
+    C.check_rays(out, g, kink_rays(st, 16), what="uniform sampling vs reference golden", strict=True)
     assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0
 
     g = C.golden("render_novelpose.npz")
@@ -101,7 +101,7 @@ def test_uniform_and_novel_pose_vs_reference_golden(scene64, state_dict):
     r = make_renderer(sc, 32, net=net)
     out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
     _, st = oracle_run(sc, state_dict, 32, rays, zero_code=True, light_center=S.LIGHT_CENTER_313)
-    C.check_rays(out, g, kink_rays(st, 32), what="novel pose")
+    C.check_rays(out, g, kink_rays(st, 32), what="novel pose (nerf.w=0, light_center) vs reference golden", strict=True)
 
 
 def test_stage_ops_bit_exact_vs_golden(scene64, state_dict):
@@ -116,7 +116,9 @@ def test_stage_ops_bit_exact_vs_golden(scene64, state_dict):
     # density-only query on the canonical points (Renderer.query_volume)
     dens = r.query_volume(cano[None], torch.tensor([scene64["frame"]]), tm, S.to_batch(scene64, torch))
     act = ~g["mask"]
-    assert np.abs(dens.cpu().numpy().ravel()[act] - g["density"][act]).max() < 5e-3  # |sigma| ~ 170
+    derr = np.abs(dens.cpu().numpy().ravel()[act] - g["density"][act])
+    assert (derr / np.maximum(np.abs(g["density"][act]), 1.0)).max() < 3e-5  # |sigma| reaches ~170: relative bound (5e-3 absolute there)
+    C.record("query_volume density vs reference golden", {"abs_max": float(derr.max()), "sigma_max": float(np.abs(g["density"][act]).max())})
     assert np.all(dens.cpu().numpy().ravel()[g["mask"]] == 0)
 
 
@@ -336,7 +338,8 @@ def test_training_mode_forward(scene64, state_dict):
     assert r.ctx.stats()["evaluated_samples"] == len(rays) * n  # the network ran on every sample
     assert C.bits_equal(out["z_vals"], g["z_vals"]) == 0
     kink = kink_rays(st, n)
-    print("train", C.check_rays(out, g, kink, what="train vs reference"), C.check_rays(out, ref, kink, what="train vs oracle"))
+    print("train", C.check_rays(out, g, kink, what="training-mode forward vs reference golden", strict=True),
+          C.check_rays(out, ref, kink, what="training-mode forward vs oracle"))
     assert np.abs(out["weights"] - g["weights"]).max() < 1e-4
     # jitter only
     st2 = {}

@@ -79,6 +79,18 @@ def test_shard_ranges_cover_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
 
 
+def test_interleaved_shards_partition_the_rays():
+    from dual_space_nerf_b200 import dist as D
+
+    for n, block in ((0, 4), (10, 3), (4096, 64), (1024 * 1024, 1024), (1000, 7)):
+        for world in (1, 2, 8):
+            parts = [D.interleaved_indices(n, r, world, block) for r in range(world)]
+            allidx = torch.cat(parts)
+            assert allidx.numel() == n and torch.equal(torch.sort(allidx)[0], torch.arange(n))
+            if n and n % (block * world) == 0:
+                assert len({p.numel() for p in parts}) == 1
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -111,6 +123,9 @@ def _worker(rank, world, port, ray_counts, q):
         full = FakeRenderer().render(batch)["coarse"]
         got = D.render_sharded(FakeRenderer(), batch)
         ok = ok and all(torch.equal(got[k], full[k]) for k in full)
+        for block in (1, 3, 16):  # rows dealt round-robin (config 4's cost-balanced split), regular and ragged tails
+            got = D.render_sharded(FakeRenderer(), batch, interleave=block)
+            ok = ok and all(torch.equal(got[k], full[k]) for k in full)
     frames = D.gather_frames(torch.full((5, 6), float(rank)))
     ok = ok and frames.shape == (world, 5, 6) and all(float(frames[r, 0, 0]) == r for r in range(world))
     q.put((rank, ok))
@@ -124,7 +139,7 @@ def test_sharded_render_equals_unsharded_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, (10, 4097, 1), q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, (10, 4097, 1, 96), q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]

@@ -107,6 +107,31 @@ def test_novel_pose_vs_golden(state_dict):
     C.check_rays(out, g, _kink_rays(st, 32), what="novel pose")
 
 
+def test_rot_and_trained_magnitude_weights_vs_golden(state_dict):
+    """Round-2 goldens (tests/make_golden_r2.py): net.set_rot / set_rot_center (model/spacenet.py:254-258) and a network whose
+    hidden layers have an rms gain > 1 (gradients grow through the backward chain)."""
+    from make_golden_r2 import ROT_ANGLE, ROT_CENTER, angle2rot, big_weight_net
+
+    g = C.golden("render_rot.npz")
+    rays = g["rays"]
+    sc = S.make_scene(64, 64, pose_seed=2)
+    st = {}
+    out = _oracle_for(sc, state_dict, 32, light_center=S.LIGHT_CENTER_313, rot=angle2rot(ROT_ANGLE).astype(np.float32),
+                      rot_center=ROT_CENTER).render(
+        sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays], sc["posed"], sc["poses"], sc["frame"],
+        Th=sc["Th"], stages=st)
+    C.check_rays(out, g, _kink_rays(st, 32), what="rot", strict=True)
+    g = C.golden("render_bigw.npz")
+    rays = g["rays"]
+    sc = S.make_scene(64, 64)
+    st = {}
+    out = _oracle_for(sc, big_weight_net(0).state_dict(), 32).render(
+        sc["ray_o"][rays], sc["ray_d"][rays], sc["near"][rays], sc["far"][rays], sc["posed"], sc["poses"], sc["frame"],
+        Th=sc["Th"], stages=st)
+    C.check_rays(out, g, _kink_rays(st, 32), what="trained-magnitude weights", strict=True)
+    assert np.abs(st["grad"]).max() > 1e3  # the chain does grow (default init: ~1e-2)
+
+
 def test_128x128x64_vs_golden(state_dict):
     g = C.golden("render_128x128x64.npz")
     rays = g["rays"]

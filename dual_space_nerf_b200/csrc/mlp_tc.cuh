@@ -79,7 +79,7 @@ constexpr int TC_NUM_OPS = 15;
 enum { A_ACT = 0, A_PE = 1, A_PE_ACT = 2, A_ACT_LO = 3 };  // A_PE_ACT: k-steps 0..3 come from the PE region, the rest from the activations;
                                                             // A_ACT_LO: operand parked in the A-lo region (seed of the backward chain)
 
-enum { K_FWD = 0, K_RGB = 1, K_BWD = 2, K_BW4 = 3, K_BW0 = 4 };
+enum { K_FWD = 0, K_RGB = 1, K_BWD = 2, K_BW4 = 3, K_BW0 = 4, K_RGB3 = 5 };
 
 struct TcOp {
   uint32_t src_off;     // byte offset of the op's first slab in the packed weight blob
@@ -110,6 +110,7 @@ struct TcParams {
   float4* out_a;
   float4* out_g;
   int density_only;
+  int rgb3;                // rgb head's 256 -> 128 layer with the 3-pass split (chosen by dsnerf_set_weights, see TcWeights::stage)
   long long* timing;       // debug: clock64 stamps of CTA 0 / first tile, NULL in production
   int debug_noload;        // debug: skip the weight stream (garbage results) to measure its cost
   int debug_passes;        // debug: 0 = normal; 1 / 2 = issue only that many MMAs per forward k-step (garbage results)
@@ -388,6 +389,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
   cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (P.timing && blockIdx.x == 0 && threadIdx.x == 0) {  // SM clock inside the kernel: clock64 against the global timer
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    P.timing[120] = clock64();
+    P.timing[121] = (long long)gt;
+  }
 
   const int64_t n_active = P.n_active_ptr ? (int64_t)*P.n_active_ptr : P.n_active_host;
   const int64_t n_tiles = (n_active + TC_TILE - 1) / TC_TILE;
@@ -446,7 +453,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         const long long t_op0 = mstamp ? clock64() : 0;
         const uint32_t d_main = tmem + (uint32_t)(op & 1) * TM_ACC;
         const uint32_t d_extra = tmem + (uint32_t)((op & 1) ^ 1) * TM_ACC;
-        ms.waited = op == 8 ? 4 : 0;  // op 8 (bW6) reads the seed that layer 6's epilogue published together with h6 (consumed by op 7)
+        // op 8 (bW6) reads the seed that layer 6's epilogue published together with h6 (consumed by op 7); with the 3-pass rgb
+        // head the A-lo region holds h6's lo part until op 7 is done, and op 7's epilogue publishes the seed as a hand-off of its own
+        ms.waited = (op == 8 && !P.rgb3) ? 4 : 0;
         switch (o.kind) {
           case K_FWD:
             // debug_passes (measurement only, wrong numerics): issue 2 or 1 of the 3 MMAs of a forward k-step = the time any
@@ -456,6 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             else run_op<128, 2, 3, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u);
             break;
           case K_RGB: run_op<64, 8, 1, 128, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
+          case K_RGB3: run_op<64, 4, 3, 128, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
           case K_BWD: run_op<128, 4, 1, 256, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
           case K_BW4: run_op<160, 2, 1, 256, true>(ms, o.n_slabs, o.a_src, d_main, d_extra); break;
           default: run_op<32, 16, 1, 64, false>(ms, o.n_slabs, o.a_src, d_main, 0u); break;
@@ -463,7 +473,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         ms.need_quarters(4);
         if (elect_one()) tc_commit2(bar_acc);  // accumulator (and the extra columns of K_BW4) complete, in both CTAs
         __syncwarp();
-        if (op != 8) ms.a_phase ^= 1;
+        if (op != 8 || P.rgb3) ms.a_phase ^= 1;
         if (mstamp) { P.timing[64 + 3 * op] = 0; P.timing[65 + 3 * op] = 0; P.timing[66 + 3 * op] = clock64() - t_op0; }
       }
     }
@@ -551,6 +561,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           acc_phase ^= 1;
           tc_fence_after();
           if (stamp) { P.timing[1 + 4 * op] = clock64(); P.timing[2 + 4 * op] = clock64(); }
+          if (P.rgb3) {
+            // the rgb MMAs have consumed h6 (hi and lo): the seed of the backward chain G6 = (w_dens / scale) * relu'(a6) now
+            // replaces h6's lo part (op 8's operand), rebuilt from the ReLU bits of layer 6
+            uint32_t m0, m1;
+            relu.get(6, m0, m1);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint4 sd0 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2));
+              const uint4 sd1 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2 + 4));
+              uint32_t g[8] = {sd0.x, sd0.y, sd0.z, sd0.w, sd1.x, sd1.y, sd1.z, sd1.w};
+              const uint32_t mw = (q4 >> 1) ? m1 : m0;
+              if ((q4 & 1) == 0) {
+                g[0] &= relu_mask2<0>(mw); g[1] &= relu_mask2<1>(mw); g[2] &= relu_mask2<2>(mw); g[3] &= relu_mask2<3>(mw);
+                g[4] &= relu_mask2<4>(mw); g[5] &= relu_mask2<5>(mw); g[6] &= relu_mask2<6>(mw); g[7] &= relu_mask2<7>(mw);
+              } else {
+                g[0] &= relu_mask2<8>(mw); g[1] &= relu_mask2<9>(mw); g[2] &= relu_mask2<10>(mw); g[3] &= relu_mask2<11>(mw);
+                g[4] &= relu_mask2<12>(mw); g[5] &= relu_mask2<13>(mw); g[6] &= relu_mask2<14>(mw); g[7] &= relu_mask2<15>(mw);
+              }
+              const uint32_t off = (uint32_t)((q4 * 64 + sub * TC_CPT) / 8) * A_CHUNK + row_off;
+              *reinterpret_cast<uint4*>(smem + SM_A_LO + off) = make_uint4(g[0], g[1], g[2], g[3]);
+              *reinterpret_cast<uint4*>(smem + SM_A_LO + off + A_CHUNK) = make_uint4(g[4], g[5], g[6], g[7]);
+              publish(q4);
+            }
+          }
           // rgb head tail: relu(acc[0:128] + b) -> Linear(128,3) partials (model/spacenet.py:75-80); 2 x 16 columns per thread
           const float* rgbw = reinterpret_cast<const float*>(smem + SM_RGBW);
           uint32_t v0[16], v1[16];
@@ -608,6 +642,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           const float* __restrict__ bias = P.bias + op * 256 + sub * TC_CPT;
           const float* __restrict__ wdp = P.w_dens + sub * TC_CPT;
           const bool last6 = op == 6;
+          const bool seed6 = last6 && !P.rgb3;  // layer 6 writes the backward seed instead of its lo part (single-pass rgb head)
           uint32_t mw0 = 0, mw1 = 0;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -616,7 +651,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
 #pragma unroll
             for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + q4 * 64) + i);
             uint4 sd0 = make_uint4(0u, 0u, 0u, 0u), sd1 = sd0;
-            if (last6) {
+            if (seed6) {
               sd0 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2));
               sd1 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2 + 4));
             }
@@ -640,6 +675,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
               if (last6) {
                 const float2 wd = __ldg(reinterpret_cast<const float2*>(wdp + q4 * 64 + 2 * j));
                 sig2 = __ffma2_rn(wd, h, sig2);
+              }
+              if (seed6) {
                 lo[j] = sd[j] & m2;
               } else {
                 const float2 hf = __half22float2(hh);
@@ -753,6 +790,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       }
     }
   }
+  if (P.timing && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    P.timing[122] = clock64();
+    P.timing[123] = (long long)gt;
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs / remote arrivals may still touch it
@@ -768,6 +811,7 @@ struct TcWeights {
   float* d_f32 = nullptr;  // biases 0..6 (7x256; row 0 per frame), b_rgb1 (128), w_rgb2 (384), w_dens (256), seed half2 pairs (128 words)
   float b_rgb2[3] = {0, 0, 0};
   float b_dens = 0.f, seed_scale = 1.f, stash_scale = 1.f;
+  bool rgb3 = false;       // rgb head first layer packed for 3 passes (hi + lo)
   bool fp16_ok = true;     // false: some weight is outside fp16 range, the tensor-core path must not be used (dsnerf.cu routes to the fp32 kernel)
   int bwd_shift[7] = {0, 0, 0, 0, 0, 0, 0};  // per-layer power-of-two scale folded into the backward weights
   TcOp ops[TC_NUM_OPS];
@@ -820,7 +864,8 @@ struct TcWeights {
             const std::vector<float>& w4, const std::vector<float>& w5, const std::vector<float>& w6, const std::vector<float>& b1,
             const std::vector<float>& b2, const std::vector<float>& b3, const std::vector<float>& b4, const std::vector<float>& b5,
             const std::vector<float>& b6, const std::vector<float>& wd, float bd, const std::vector<float>& wr1,
-            const std::vector<float>& br1, const std::vector<float>& wr2, const std::vector<float>& br2) {
+            const std::vector<float>& br1, const std::vector<float>& wr2, const std::vector<float>& br2, bool rgb_three_pass) {
+    rgb3 = rgb_three_pass;
     const std::vector<float>* W[7] = {&w0, &w1, &w2, &w3, &w4, &w5, &w6};
     std::vector<__half> blob;
     std::vector<float> B;
@@ -846,7 +891,8 @@ struct TcWeights {
     B.assign((size_t)128 * 256, 0.f);
     for (int n = 0; n < 128; ++n)
       for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = wr1[(size_t)n * 256 + k];
-    pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 0, 256, 8, false, B);
+    if (rgb3) pack_op(blob, ops[oi++], K_RGB3, A_ACT, 128, 0, 256, 4, true, B);
+    else pack_op(blob, ops[oi++], K_RGB, A_ACT, 128, 0, 256, 8, false, B);
     // fp16 range: the forward operands are fp16 hi/lo splits of the weights, so |w| must be below 65504; the backward chain
     // G_{l-1} = (G_l W_l) * relu' repacks G to fp16 at every layer, so each backward weight matrix carries a power-of-two scale
     // 2^shift[l] ~ 1 / (rms gain of the layer) that keeps |G| near the seed's magnitude whatever the checkpoint's weight norms are
@@ -954,6 +1000,7 @@ inline int tc_launch(TcWeights& w, long long* timing, int debug_noload, int debu
   p.out_a = out_a;
   p.out_g = out_g;
   p.density_only = density_only;
+  p.rgb3 = w.rgb3 ? 1 : 0;
   p.timing = timing;
   p.debug_noload = debug_noload;
   p.debug_passes = debug_passes;

@@ -211,12 +211,16 @@ struct CompositeArgs {
   // training mode (utils/nerf_net_utils.py:29-33): noise (R,N) = randn * raw_noise_std is added to the density before the
   // ReLU.  all_raw: raw holds EVERY sample and a clear mask bit only zeroes the density (can_render.py:118-120).
   const float* noise; int all_raw;
+  // fused all-gather (dsnerf_render_gather): the per-ray outputs are ALSO stored into this rank's block
+  // [rgb (R,3) | depth (R) | acc (R) | disp (R)] of every peer GPU's frame buffer (peer-mapped pointers over NVLink), or once
+  // through the NVSwitch multicast address `mc` (multimem.st: the switch replicates the store to every GPU of the group).
+  int n_peers; float* peer[7]; float* mc;
 };
 
-__global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
-  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (r >= a.R) return;
+constexpr int COMP_RAYS = 32;  // rays per block, one warp each
+
+// one ray by one warp; the six outputs are valid in lane 0
+__device__ __forceinline__ void composite_ray(const CompositeArgs& a, int64_t r, int lane, float (&o)[6]) {
   float nd = xnorm3(v3(a.ray_d[3 * r], a.ray_d[3 * r + 1], a.ray_d[3 * r + 2]));
   float near = a.z_in ? 0.f : a.near[r], far = a.z_in ? 0.f : a.far[r];
   if (a.sample_mask && !a.z_in && !a.noise && !a.all_raw) {
@@ -236,11 +240,8 @@ __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
         if (a.weights) a.weights[b0 + i] = 0.f;
         if (a.z_out) a.z_out[b0 + i] = sample_z(near, far, a.tvals[i]);
       }
-      if (lane == 0) {
-        a.rgb[3 * r] = 0.f; a.rgb[3 * r + 1] = 0.f; a.rgb[3 * r + 2] = 0.f;
-        a.depth[r] = 0.f; a.acc[r] = 0.f;
-        a.disp[r] = __int_as_float(0x7fc00000);
-      }
+      o[0] = o[1] = o[2] = o[3] = o[4] = 0.f;
+      o[5] = __int_as_float(0x7fc00000);
       return;
     }
   }
@@ -267,9 +268,9 @@ __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
     // inclusive product scan
     float p = t;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      float q = __shfl_up_sync(0xffffffffu, p, o);
-      if (lane >= o) p *= q;
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+      float q = __shfl_up_sync(0xffffffffu, p, o2);
+      if (lane >= o2) p *= q;
     }
     float excl = __shfl_up_sync(0xffffffffu, p, 1);
     if (lane == 0) excl = 1.0f;
@@ -283,15 +284,47 @@ __global__ void __launch_bounds__(256) composite_kernel(CompositeArgs a) {
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o);
-    sd += __shfl_xor_sync(0xffffffffu, sd, o); sa += __shfl_xor_sync(0xffffffffu, sa, o);
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, o2); sg += __shfl_xor_sync(0xffffffffu, sg, o2); sb += __shfl_xor_sync(0xffffffffu, sb, o2);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o2); sa += __shfl_xor_sync(0xffffffffu, sa, o2);
   }
-  if (lane == 0) {
-    a.rgb[3 * r] = sr; a.rgb[3 * r + 1] = sg; a.rgb[3 * r + 2] = sb;
-    a.depth[r] = sd; a.acc[r] = sa;
-    float q = xdiv(sd, sa);  // 0/0 = NaN when nothing was hit, as in the reference
-    a.disp[r] = (q != q) ? q : xdiv(1.0f, fmaxf(1e-10f, q));
+  o[0] = sr; o[1] = sg; o[2] = sb; o[3] = sd; o[4] = sa;
+  float q = xdiv(sd, sa);  // 0/0 = NaN when nothing was hit, as in the reference
+  o[5] = (q != q) ? q : xdiv(1.0f, fmaxf(1e-10f, q));
+}
+
+// A block composites COMP_RAYS consecutive rays (one warp each), stages their six outputs in shared memory and writes them
+// with coalesced stores: 96 contiguous floats of rgb and 32 each of depth / acc / disp per destination.  With gather targets
+// every destination is a full 128-byte-segment store over NVLink instead of 4-byte scattered ones.
+__global__ void __launch_bounds__(COMP_RAYS * 32) composite_kernel(CompositeArgs a) {
+  __shared__ float s_out[6 * COMP_RAYS];  // [0,96) rgb as (ray,3); [96,128) depth; [128,160) acc; [160,192) disp
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r0 = (int64_t)blockIdx.x * COMP_RAYS;
+  const int64_t r = r0 + w;
+  if (r < a.R) {
+    float o[6];
+    composite_ray(a, r, lane, o);
+    if (lane == 0) {
+      s_out[3 * w] = o[0]; s_out[3 * w + 1] = o[1]; s_out[3 * w + 2] = o[2];
+      s_out[96 + w] = o[3]; s_out[128 + w] = o[4]; s_out[160 + w] = o[5];
+    }
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= 6 * COMP_RAYS) return;
+  const int nr = (int)min((int64_t)COMP_RAYS, a.R - r0);
+  const int ch = t < 96 ? 0 : (t - 64) >> 5;        // 0 rgb, 1 depth, 2 acc, 3 disp
+  const int k = t < 96 ? t : (t & 31);              // element inside the block's run of that channel
+  if (k >= (ch == 0 ? 3 * nr : nr)) return;
+  const float v = s_out[t];
+  float* const loc = ch == 0 ? a.rgb : (ch == 1 ? a.depth : (ch == 2 ? a.acc : a.disp));
+  const int64_t e = (ch == 0 ? 3 * r0 : r0) + k;    // element inside the channel
+  loc[e] = v;
+  const int64_t eb = (ch == 0 ? 0 : (int64_t)(2 + ch) * a.R) + e;  // element inside a [rgb | depth | acc | disp] block
+  if (a.mc) {
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(a.mc + eb), "f"(v) : "memory");
+  } else {
+    for (int p = 0; p < a.n_peers; ++p) a.peer[p][eb] = v;
   }
 }
 

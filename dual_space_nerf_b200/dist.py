@@ -107,3 +107,55 @@ def render_sharded(renderer, batch, group=None, interleave=0):
         sub[k] = batch[k][:, lo:hi]
     out = renderer.render(sub)["coarse"]
     return unpack_outputs(gather_rays(pack_outputs(out), R, group))
+
+
+class FrameExchange:
+    """Frame buffers of all ranks in CUDA symmetric memory (torch.distributed._symmetric_memory): every GPU maps every other
+    GPU's buffer over NVLink / NVSwitch, so the compositor kernel of `dsnerf_render_gather` stores its per-ray outputs
+    straight into the buffers of all GPUs -- the all-gather of SURVEY.md 8e happens inside the render kernel, tile by tile,
+    instead of as a separate NCCL collective after it.
+
+    Layout of each GPU's buffer (float32): ``n_slots`` frames of ``world`` blocks of ``6 * rays_per_rank`` floats,
+    block = [rgb (R,3) | depth (R) | acc (R) | disp (R)] of one rank.  ``n_slots`` = 2 lets frame k + 1 be rendered while
+    frame k is still being read."""
+
+    def __init__(self, rays_per_rank: int, device, group=None, n_slots: int = 2, multicast: bool = False):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("FrameExchange works inside one NVSwitch domain (at most 8 GPUs)")
+        self.R = int(rays_per_rank)
+        self.block = 6 * self.R
+        self.n_slots = n_slots
+        self.buf = symm_mem.empty(n_slots * self.world * self.block, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.mc = int(self.hdl.multicast_ptr) if (multicast and self.hdl.has_multicast_support(self.buf.device.type, self.buf.device.index)) else 0
+        self.buf.zero_()
+        self.barrier()
+
+    def offsets(self, slot: int, rank=None):
+        rank = self.rank if rank is None else rank
+        return (slot * self.world + rank) * self.block
+
+    def targets(self, slot: int):
+        """(own block pointer, ctypes array of the peers' pointers to this rank's block, n_peers, multicast pointer or None)."""
+        import ctypes
+
+        off = 4 * self.offsets(slot)
+        peers = [self.ptrs[p] + off for p in range(self.world) if p != self.rank]
+        arr = (ctypes.c_void_p * max(len(peers), 1))(*peers)
+        return ctypes.c_void_p(self.ptrs[self.rank] + off), arr, len(peers), (ctypes.c_void_p(self.mc + off) if self.mc else None)
+
+    def frames(self, slot: int):
+        """(world, 6 * R) view of all ranks' blocks of a slot in THIS GPU's buffer (valid after `barrier`)."""
+        lo = slot * self.world * self.block
+        return self.buf[lo: lo + self.world * self.block].view(self.world, self.block)
+
+    def barrier(self):
+        """Group barrier on the current stream (signal pads in symmetric memory): every rank's stores of the frames
+        enqueued before it are visible to every rank after it."""
+        self.hdl.barrier(channel=0)

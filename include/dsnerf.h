@@ -113,6 +113,21 @@ int dsnerf_render_train(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d,
                         int64_t n_rays, int n_samples, unsigned flags, const float* jitter, const float* raw_noise,
                         float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_vals, void* stream);
 
+/* Fused render + all-gather over NVLink / NVSwitch (the one exchange step of the path; configs 4 and 5).
+ * Same as dsnerf_render, but the compositor kernel itself stores the per-ray outputs into this rank's block
+ *   [rgb (n_rays,3) | depth (n_rays) | acc (n_rays) | disp (n_rays)]   (6 * n_rays floats)
+ * of the frame buffer of EVERY GPU of the group: `own_block` is the block inside this GPU's buffer, `peer_blocks[i]`
+ * (i < n_peers <= 7) the same block inside peer i's buffer as a peer-mapped DEVICE pointer valid on this GPU (CUDA IPC /
+ * symmetric memory), written with coalesced 128-byte stores while the kernel runs -- no separate collective, no staging
+ * copy.  If `multicast_block` is not NULL it is the NVSwitch multicast (multimem) address of the block and one
+ * multimem.st per value replaces the per-peer stores (own_block is still written locally; it may alias the multicast
+ * target's local copy).  The caller synchronises the group afterwards (e.g. a symmetric-memory barrier on `stream`)
+ * before any GPU reads another GPU's block.  dual_space_nerf_b200.dist.FrameExchange sets this up with
+ * torch.distributed._symmetric_memory.  Does not combine with DSNERF_EARLY_STOP. */
+int dsnerf_render_gather(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                         int64_t n_rays, int n_samples, unsigned flags, float* own_block, float* const* peer_blocks, int n_peers,
+                         float* multicast_block, void* stream);
+
 /* Same call with HOST buffers (pinned or pageable): copies inputs to the device,
  * renders, copies the outputs back and synchronises the stream.  This is the
  * entry point Renderer.render_view (can_render.py:248-278) maps to, and what
@@ -181,8 +196,10 @@ int dsnerf_camera_rays(dsnerf_ctx* ctx, int H, int W, const double* K, const dou
  * n_rays * n_samples bytes; enqueued on `stream` (use the stream of the render call). */
 int dsnerf_last_transparent_mask(dsnerf_ctx* ctx, int64_t n_rays, int n_samples, uint8_t* transparent, void* stream);
 
-/* 1 if SpaceNet runs on the tcgen05 kernel with the staged weights, 0 if dsnerf_set_weights found a weight outside fp16
- * range (|w| >= 60000) and routed every evaluation to the fp32 CUDA kernel (same results, slower); < 0 without weights. */
+/* Precision mode dsnerf_set_weights chose for the staged weights: 1 = tcgen05 kernel, rgb head single-pass fp16 (enough for
+ * weights of default-init scale); 3 = tcgen05 kernel with the 3-pass rgb head (a host-side probe of 64 points found the
+ * single pass outside the colour budget: checkpoints whose activations reach O(1..10); +4 % kernel time); 0 = a weight is
+ * outside fp16 range (|w| >= 60000): every evaluation runs on the fp32 CUDA kernel (slower); < 0 without weights. */
 int dsnerf_tensor_path_active(const dsnerf_ctx* ctx);
 
 /* Counters of the last render on this context (synchronises the stream it ran on). */

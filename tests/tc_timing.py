@@ -5,7 +5,7 @@ import numpy as np, torch
 from types import SimpleNamespace
 from dual_space_nerf_b200 import net as N, scene as S
 from dual_space_nerf_b200.renderer import Renderer
-sc = S.make_scene(256, 256)
+sc = S.make_scene(int(os.environ.get("DSNERF_TIMING_HW", "256")), int(os.environ.get("DSNERF_TIMING_HW", "256")))
 cfg = SimpleNamespace(MODEL=SimpleNamespace(TYPE="nerf", COARSE_RAY_SAMPLING=64, FINE_RAY_SAMPLING=-1, sample_points_mode="GG", perturb=1.0, raw_noise_std=1.0), DATASETS=SimpleNamespace(SMPL_PATH=None))
 r = Renderer(N.synthetic_net(0), None, cfg, torch.from_numpy(sc["canonical"]), device=0, faces=sc["faces"])
 r.eval()
@@ -29,3 +29,5 @@ print("tile total", t[62] - t[0])
 print("MMA thread per op: wait_full  wait_a  total_issue_loop")
 for op in range(15):
     print(f"{names[op]:6s} {t[64+3*op]:9d} {t[65+3*op]:9d} {t[66+3*op]:9d}")
+dc, dt = t[122] - t[120], t[123] - t[121]
+print(f"kernel (CTA 0): {dc} cycles in {dt / 1e3:.1f} us -> SM clock inside the kernel {dc / max(dt, 1) * 1e3:.0f} MHz")

@@ -98,15 +98,15 @@ def test_pointwise_surface_vs_stages_golden(scene64, state_dict):
     color, dens, _ = r.net(pts6.reshape(-1, 6), rays6.reshape(-1, 6), frame_idx, batch_info=b)
     color, dens = color.cpu().numpy(), dens.cpu().numpy()[:, 0]
     _, st = oracle_run(scene64, state_dict, n, rays)
-    derr = np.abs(dens - g["density"]) / np.maximum(np.abs(g["density"]), 1.0)
+    derr = np.abs(dens - g["density"])  # absolute: the density head's terms (~10^2) cancel, see test_stage_ops_bit_exact_vs_golden
     cerr = np.abs(color - g["color"]).max(1)
     # the oracle's kink margin exists for the non-transparent samples only; the rest are checked with the plain bound, and
     # whatever exceeds it must be a sample that the fp32 SIMT kernel (no operand rounding at all) also moves
     loose = cerr > 2e-4
-    print(f"net.forward on {len(dens)} samples: max rel |d sigma| {derr.max():.2e}, max |d colour| {cerr.max():.2e}, over 2e-4: {int(loose.sum())}")
-    assert derr.max() < 3e-5
+    print(f"net.forward on {len(dens)} samples: max |d sigma| {derr.max():.2e}, max |d colour| {cerr.max():.2e}, over 2e-4: {int(loose.sum())}")
+    assert derr.max() < 5e-3
     assert loose.mean() < 0.003 and cerr.max() < C.KINK_RGB_BOUND
-    C.record("net.forward per-sample vs reference golden", {"sigma_rel_max": float(derr.max()), "colour_abs_max": float(cerr.max()),
+    C.record("net.forward per-sample vs reference golden", {"sigma_abs_max": float(derr.max()), "colour_abs_max": float(cerr.max()),
                                                             "samples_over_2e-4": int(loose.sum()), "samples": int(len(dens))})
     # density_only branch (model/spacenet.py:238-241)
     d_only = r.net(pts6.reshape(-1, 6), rays6.reshape(-1, 6), frame_idx, batch_info=b, density_only=True)
@@ -149,11 +149,11 @@ def test_query_volume_as_visualizer_calls_it(scene64, state_dict):
     act = ~g["mask"][:P]
     for i, code in enumerate(codes.tolist()):
         _, sig, _ = O.spacenet_forward(W, g["xyz_cano"][:P][act], W.embedding[code], pf, want_grad=False, density_only=True)
-        err = np.abs(dens[i, act, 0] - sig) / np.maximum(np.abs(sig), 1.0)
-        assert err.max() < 3e-5, (i, float(err.max()))
+        err = np.abs(dens[i, act, 0] - sig)
+        assert err.max() < 5e-3, (i, float(err.max()))
         assert np.all(dens[i, ~act, 0] == 0)
     assert np.abs(dens[0] - dens[1]).max() > 1e-2  # the two latent codes do differ
-    assert np.abs(dens[0, act, 0] - g["density"][:P][act]).max() / 170.0 < 3e-5  # entry 0 = the reference's own frame
+    assert np.abs(dens[0, act, 0] - g["density"][:P][act]).max() < 5e-3  # entry 0 = the reference's own frame
     with pytest.raises(ValueError):
         r.query_volume(pts6[..., :5], codes, None, b)
     with pytest.raises(ValueError):
@@ -259,9 +259,13 @@ def test_trained_magnitude_weights_and_fp16_range(state_dict):
     for mlp in ("tc", "simt"):
         r = make_renderer(sc, 32, net=net, mlp=mlp)
         out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
-        assert r.ctx.L.dsnerf_tensor_path_active(r.ctx.h) == 1
+        assert r.ctx.L.dsnerf_tensor_path_active(r.ctx.h) == 3  # the staging probe asked for the 3-pass rgb head
         _, st = oracle_run(sc, net.state_dict(), 32, rays)
         print(mlp, C.check_rays(out, g, kink_rays(st, 32), what=f"trained-magnitude weights vs reference golden [{mlp}]"))
+    assert make_renderer(sc, 32).ctx.L.dsnerf_tensor_path_active is not None
+    r0 = make_renderer(sc, 32)
+    r0.render(S.to_batch(sc, torch, rays=rays[:8]))
+    assert r0.ctx.L.dsnerf_tensor_path_active(r0.ctx.h) == 1  # default-init scale: single-pass rgb head
     # out-of-range weight: one hidden weight of 1e5 (fp16 max 65504), exactly cancelled by a dead ReLU input is not needed --
     # compare the routed path with the explicitly requested fp32 kernel: identical
     net2 = N.synthetic_net(0)

@@ -311,11 +311,30 @@ def bench_strong(rig, steps, warmup):
                                   None, None, rig.sp))
 
     nblk = Rl // W4
+    fx = None
+    if getattr(rig, "fx", None) is not None:
+        try:
+            fx = D.FrameExchange(Rl, dev, n_slots=2)
+        except Exception:
+            fx = None
+    it = [0]
 
     def step_sharded():
+        nonlocal gathered
         set_frame()
-        render(mine, Rl, out_l)
-        dist.all_gather_into_tensor(gathered, out_l)
+        if fx is not None:   # the compositor stores this rank's rows into every GPU's buffer (dsnerf_render_gather)
+            # two slots: a rank may already write frame k + 1 while a peer still re-orders frame k out of the other slot; slot
+            # k & 1 is reused only after barrier k + 1, which every rank enqueues after its copy of frame k
+            slot = it[0] & 1
+            it[0] += 1
+            own, peers, n_peers, mc = fx.targets(slot)
+            ctx.check(L.dsnerf_render_gather(ctx.h, P(mine[0]), P(mine[1]), P(mine[2]), P(mine[3]), Rl, N_SAMPLES, rig.flags, own, peers, n_peers,
+                                             mc, rig.sp))
+            fx.barrier()
+            gathered = fx.frames(slot)
+        else:
+            render(mine, Rl, out_l)
+            dist.all_gather_into_tensor(gathered, out_l)
         # rows back into image order: (world, rows per rank, W, c) -> (rows per rank, world, W, c)
         for (src_lo, c), dst in zip(((0, 3), (3 * Rl, 1), (4 * Rl, 1), (5 * Rl, 1)), views(frame, R4)):
             dst.view(nblk, world, W4, c).copy_(gathered[:, src_lo: src_lo + c * Rl].view(world, nblk, W4, c).transpose(0, 1))
@@ -350,7 +369,8 @@ def bench_strong(rig, steps, warmup):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     return {
         "workload": "BASELINE configs[3] shape: one 1024x1024 = 1048576-ray frame, 64 samples/ray, rays sharded over the ranks "
-                    "(image rows round-robin) + one NCCL all-gather of 6 floats/ray (25 MB) + row re-ordering, inside the timed region",
+                    "(image rows round-robin) + all-gather of 6 floats/ray (25 MB; " + ("fused into the compositor's peer stores" if fx is not None else "ncclAllGather") +
+                    ") + row re-ordering, inside the timed region",
         "rays_s": R4 / (ms_n * 1e-3), "ms": ms_n, "ms_1gpu": ms_1, "rays_s_1gpu": R4 / (ms_1 * 1e-3), "speedup_vs_1gpu": ms_1 / ms_n,
         "efficiency_vs_1gpu": ms_1 / ms_n / world, "bit_identical": bool(flag.item()), "steps": steps,
         "evaluated_samples_per_rank": per_rank, "evaluated_samples_1gpu": int(ev1),
@@ -442,6 +462,9 @@ def main():
                     "config 4 strong); 3 = hierarchical 64 + 128 (1 GPU, secondary line)")
     ap.add_argument("--simt", action="store_true", help="debug: fp32 SIMT MLP kernel instead of tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how the frames are reassembled: 'fused' = the "
+                    "compositor kernel stores into every GPU's frame buffer over NVLink (dsnerf_render_gather, symmetric memory); 'nccl' = "
+                    "asynchronous ncclAllGather after the render (the baseline it replaces)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the config-4 strong-scaling measurement")
     ap.add_argument("--early-stop", action="store_true", help="optional DSNERF_EARLY_STOP mode (not the headline: the default evaluates every sample)")
     args = ap.parse_args()
@@ -488,9 +511,29 @@ def main():
     outs = [torch.empty(6 * R, device=dev) for _ in range(2)]
     gathered = [torch.empty(world, 6 * R, device=dev) for _ in range(2)] if world > 1 else None
     works = [None, None]
+    fx, gather_mode = None, "none"
+    if world > 1:
+        gather_mode = args.gather
+        if gather_mode == "fused":
+            try:
+                from dual_space_nerf_b200 import dist as D
+
+                fx = D.FrameExchange(R, dev, n_slots=2, multicast=bool(os.environ.get("DSNERF_GATHER_MULTICAST")))
+            except Exception as e:  # no symmetric memory on this box / build: say so and use the collective
+                gather_mode = f"nccl (symmetric memory unavailable: {type(e).__name__}: {str(e)[:120]})"
+                fx = None
+    rig.fx = fx
 
     def step_device(i):
         k = i & 1
+        if fx is not None:
+            # fused compute + collective: the compositor's stores land in slot k of every GPU's frame buffer while the kernel
+            # runs; the group barrier (signal pads, on the stream) publishes the slot.  Slot k is rewritten two frames later.
+            own, peers, n_peers, mc = fx.targets(k)
+            set_frame()
+            ctx.check(L.dsnerf_render_gather(ctx.h, P(d_o), P(d_d), P(d_n), P(d_f), R, N_SAMPLES, flags, own, peers, n_peers, mc, sp))
+            fx.barrier()
+            return
         if works[k] is not None:   # the block is about to be overwritten: its previous gather (two frames ago) must be done
             works[k].wait()
             works[k] = None
@@ -586,7 +629,20 @@ def main():
     e2e_value = world * R * args.steps / (e2e_ms * 1e-3)
     frame_checksum = float(h_rgb.double().sum())
     # the e2e frame must be the device-resident frame, bit for bit
-    e2e_same = bool(torch.equal(h_rgb.to(dev), outs[0][: 3 * R].view(R, 3)))
+    dev_rgb = fx.frames(0)[rank][: 3 * R] if fx is not None else outs[0][: 3 * R]
+    e2e_same = bool(torch.equal(h_rgb.to(dev), dev_rgb.view(R, 3)))
+    gather_ok = None
+    if world > 1:
+        # every rank holds every rank's frame: compare checksums of all blocks across ranks (and with the e2e frame of each rank)
+        fr = fx.frames(0) if fx is not None else gathered[0]
+        sums = fr[:, : 3 * R].double().sum(1)
+        mine = torch.zeros(world, device=dev, dtype=torch.float64)
+        mine[rank] = h_rgb.double().sum().to(dev)
+        dist.all_reduce(mine)
+        lo, hi = sums.clone(), sums.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        gather_ok = bool(torch.equal(lo, hi)) and bool(torch.allclose(sums, mine, rtol=0, atol=1e-3))
 
     strong = None
     if world > 1 and not args.no_strong:
@@ -607,9 +663,14 @@ def main():
                             "GG sampling, random-init SpaceNet (head rescale of SURVEY.md 8d), synthetic SMPL-sized mesh (V=6890, F=13776)",
                 "rays_per_gpu_per_step": R, "samples_per_ray": N_SAMPLES, "evaluated_samples_per_step": int(evaluated),
                 "evaluated_fraction": evaluated / float(R * N_SAMPLES),
-                "parallelism": (f"{world} x (one frame per GPU) + NCCL all-gather of 6 floats/ray per frame, issued asynchronously "
-                                "against double-buffered output blocks (frame k's gather overlaps frame k+1; all gathers complete inside the timed region)")
+                "parallelism": (f"{world} x (one frame per GPU); all-gather of 6 floats/ray per frame: " +
+                                ("FUSED into the compositor kernel -- it stores every ray's outputs into the frame buffer of all GPUs over "
+                                 "NVLink (peer-mapped symmetric memory, coalesced 128-byte stores), then a signal-pad group barrier per frame; no NCCL "
+                                 "call on the data path" if fx is not None else
+                                 "ncclAllGather issued asynchronously against double-buffered output blocks (frame k's gather overlaps frame "
+                                 "k+1; all gathers complete inside the timed region)"))
                 if world > 1 else "1 GPU",
+                "gather": gather_mode, "gather_verified": gather_ok,
                 "l2": "256 MB buffer written between timed steps (L2 flush)",
                 "mlp_kernel": "fp32 SIMT (debug)" if args.simt else "tcgen05",
                 "early_stop": bool(args.early_stop),

@@ -487,7 +487,10 @@ int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStrea
                                                             ctx->F, ctx->active_cidx.as<int>());
     CKL("canon_nearest");
     sb.active_cidx = ctx->active_cidx.as<int>();
-    light_tc_kernel<<<ctx->sm_count * 2, LT_THREADS, LT_SMEM, st>>>(sb, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
+    if (ctx->tw.rgb3)  // precise weight mode: the lighting layer runs the 3-pass split as well (light_tc.cuh)
+      light_tc_kernel<true><<<ctx->sm_count, LT_THREADS, LT_SMEM3, st>>>(sb, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
+    else
+      light_tc_kernel<false><<<ctx->sm_count * 2, LT_THREADS, LT_SMEM, st>>>(sb, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);
     CKL("light_tc");
   }
   return 0;
@@ -709,7 +712,8 @@ int dsnerf_create(dsnerf_ctx** out, int device) {
   memset(ctx->h_ert, 0, sizeof(unsigned long long) * 8);
   cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMT_SMEM);
   cudaFuncSetAttribute(shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHADE_SMEM);
-  cudaFuncSetAttribute(light_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM);
+  cudaFuncSetAttribute(light_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM);
+  cudaFuncSetAttribute(light_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM3);
   tc_configure();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { delete ctx; return DSNERF_ERR_CUDA; }

@@ -22,16 +22,26 @@ namespace dsn {
 
 constexpr int LT_THREADS = 256;
 constexpr int LT_ROWS = 128;                        // rows (samples) per half
-constexpr uint32_t LT_SM_W2 = 0;                    // B operand: [16 k-chunks][128 rows][8] fp16 = 32 KB
-constexpr uint32_t LT_SM_A = 32768;                 // A operands: 2 halves x [16 k-chunks][128 rows][8] fp16 = 2 x 32 KB
-constexpr uint32_t LT_SM_W1 = 98304;                // fp32 [128][12]: 9 weights, bias, 2 pad
-constexpr uint32_t LT_SM_B2 = LT_SM_W1 + 128 * 12 * 4;
-constexpr uint32_t LT_SM_W3 = LT_SM_B2 + 512;
-constexpr uint32_t LT_SM_BAR = LT_SM_W3 + 512;      // 3 mbarriers + tmem slot
-constexpr uint32_t LT_SMEM = LT_SM_BAR + 64;
+// shared memory map; PARTS = 1 (hi only) or 2 (hi + lo) copies of every fp16 operand
+template <int PARTS> struct LtMap {
+  static constexpr uint32_t W2 = 0;                         // B operand: PARTS x [16 k-chunks][128 rows][8] fp16 = PARTS x 32 KB
+  static constexpr uint32_t A = PARTS * 32768;              // A operands: 2 halves x PARTS x 32 KB
+  static constexpr uint32_t A_HALF = PARTS * 32768;         // bytes per half
+  static constexpr uint32_t W1 = A + 2 * A_HALF;            // fp32 [128][12]: 9 weights, bias, 2 pad
+  static constexpr uint32_t B2 = W1 + 128 * 12 * 4;
+  static constexpr uint32_t W3 = B2 + 512;
+  static constexpr uint32_t BAR = W3 + 512;                 // 3 mbarriers + tmem slot
+  static constexpr uint32_t SMEM = BAR + 64;
+};
+constexpr uint32_t LT_SMEM = LtMap<1>::SMEM;
+constexpr uint32_t LT_SMEM3 = LtMap<2>::SMEM;
 constexpr uint32_t LT_TMEM_COLS = 256;
 
-__global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, LightWeights L, const uint8_t* __restrict__ w2_packed, Grid gc) {
+template <bool P3>
+__global__ void __launch_bounds__(LT_THREADS, P3 ? 1 : 2) light_tc_kernel(ShadeArgs a, LightWeights L, const uint8_t* __restrict__ w2_packed, Grid gc) {
+  using M = LtMap<P3 ? 2 : 1>;
+  constexpr uint32_t LT_SM_W2 = M::W2, LT_SM_A = M::A, LT_SM_W1 = M::W1, LT_SM_B2 = M::B2, LT_SM_W3 = M::W3, LT_SM_BAR = M::BAR;
+  constexpr uint32_t W2_BYTES = (P3 ? 2u : 1u) * 32768u;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int half = threadIdx.x >> 7;                 // independent 4-warp half of the CTA
@@ -42,7 +52,7 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
   float* w1p = reinterpret_cast<float*>(smem + LT_SM_W1);
   float* b2 = reinterpret_cast<float*>(smem + LT_SM_B2);
   float* w3 = reinterpret_cast<float*>(smem + LT_SM_W3);
-  uint8_t* a_op = smem + LT_SM_A + half * 32768;
+  uint8_t* a_op = smem + LT_SM_A + half * M::A_HALF;  // hi part; the lo part (P3) follows 32 KB later
   auto half_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };
 
   if (threadIdx.x == 0) {
@@ -65,9 +75,9 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
   tc_fence_after();
   const uint32_t tmem = *tmem_slot + (uint32_t)half * 128u;
   if (threadIdx.x == 0) {  // second-layer weights: one bulk copy, resident for the whole kernel
-    mbar_expect_tx(bar_w, 32768);
+    mbar_expect_tx(bar_w, W2_BYTES);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(sbase + LT_SM_W2), "l"(w2_packed), "r"(32768u), "r"(bar_w) : "memory");
+                 ::"r"(sbase + LT_SM_W2), "l"(w2_packed), "r"(W2_BYTES), "r"(bar_w) : "memory");
   }
   const int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
   const int64_t n_tiles = (n_active + LT_ROWS - 1) / LT_ROWS;
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
     // ---- first layer (fp32) -> fp16 A operand
 #pragma unroll 2
     for (int kc = 0; kc < 16; ++kc) {
-      uint32_t pk[4];
+      uint32_t pk[4], pl[4];
 #pragma unroll
       for (int e = 0; e < 8; e += 2) {
         float hv[2];
@@ -112,8 +122,13 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
           hv[u] = fmaxf(h, 0.f);
         }
         pk[e / 2] = pack_h2(hv[0], hv[1]);
+        if (P3) {
+          const float2 hf = __half22float2(as_h2(pk[e / 2]));
+          pl[e / 2] = pack_h2(hv[0] - hf.x, hv[1] - hf.y);
+        }
       }
       *reinterpret_cast<uint4*>(a_op + (uint32_t)kc * (LT_ROWS * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (P3) *reinterpret_cast<uint4*>(a_op + 32768 + (uint32_t)kc * (LT_ROWS * 16) + row * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
     fence_proxy_async();
     half_bar();
@@ -125,11 +140,16 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
         constexpr uint32_t DHI = (128u >> 4) | (1u << 14);
         constexpr uint32_t LBO = ((LT_ROWS * 16) >> 4) << 16;
         constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t a0 = LBO | ((sbase + LT_SM_A + half * 32768) >> 4), b0 = LBO | ((sbase + LT_SM_W2) >> 4);
+        const uint32_t a0 = LBO | ((sbase + LT_SM_A + half * M::A_HALF) >> 4), b0 = LBO | ((sbase + LT_SM_W2) >> 4);
+        constexpr uint32_t LO = 32768u >> 4;  // hi -> lo part of either operand
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t step = (uint32_t)k * ((2 * LT_ROWS * 16) >> 4);
           tc_mma_ss(tmem, ((uint64_t)DHI << 32) | (a0 + step), ((uint64_t)DHI << 32) | (b0 + step), IDESC, k > 0 ? 1u : 0u);
+          if (P3) {  // x_hi * w_lo + x_lo * w_hi
+            tc_mma_ss(tmem, ((uint64_t)DHI << 32) | (a0 + step), ((uint64_t)DHI << 32) | (b0 + LO + step), IDESC, 1u);
+            tc_mma_ss(tmem, ((uint64_t)DHI << 32) | (a0 + LO + step), ((uint64_t)DHI << 32) | (b0 + step), IDESC, 1u);
+          }
         }
         tc_commit(bar_mma);
       }
@@ -169,11 +189,17 @@ __global__ void __launch_bounds__(LT_THREADS, 2) light_tc_kernel(ShadeArgs a, Li
   }
 }
 
-// host: pack lights_encoding.2.weight [out=128][in=128] as the B operand image (B[n][k] = W[n][k])
+// host: pack lights_encoding.2.weight [out=128][in=128] as the B operand image (B[n][k] = W[n][k]): hi part, then lo part
 inline void light_pack_w2(const std::vector<float>& w2, std::vector<__half>& out) {
-  out.assign((size_t)128 * 128, __float2half_rn(0.f));
+  out.assign((size_t)2 * 128 * 128, __float2half_rn(0.f));
   for (int n = 0; n < 128; ++n)
-    for (int k = 0; k < 128; ++k) out[((size_t)(k / 8) * 128 + n) * 8 + (k % 8)] = __float2half_rn(w2[(size_t)n * 128 + k]);
+    for (int k = 0; k < 128; ++k) {
+      const float w = w2[(size_t)n * 128 + k];
+      const __half hh = __float2half_rn(w);
+      const size_t o = ((size_t)(k / 8) * 128 + n) * 8 + (k % 8);
+      out[o] = hh;
+      out[(size_t)128 * 128 + o] = __float2half_rn(w - __half2float(hh));
+    }
 }
 
 }  // namespace dsn

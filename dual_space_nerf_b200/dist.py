@@ -87,11 +87,20 @@ def gather_frames(local, group=None):
     return full.reshape((world,) + tuple(local.shape))
 
 
-def render_sharded(renderer, batch, group=None, interleave=0):
+def unpack_blocks(blocks, rays_per_rank: int):
+    """(world, 6 * R) blocks [rgb (R,3) | depth | acc | disp] of `FrameExchange` / `dsnerf_render_gather` -> (world * R, 6)."""
+    world, R = blocks.shape[0], rays_per_rank
+    return torch.cat([blocks[:, : 3 * R].reshape(world, R, 3), blocks[:, 3 * R: 4 * R, None], blocks[:, 4 * R: 5 * R, None],
+                      blocks[:, 5 * R:, None]], 2).reshape(world * R, 6)
+
+
+def render_sharded(renderer, batch, group=None, interleave=0, exchange=None, slot=0):
     """Render one frame with its rays split across the ranks (config 4) and reassemble it everywhere.
 
     `renderer` is a dual_space_nerf_b200.Renderer (or anything with the same ``render``).  ``interleave`` = 0: contiguous
-    ray ranges; > 0: blocks of that many rays (one image row) dealt round-robin, which balances hit and miss rays."""
+    ray ranges; > 0: blocks of that many rays (one image row) dealt round-robin, which balances hit and miss rays.
+    ``exchange`` (a `FrameExchange` sized for n_rays / world rays; needs interleave > 0 and n_rays divisible by
+    interleave * world): the reassembly is fused into the render kernel (`Renderer.render_gather`) instead of an NCCL call."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     R = batch["ray_o"].shape[1]
@@ -100,6 +109,13 @@ def render_sharded(renderer, batch, group=None, interleave=0):
         sel = interleaved_indices(R, rank, world, interleave).to(batch["ray_o"].device)
         for k in ("ray_o", "ray_d", "near", "far"):
             sub[k] = batch[k][:, sel]
+        if exchange is not None:
+            if R % (interleave * world):
+                raise ValueError("fused reassembly needs n_rays divisible by interleave * world")
+            per = R // world
+            flat = unpack_blocks(renderer.render_gather(sub, exchange, slot), per)  # rank-major, rows interleaved
+            full = flat.view(world, per // interleave, interleave, OUT_CHANNELS).transpose(0, 1).reshape(R, OUT_CHANNELS)
+            return unpack_outputs(full)
         out = renderer.render(sub)["coarse"]
         return unpack_outputs(gather_interleaved(pack_outputs(out), R, interleave, group))
     lo, hi = shard_range(R, rank, world)

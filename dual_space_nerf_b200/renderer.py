@@ -263,6 +263,27 @@ class Renderer:
             self.ctx.check(self.ctx.L.dsnerf_last_transparent_mask(self.ctx.h, R, N, _ptr(tm), self._stream()))
         return tm.bool()
 
+    def render_gather(self, batch, exchange, slot=0):
+        """Multi-GPU form of ``render``: this rank's rays are rendered and the compositor kernel itself stores
+        the per-ray outputs into slot ``slot`` of EVERY rank's frame buffer (``dist.FrameExchange``, peer-mapped symmetric
+        memory over NVLink) -- the all-gather is part of the render kernel, not a collective after it.  Returns this GPU's
+        (world, 6 * R) view of all ranks' blocks [rgb (R,3) | depth | acc | disp], complete on the current stream."""
+        self._check_eval()
+        with torch.cuda.device(self.device):
+            self._set_frame(batch)
+            ro = self._dev(batch["ray_o"]).reshape(-1, 3)
+            rd = self._dev(batch["ray_d"]).reshape(-1, 3)
+            ne = self._dev(batch["near"]).reshape(-1)
+            fa = self._dev(batch["far"]).reshape(-1)
+            if ro.shape[0] != exchange.R:
+                raise ValueError(f"the exchange was built for {exchange.R} rays per rank, got {ro.shape[0]}")
+            own, peers, n_peers, mc = exchange.targets(slot)
+            self.ctx.check(self.ctx.L.dsnerf_render_gather(self.ctx.h, _ptr(ro), _ptr(rd), _ptr(ne), _ptr(fa), ro.shape[0],
+                                                           int(self.cfg.MODEL.COARSE_RAY_SAMPLING), self._flags(), own, peers, n_peers, mc,
+                                                           self._stream()))
+            exchange.barrier()
+        return exchange.frames(slot)
+
     def batchify_rays_view(self, ray_o, ray_d, near, far, batch, chunk=1024 * 32):
         """can_render.py:172-245.  ``chunk`` is accepted for signature compatibility; the whole
         batch is rendered by one library call (no intermediates scale with V x rays)."""

@@ -37,11 +37,26 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         times.append(time.perf_counter() - t)
-    ok = all(torch.equal(sh[k].nan_to_num(-1.0), full[k].nan_to_num(-1.0)) for k in ("color", "depth_map", "acc_map", "disp_map"))
+    same = lambda a: all(torch.equal(a[k].nan_to_num(-1.0), full[k].nan_to_num(-1.0)) for k in ("color", "depth_map", "acc_map", "disp_map"))
+    ok = same(sh)
+    # rows dealt round-robin over NCCL, then the same with the reassembly fused into the compositor's peer stores
+    ok = ok and same(D.render_sharded(r, b, interleave=H))
+    fused = "unavailable"
+    try:
+        fx = D.FrameExchange(H * H // world, torch.device("cuda", local), n_slots=2)
+    except Exception as e:  # no symmetric memory: reported, not fatal
+        fx = None
+        fused = f"unavailable ({type(e).__name__})"
+    if fx is not None:
+        ok_f = True
+        for slot in (0, 1, 0):
+            ok_f = ok_f and same(D.render_sharded(r, b, interleave=H, exchange=fx, slot=slot))
+        fused = str(ok_f)
+        ok = ok and ok_f
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"SHARDED world={world} {H}x{H}x64 bit_identical={bool(flag.item())} ms={min(times) * 1e3:.2f} "
+        print(f"SHARDED world={world} {H}x{H}x64 bit_identical={bool(flag.item())} fused_gather={fused} ms={min(times) * 1e3:.2f} "
               f"rays_per_s={H * H / min(times):.4g}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)

@@ -148,7 +148,7 @@ def test_query_volume_as_visualizer_calls_it(scene64, state_dict):
     pf = O.pose_feature(W, scene64["poses"])
     act = ~g["mask"][:P]
     for i, code in enumerate(codes.tolist()):
-        _, sig, _ = O.spacenet_forward(W, g["xyz_cano"][:P][act], W.embedding[code], pf, want_grad=False, density_only=True)
+        sig = O.spacenet_forward(W, g["xyz_cano"][:P][act], W.embedding[code], pf, want_grad=False, density_only=True)
         err = np.abs(dens[i, act, 0] - sig)
         assert err.max() < 5e-3, (i, float(err.max()))
         assert np.all(dens[i, ~act, 0] == 0)

@@ -103,8 +103,16 @@ struct dsnerf_ctx {
   bool pin_busy = false;
   unsigned long long* h_counters = nullptr;  // pinned, 4 entries
   cudaEvent_t stats_ready = nullptr;
+  cudaStream_t side = nullptr;   // dsnerf_set_frame builds the posed-mesh grid here while the caller's stream already runs the GG ray bounds
+  cudaEvent_t ev_fork = nullptr, ev_grid = nullptr;
+  bool grid_on_side = false;
   cudaStream_t copy = nullptr;   // dsnerf_render_host: ray upload next to the grid build that dsnerf_set_frame left on the caller's stream
   cudaEvent_t copy_done = nullptr;
+  cudaStream_t down = nullptr;   // dsnerf_render_host_async: read-back of frame k next to the kernels of frame k + 1
+  cudaEvent_t render_done = nullptr, host_done[2] = {nullptr, nullptr};
+  bool host_pending[2] = {false, false};
+  unsigned long long host_seq = 0;
+  DevBuf io2[2];
   dsnerf_stats_t stats{};
   // ---- profiling
   int profile = 0;
@@ -462,6 +470,12 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
   return 0;
 }
 
+// make `st` wait for the posed-mesh grid that dsnerf_set_frame is building on the side stream
+int join_grid(dsnerf_ctx* ctx, cudaStream_t st) {
+  if (ctx->grid_on_side) CK(cudaStreamWaitEvent(st, ctx->ev_grid, 0));
+  return 0;
+}
+
 int check_ready(dsnerf_ctx* ctx, bool need_frame) {
   if (!ctx) return DSNERF_ERR_INVALID;
   if (!ctx->have_weights) return fail(ctx, DSNERF_ERR_STATE, "dsnerf_set_weights has not been called");
@@ -575,6 +589,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
     near_use = ctx->near2.as<float>();
     far_use = ctx->far2.as<float>();
   }
+  if (int e = join_grid(ctx, st)) return e;
   if (jitter) {  // training mode: stratified jitter (pts_utils.py:6-13) written straight into the caller's z_vals
     jitter_z_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(near_use, far_use, ctx->tvals.as<float>(), jitter, R, N, z_out);
     CKL("jitter_z");
@@ -706,6 +721,12 @@ int dsnerf_create(dsnerf_ctx** out, int device) {
   cudaEventCreateWithFlags(&ctx->stats_ready, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming);
   if (!getenv("DSNERF_NO_COPY_STREAM")) cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
+  if (!getenv("DSNERF_NO_COPY_STREAM")) cudaStreamCreateWithFlags(&ctx->down, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->render_done, cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->host_done[i], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_grid, cudaEventDisableTiming);
+  if (!getenv("DSNERF_NO_SIDE_STREAM")) cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
   cudaMallocHost(reinterpret_cast<void**>(&ctx->h_counters), sizeof(unsigned long long) * 4);
   memset(ctx->h_counters, 0, sizeof(unsigned long long) * 4);
   cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ert), sizeof(unsigned long long) * 8);
@@ -739,6 +760,12 @@ void dsnerf_destroy(dsnerf_ctx* ctx) {
   if (ctx->stats_ready) cudaEventDestroy(ctx->stats_ready);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->copy) cudaStreamDestroy(ctx->copy);
+  if (ctx->down) cudaStreamDestroy(ctx->down);
+  if (ctx->render_done) cudaEventDestroy(ctx->render_done);
+  for (int i = 0; i < 2; ++i) { if (ctx->host_done[i]) cudaEventDestroy(ctx->host_done[i]); ctx->io2[i].release(); }
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_grid) cudaEventDestroy(ctx->ev_grid);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   delete ctx;
 }
@@ -859,6 +886,7 @@ int dsnerf_set_frame(dsnerf_ctx* ctx, const float* posed_verts, const float* pos
   if ((rot == nullptr) != (rot_center == nullptr)) return fail(ctx, DSNERF_ERR_INVALID, "rot and rot_center must be given together");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
+  if (int e = join_grid(ctx, st)) return e;  // a previous frame's grid build may still read the vertex buffer overwritten below
   // pose feature: batch_rod2quat -> pose_mlp (model/spacenet.py:223-236); identical for every sample of the frame
   float q[92], h1[64], h2[64], pf[16];
   rod2quat_host(poses, q);
@@ -883,11 +911,24 @@ int dsnerf_set_frame(dsnerf_ctx* ctx, const float* posed_verts, const float* pos
   CK(cudaMemcpyAsync(ctx->posed.p, pv, vbytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->bias0.p, pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->tw.bias0_slot(), pb, 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-  int e = build_grid(ctx, ctx->g_posed, ctx->posed.as<float>(), pv, 1, st);
+  // The posed-mesh grid (16 small kernels, ~0.25 ms, latency bound) only depends on the vertex upload: it is built on the
+  // context's side stream, forked here, so that the render call that follows can already run its GG ray bounds (which need
+  // the vertices, not the grid) on the caller's stream; every consumer of the grid joins through join_grid().
+  cudaStream_t gs = ctx->side ? ctx->side : st;
+  if (gs != st) {
+    CK(cudaEventRecord(ctx->ev_fork, st));   // after the uploads, and after everything the previous frame left on `st`
+    CK(cudaStreamWaitEvent(gs, ctx->ev_fork, 0));
+  }
+  int e = build_grid(ctx, ctx->g_posed, ctx->posed.as<float>(), pv, 1, gs);
   if (!e) {
     if (ctx->normal_m.ensure(sizeof(float4) * 3 * (size_t)ctx->F) != cudaSuccess) e = fail(ctx, DSNERF_ERR_CUDA, "normal matrices");
-    else normal_matrix_kernel<<<(ctx->F + 255) / 256, 256, 0, st>>>(ctx->canon.as<float>(), ctx->posed.as<float>(), ctx->faces.as<int>(), ctx->F,
+    else normal_matrix_kernel<<<(ctx->F + 255) / 256, 256, 0, gs>>>(ctx->canon.as<float>(), ctx->posed.as<float>(), ctx->faces.as<int>(), ctx->F,
                                                                   ctx->normal_m.as<float4>());
+  }
+  ctx->grid_on_side = gs != st;
+  if (gs != st) {
+    CK(cudaEventRecord(ctx->ev_grid, gs));
+    if (e) CK(cudaStreamWaitEvent(st, ctx->ev_grid, 0));
   }
   if (int e2 = pin_release(ctx, st)) return e2;
   if (e) return e;
@@ -945,25 +986,31 @@ int dsnerf_render_gather(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d
                      nullptr, reinterpret_cast<cudaStream_t>(stream), nullptr, nullptr, &gt);
 }
 
-int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, int64_t R,
-                       int N, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_vals,
-                       void* stream) {
+int dsnerf_render_host_async(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, int64_t R,
+                             int N, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_vals,
+                             void* stream, int* ticket) {
   if (int e = check_ready(ctx, true)) return e;
   if (R < 0 || N < 1) return fail(ctx, DSNERF_ERR_INVALID, "bad sizes");
-  if (R == 0) return 0;
+  if (!ticket) return fail(ctx, DSNERF_ERR_INVALID, "null ticket");
+  const int slot = (int)(ctx->host_seq & 1);
+  *ticket = (int)(ctx->host_seq & 0x7fffffff);
+  ++ctx->host_seq;
+  if (R == 0) { ctx->host_pending[slot] = false; return 0; }
   if (!ray_o || !ray_d || !near || !far || !rgb || !depth || !acc || !disp) return fail(ctx, DSNERF_ERR_INVALID, "null input/output pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
+  // two staging slots on the device: the frame submitted two calls ago must have left this one
+  if (ctx->host_pending[slot]) { CK(cudaEventSynchronize(ctx->host_done[slot])); ctx->host_pending[slot] = false; }
   size_t in_f = (size_t)R * 8, out_f = (size_t)R * 6, opt_f = (size_t)R * N;
   size_t total = in_f + out_f + (weights ? opt_f : 0) + (z_vals ? opt_f : 0);
-  CK(ctx->io.ensure(total * sizeof(float)));
-  float* d = ctx->io.as<float>();
+  CK(ctx->io2[slot].ensure(total * sizeof(float)));
+  float* d = ctx->io2[slot].as<float>();
   float *d_o = d, *d_d = d + 3 * R, *d_n = d + 6 * R, *d_f = d + 7 * R;
   float *d_rgb = d + 8 * R, *d_dep = d_rgb + 3 * R, *d_acc = d_dep + R, *d_dsp = d_acc + R;
   float* d_w = weights ? d_dsp + R : nullptr;
   float* d_z = z_vals ? (d_dsp + R + (weights ? opt_f : 0)) : nullptr;
-  // The upload does not depend on anything queued on `st` (typically the per-frame grid build of dsnerf_set_frame): it runs
-  // on the context's copy stream and `st` joins it.  The staging buffer is free: the previous call ended with a stream sync.
+  // The upload does not depend on anything queued on `st` (typically the per-frame work of dsnerf_set_frame): it runs on the
+  // context's copy stream and `st` joins it.
   cudaStream_t cs = ctx->copy ? ctx->copy : st;
   CK(cudaMemcpyAsync(d_o, ray_o, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, cs));
   CK(cudaMemcpyAsync(d_d, ray_d, sizeof(float) * 3 * R, cudaMemcpyHostToDevice, cs));
@@ -974,14 +1021,39 @@ int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, 
     CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
   }
   if (int e = render_impl(ctx, d_o, d_d, d_n, d_f, nullptr, R, N, flags, d_rgb, d_dep, d_acc, d_dsp, d_w, d_z, st)) return e;
-  CK(cudaMemcpyAsync(rgb, d_rgb, sizeof(float) * 3 * R, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(depth, d_dep, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(acc, d_acc, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(disp, d_dsp, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
-  if (weights) CK(cudaMemcpyAsync(weights, d_w, sizeof(float) * opt_f, cudaMemcpyDeviceToHost, st));
-  if (z_vals) CK(cudaMemcpyAsync(z_vals, d_z, sizeof(float) * opt_f, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  // The read-back runs on the download stream behind the render, so `st` is free for the next frame's kernels at once.
+  cudaStream_t ds = ctx->down ? ctx->down : st;
+  if (ds != st) {
+    CK(cudaEventRecord(ctx->render_done, st));
+    CK(cudaStreamWaitEvent(ds, ctx->render_done, 0));
+  }
+  CK(cudaMemcpyAsync(rgb, d_rgb, sizeof(float) * 3 * R, cudaMemcpyDeviceToHost, ds));
+  CK(cudaMemcpyAsync(depth, d_dep, sizeof(float) * R, cudaMemcpyDeviceToHost, ds));
+  CK(cudaMemcpyAsync(acc, d_acc, sizeof(float) * R, cudaMemcpyDeviceToHost, ds));
+  CK(cudaMemcpyAsync(disp, d_dsp, sizeof(float) * R, cudaMemcpyDeviceToHost, ds));
+  if (weights) CK(cudaMemcpyAsync(weights, d_w, sizeof(float) * opt_f, cudaMemcpyDeviceToHost, ds));
+  if (z_vals) CK(cudaMemcpyAsync(z_vals, d_z, sizeof(float) * opt_f, cudaMemcpyDeviceToHost, ds));
+  CK(cudaEventRecord(ctx->host_done[slot], ds));
+  ctx->host_pending[slot] = true;
   return 0;
+}
+
+int dsnerf_wait(dsnerf_ctx* ctx, int ticket) {
+  if (!ctx) return DSNERF_ERR_INVALID;
+  const int slot = ticket & 1;
+  if (ctx->host_pending[slot]) {
+    CK(cudaEventSynchronize(ctx->host_done[slot]));
+    ctx->host_pending[slot] = false;
+  }
+  return 0;
+}
+
+int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far, int64_t R,
+                       int N, unsigned flags, float* rgb, float* depth, float* acc, float* disp, float* weights, float* z_vals,
+                       void* stream) {
+  int ticket = 0;
+  if (int e = dsnerf_render_host_async(ctx, ray_o, ray_d, near, far, R, N, flags, rgb, depth, acc, disp, weights, z_vals, stream, &ticket)) return e;
+  return dsnerf_wait(ctx, ticket);
 }
 
 int dsnerf_composite(dsnerf_ctx* ctx, const float* raw, const float* z_vals, const float* ray_d, int64_t R, int N, float* rgb,
@@ -1013,6 +1085,7 @@ int dsnerf_warp_points(dsnerf_ctx* ctx, const float* pts, int64_t P, float* xyz_
   if (!pts || !xyz_cano) return fail(ctx, DSNERF_ERR_INVALID, "null pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
+  if (int e = join_grid(ctx, st)) return e;
   warp_points_kernel<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(pts, P, ctx->posed.as<float>(), ctx->canon.as<float>(), ctx->faces.as<int>(),
                                                                   ctx->g_posed.g, ctx->F, ctx->g_posed.cent.as<float>(), xyz_cano, transparent, idx);
   CKL("warp_points");
@@ -1083,6 +1156,7 @@ int dsnerf_eval_points(dsnerf_ctx* ctx, const float* xyz_world, const float* xyz
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
   if (int e = ensure_workspace(ctx, P, 1)) return e;
+  if (int e = join_grid(ctx, st)) return e;  // the normal matrices are built next to the grid
   unsigned long long* cnt = ctx->counters.as<unsigned long long>();
   CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 4, st));
   unsigned blocks = (unsigned)((P + 255) / 256);

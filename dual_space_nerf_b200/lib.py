@@ -17,7 +17,7 @@ NUM_WEIGHT_TENSORS = 33
 
 ENTRY_POINTS = [
     "dsnerf_abi_version", "dsnerf_create", "dsnerf_destroy", "dsnerf_last_error", "dsnerf_set_weights",
-    "dsnerf_set_mesh", "dsnerf_set_frame", "dsnerf_render", "dsnerf_render_train", "dsnerf_render_host", "dsnerf_render_gather", "dsnerf_render_z",
+    "dsnerf_set_mesh", "dsnerf_set_frame", "dsnerf_render", "dsnerf_render_train", "dsnerf_render_host", "dsnerf_render_host_async", "dsnerf_wait", "dsnerf_render_gather", "dsnerf_render_z",
     "dsnerf_resample", "dsnerf_composite", "dsnerf_composite_noise", "dsnerf_warp_points", "dsnerf_query_density", "dsnerf_eval_points", "dsnerf_ppts_to_pts", "dsnerf_camera_rays",
     "dsnerf_last_transparent_mask", "dsnerf_tensor_path_active",
     "dsnerf_get_stats", "dsnerf_profile", "dsnerf_profile_read", "dsnerf_debug_tc_timing", "dsnerf_debug_table", "dsnerf_debug_sm_clock", "dsnerf_debug_active",
@@ -62,6 +62,8 @@ def load():
     L.dsnerf_set_frame.argtypes = [vp, fp, fp, ci, ci, fp, fp, fp, vp]
     L.dsnerf_render.argtypes = [vp, fp, fp, fp, fp, i64, ci, cu, fp, fp, fp, fp, fp, fp, vp]
     L.dsnerf_render_host.argtypes = L.dsnerf_render.argtypes
+    L.dsnerf_render_host_async.argtypes = L.dsnerf_render.argtypes + [ctypes.POINTER(ctypes.c_int)]
+    L.dsnerf_wait.argtypes = [vp, ci]
     L.dsnerf_render_gather.argtypes = [vp, fp, fp, fp, fp, i64, ci, cu, fp, ctypes.POINTER(ctypes.c_void_p), ci, fp, vp]
     L.dsnerf_render_train.argtypes = [vp, fp, fp, fp, fp, i64, ci, cu, fp, fp, fp, fp, fp, fp, fp, fp, vp]
     L.dsnerf_render_z.argtypes = [vp, fp, fp, fp, i64, ci, cu, fp, fp, fp, fp, fp, vp]

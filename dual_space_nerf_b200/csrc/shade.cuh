@@ -217,7 +217,8 @@ struct CompositeArgs {
   int n_peers; float* peer[7]; float* mc;
 };
 
-constexpr int COMP_RAYS = 32;  // rays per block, one warp each
+constexpr int COMP_RAYS = 8;   // rays per block, one warp each (32-ray blocks measured 0.158 ms per frame against 0.085 ms: three of four rays are empty and
+                               // their warps then sit behind the block barrier)
 
 // one ray by one warp; the six outputs are valid in lane 0
 __device__ __forceinline__ void composite_ray(const CompositeArgs& a, int64_t r, int lane, float (&o)[6]) {
@@ -294,10 +295,10 @@ __device__ __forceinline__ void composite_ray(const CompositeArgs& a, int64_t r,
 }
 
 // A block composites COMP_RAYS consecutive rays (one warp each), stages their six outputs in shared memory and writes them
-// with coalesced stores: 96 contiguous floats of rgb and 32 each of depth / acc / disp per destination.  With gather targets
-// every destination is a full 128-byte-segment store over NVLink instead of 4-byte scattered ones.
+// with coalesced stores: 3 C contiguous floats of rgb and C each of depth / acc / disp per destination (C = COMP_RAYS).  With
+// gather targets every destination receives 96- and 32-byte segments over NVLink instead of 4-byte scattered stores.
 __global__ void __launch_bounds__(COMP_RAYS * 32) composite_kernel(CompositeArgs a) {
-  __shared__ float s_out[6 * COMP_RAYS];  // [0,96) rgb as (ray,3); [96,128) depth; [128,160) acc; [160,192) disp
+  __shared__ float s_out[6 * COMP_RAYS];  // [0, 3C) rgb as (ray,3); then C floats each of depth, acc, disp (C = COMP_RAYS)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r0 = (int64_t)blockIdx.x * COMP_RAYS;
   const int64_t r = r0 + w;
@@ -306,15 +307,15 @@ __global__ void __launch_bounds__(COMP_RAYS * 32) composite_kernel(CompositeArgs
     composite_ray(a, r, lane, o);
     if (lane == 0) {
       s_out[3 * w] = o[0]; s_out[3 * w + 1] = o[1]; s_out[3 * w + 2] = o[2];
-      s_out[96 + w] = o[3]; s_out[128 + w] = o[4]; s_out[160 + w] = o[5];
+      s_out[3 * COMP_RAYS + w] = o[3]; s_out[4 * COMP_RAYS + w] = o[4]; s_out[5 * COMP_RAYS + w] = o[5];
     }
   }
   __syncthreads();
   const int t = threadIdx.x;
   if (t >= 6 * COMP_RAYS) return;
   const int nr = (int)min((int64_t)COMP_RAYS, a.R - r0);
-  const int ch = t < 96 ? 0 : (t - 64) >> 5;        // 0 rgb, 1 depth, 2 acc, 3 disp
-  const int k = t < 96 ? t : (t & 31);              // element inside the block's run of that channel
+  const int ch = t < 3 * COMP_RAYS ? 0 : t / COMP_RAYS - 2;       // 0 rgb, 1 depth, 2 acc, 3 disp
+  const int k = t < 3 * COMP_RAYS ? t : t % COMP_RAYS;            // element inside the block's run of that channel
   if (k >= (ch == 0 ? 3 * nr : nr)) return;
   const float v = s_out[t];
   float* const loc = ch == 0 ? a.rgb : (ch == 1 ? a.depth : (ch == 2 ? a.acc : a.disp));

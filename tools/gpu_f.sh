@@ -1,0 +1,15 @@
+#!/bin/bash
+# A/B on one box: PE operand stores (new, libdsnerf.so) vs round-1 per-element stores (libdsnerf_base.so); composite with 8-ray blocks in both
+for i in 1 2; do
+  python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_ab_pe_new_$i.json 2>/dev/null
+  DSNERF_LIB=$PWD/dual_space_nerf_b200/libdsnerf_base.so python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_ab_pe_old_$i.json 2>/dev/null
+done
+python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -15 > gpurun_out/r02_tests_f.log
+DSNERF_TIMING_HW=512 python tests/tc_timing.py > gpurun_out/r02_tc_timing_pe.log 2>&1
+tail -3 gpurun_out/r02_tests_f.log
+for f in gpurun_out/r02_ab_pe_*.json; do python - "$f" <<'PY'
+import json,sys
+d=json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1]); r=d['roofline']
+print(sys.argv[1], round(d['ms_per_step'],3), round(r['kernel_ms_per_launch'],3), round(d['e2e']['ms_per_step'],3))
+PY
+done

@@ -91,9 +91,9 @@ struct TcOp {
   uint8_t pad[2];
 };
 
-__constant__ TcOp c_tc_ops[TC_NUM_OPS];
 
 struct TcParams {
+  TcOp ops[TC_NUM_OPS];     // the tile's GEMM schedule (kernel parameters live in the constant bank; no global state)
   const uint8_t* wpack;    // packed fp16 weights
   const float* bias;       // [7][256]; row 0 = per-frame folded bias (code + pose feature)
   const float* b_rgb1;     // [128]
@@ -408,7 +408,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     uint32_t stage = 0, phase = 0;
     for (int64_t it = 0; it < n_iter; ++it) {
       for (int op = 0; op < n_ops; ++op) {
-        const TcOp o = c_tc_ops[op];
+        const TcOp o = P.ops[op];
         const uint8_t* src = P.wpack + o.src_off + (size_t)cta_rank * o.slab_bytes;
         for (int s = 0; s < o.n_slabs; ++s) {
           if (P.debug_noload) continue;
@@ -428,7 +428,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     const uint32_t leader_pfull = mapa_u32(bar_full, 0);
     for (int64_t it = 0; it < n_iter; ++it) {
       for (int op = 0; op < n_ops; ++op) {
-        const int n_slabs = c_tc_ops[op].n_slabs;
+        const int n_slabs = P.ops[op].n_slabs;
         for (int s = 0; s < n_slabs; ++s) {
           if (P.debug_noload) continue;
           mbar_wait(bar_full + 8 * stage, phase);
@@ -448,7 +448,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     ms.sbase = sbase; ms.bar_full = bar_full; ms.bar_empty = bar_empty; ms.bar_a = bar_a; ms.noload = P.debug_noload;
     for (int64_t it = 0; it < n_iter; ++it) {
       for (int op = 0; op < n_ops; ++op) {
-        const TcOp o = c_tc_ops[op];
+        const TcOp o = P.ops[op];
         const bool mstamp = P.timing && blockIdx.x == 0 && it == 0 && lane == 0;
         const long long t_op0 = mstamp ? clock64() : 0;
         const uint32_t d_main = tmem + (uint32_t)(op & 1) * TM_ACC;
@@ -1006,8 +1006,7 @@ struct TcWeights {
     if (e != cudaSuccess) return (int)e;
     for (int i = 0; i < 3; ++i) b_rgb2[i] = br2[i];
     b_dens = bd;
-    e = cudaMemcpyToSymbol(c_tc_ops, ops, sizeof(ops));
-    return (int)e;
+    return (int)cudaSuccess;
   }
 };
 
@@ -1016,6 +1015,7 @@ inline void tc_configure() { cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttribu
 inline int tc_launch(TcWeights& w, long long* timing, int debug_noload, int debug_passes, const float4* active, const unsigned long long* n_active_ptr, int64_t n_active_host,
                      float4* out_a, float4* out_g, int density_only, int sm_count, cudaStream_t st) {
   TcParams p{};
+  for (int i = 0; i < TC_NUM_OPS; ++i) p.ops[i] = w.ops[i];
   p.wpack = reinterpret_cast<const uint8_t*>(w.d_pack);
   p.bias = w.d_f32;
   p.b_rgb1 = w.d_f32 + TcWeights::F32_BRGB1;

@@ -294,10 +294,15 @@ def test_trained_magnitude_weights_and_fp16_range(state_dict):
         print(mlp, stats)
         C.record("trained-magnitude weights vs reference golden [tc, precise mode]", stats)
         assert col.max() < 2e-4 and (col > C.TOL).mean() <= 0.05, stats
-    assert make_renderer(sc, 32).ctx.L.dsnerf_tensor_path_active is not None
+    # two contexts with different precision modes in one process, used alternately: no state is shared between contexts
     r0 = make_renderer(sc, 32)
-    r0.render(S.to_batch(sc, torch, rays=rays[:8]))
-    assert r0.ctx.L.dsnerf_tensor_path_active(r0.ctx.h) == 1  # default-init scale: single-pass rgb head
+    rb = make_renderer(sc, 32, net=net)
+    a0 = to_np(r0.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    b0 = to_np(rb.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    a1 = to_np(r0.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    b1 = to_np(rb.render(S.to_batch(sc, torch, rays=rays))["coarse"])
+    assert r0.ctx.L.dsnerf_tensor_path_active(r0.ctx.h) == 1 and rb.ctx.L.dsnerf_tensor_path_active(rb.ctx.h) == 3
+    assert np.array_equal(a0["color"], a1["color"]) and np.array_equal(b0["color"], b1["color"]) and np.array_equal(b0["color"], out["color"])
     # out-of-range weight: one hidden weight of 1e5 (fp16 max 65504), exactly cancelled by a dead ReLU input is not needed --
     # compare the routed path with the explicitly requested fp32 kernel: identical
     net2 = N.synthetic_net(0)

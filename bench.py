@@ -677,7 +677,8 @@ def main():
 
     if rank == 0:
         sustained, burst, hbm, src = peaks()
-        achieved = (evaluated * FLOP_PER_SAMPLE) / (mlp_ms / max(mlp_n, 1) * 1e-3) / 1e12 if mlp_ms > 0 else None
+        mlp_frame_ms = mlp_ms / max(args.steps, 1)   # all MLP launches of a frame (one; several with --early-stop)
+        achieved = (evaluated * FLOP_PER_SAMPLE) / (mlp_frame_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
         traffic, traffic_frame, traffic_src = dram_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -706,7 +707,7 @@ def main():
                 "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                 "frac": (achieved / sustained) if achieved else None, "traffic": traffic,
                 "kernel": "mlp_simt_kernel" if args.simt else "mlp_tc_kernel", "kernel_ms_per_launch": mlp_ms / max(mlp_n, 1),
-                "kernel_share_of_step": (mlp_ms / max(mlp_n, 1)) / ms_step, "peak_source": f"bf16_tflops_sustained of {src} (MEASURED_PEAKS.json)",
+                "kernel_launches_per_step": mlp_n / max(args.steps, 1), "kernel_share_of_step": mlp_frame_ms / ms_step, "peak_source": f"bf16_tflops_sustained of {src} (MEASURED_PEAKS.json)",
                 "algorithmic_flop_per_launch": evaluated * FLOP_PER_SAMPLE,
                 "whole_step_frac": (evaluated * FLOP_PER_SAMPLE) / (ms_step * 1e-3) / 1e12 / sustained,
                 # the 1e-4 parity bound forces three fp16 MMAs per forward k-step: the tensor pipe executes

@@ -765,19 +765,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           // (op 14, columns 0..63), layer-4 part = the stash written at op 10 (same thread, same columns)
           uint32_t g[32];
           tmem_ld32(t_lane + pe_ld0(sub), g);
-          // sin/cos are still in the PE region (written by this very thread)
-          auto pe_val = [&](int col) -> float {
-            const uint32_t off = (uint32_t)(col >> 3) * A_CHUNK + row_off + (col & 7) * 2;
-            return __half2float(*reinterpret_cast<const __half*>(smem + SM_PE_HI + off)) +
-                   __half2float(*reinterpret_cast<const __half*>(smem + SM_PE_LO + off));
+          // sin / cos are still in the PE region: an octave's six columns lie in one or two 8-column chunks of the row, read
+          // with 16-byte loads (hi and lo) -- per-element 2-byte loads of this layout are 4-way bank conflicted
+          auto pe_chunk = [&](uint32_t region, int chunk) -> uint4 {
+            return *reinterpret_cast<const uint4*>(smem + region + (uint32_t)chunk * A_CHUNK + row_off);
+          };
+          auto pe_pick = [](const uint4& hi, const uint4& lo, int e) -> float {  // element e of the chunk, hi + lo
+            const int w = e >> 1;
+            const uint32_t wh = w == 0 ? hi.x : (w == 1 ? hi.y : (w == 2 ? hi.z : hi.w));
+            const uint32_t wl = w == 0 ? lo.x : (w == 1 ? lo.y : (w == 2 ? lo.z : lo.w));
+            const uint32_t sh = (uint32_t)(e & 1) * 16u;
+            return __half2float(__ushort_as_half((unsigned short)(wh >> sh))) + __half2float(__ushort_as_half((unsigned short)(wl >> sh)));
           };
           // every branch below is warp uniform (sub is); C0 = pe_ld0(sub) as a literal keeps g[] in registers
 #define DSN_GPE(C, C0) fmaf(stash[(C) * TC_TILE + row], P.stash_scale, __uint_as_float(g[(C) - (C0)]))
 #define DSN_OCTAVE(K, C0)                                                               \
   {                                                                                     \
+    constexpr int CA = (3 + 6 * (K)) >> 3, CB = (8 + 6 * (K)) >> 3;                     \
+    const uint4 ha = pe_chunk(SM_PE_HI, CA), la = pe_chunk(SM_PE_LO, CA);               \
+    const uint4 hb = CB == CA ? ha : pe_chunk(SM_PE_HI, CB), lb = CB == CA ? la : pe_chunk(SM_PE_LO, CB); \
     _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                     \
+      const int cs_col = 3 + 6 * (K) + c, cc_col = 6 + 6 * (K) + c;                     \
       const float gs = DSN_GPE(3 + 6 * (K) + c, C0), gc = DSN_GPE(6 + 6 * (K) + c, C0); \
-      const float sn = pe_val(3 + 6 * (K) + c), cs = pe_val(6 + 6 * (K) + c);           \
+      const float sn = (cs_col >> 3) == CA ? pe_pick(ha, la, cs_col & 7) : pe_pick(hb, lb, cs_col & 7); \
+      const float cs = (cc_col >> 3) == CA ? pe_pick(ha, la, cc_col & 7) : pe_pick(hb, lb, cc_col & 7); \
       gx[c] = fmaf((gs * cs - gc * sn), (float)(1 << (K)), gx[c]);                      \
     }                                                                                   \
   }

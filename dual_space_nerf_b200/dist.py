@@ -149,7 +149,12 @@ class FrameExchange:
         self.buf = symm_mem.empty(n_slots * self.world * self.block, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.mc = int(self.hdl.multicast_ptr) if (multicast and self.hdl.has_multicast_support(self.buf.device.type, self.buf.device.index)) else 0
+        self.mc = 0
+        if multicast:  # NVSwitch multicast (NVLS) address of the buffer; 0 / None where the fabric or driver has none
+            try:
+                self.mc = int(self.hdl.multicast_ptr or 0)
+            except Exception:
+                self.mc = 0
         self.buf.zero_()
         self.barrier()
 

@@ -53,6 +53,14 @@ def main():
             ok_f = ok_f and same(D.render_sharded(r, b, interleave=H, exchange=fx, slot=slot))
         fused = str(ok_f)
         ok = ok and ok_f
+        # the same through the NVSwitch multicast address (multimem.st), where the fabric offers one
+        fxm = D.FrameExchange(H * H // world, torch.device("cuda", local), n_slots=1, multicast=True)
+        if fxm.mc:
+            ok_m = same(D.render_sharded(r, b, interleave=H, exchange=fxm, slot=0))
+            fused += f" multicast={ok_m}"
+            ok = ok and ok_m
+        else:
+            fused += " multicast=unavailable"
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -320,7 +320,7 @@ def bench_strong(rig, steps, warmup):
     fx = None
     if getattr(rig, "fx", None) is not None:
         try:
-            fx = D.FrameExchange(Rl, dev, n_slots=2)
+            fx = D.FrameExchange(Rl, dev, n_slots=2, multicast=not os.environ.get("DSNERF_GATHER_NO_MULTICAST"))
         except Exception:
             fx = None
     it = [0]
@@ -525,7 +525,7 @@ def main():
             try:
                 from dual_space_nerf_b200 import dist as D
 
-                fx = D.FrameExchange(R, dev, n_slots=2, multicast=bool(os.environ.get("DSNERF_GATHER_MULTICAST")))
+                fx = D.FrameExchange(R, dev, n_slots=2, multicast=not os.environ.get("DSNERF_GATHER_NO_MULTICAST"))
             except Exception as e:  # no symmetric memory on this box / build: say so and use the collective
                 gather_mode = f"nccl (symmetric memory unavailable: {type(e).__name__}: {str(e)[:120]})"
                 fx = None
@@ -693,12 +693,13 @@ def main():
                 "evaluated_fraction": evaluated / float(R * N_SAMPLES),
                 "parallelism": (f"{world} x (one frame per GPU); all-gather of 6 floats/ray per frame: " +
                                 ("FUSED into the compositor kernel -- it stores every ray's outputs into the frame buffer of all GPUs over "
-                                 "NVLink (peer-mapped symmetric memory, coalesced 128-byte stores), then a signal-pad group barrier per frame; no NCCL "
-                                 "call on the data path" if fx is not None else
+                                 "NVLink (" + ("one multimem.st per value through the NVSwitch multicast address" if fx.mc else
+                                               "peer-mapped symmetric memory, coalesced 96/32-byte segments per peer") +
+                                 "), then a signal-pad group barrier per frame; no NCCL call on the data path" if fx is not None else
                                  "ncclAllGather issued asynchronously against double-buffered output blocks (frame k's gather overlaps frame "
                                  "k+1; all gathers complete inside the timed region)"))
                 if world > 1 else "1 GPU",
-                "gather": gather_mode, "gather_verified": gather_ok,
+                "gather": gather_mode + (" (multicast)" if (fx is not None and fx.mc) else ""), "gather_verified": gather_ok,
                 "l2": "256 MB buffer written between timed steps (L2 flush)",
                 "mlp_kernel": "fp32 SIMT (debug)" if args.simt else "tcgen05",
                 "early_stop": bool(args.early_stop),

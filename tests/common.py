@@ -16,10 +16,11 @@ TOL = 1e-4
 # correct fp32 implementations (even the reference on CPU vs GPU) may disagree on
 # its normal by O(0.1) and on its colour by O(1e-3).  Rays containing such a
 # sample are exempt from the 1e-4 RGB bound, must stay within KINK_RGB_BOUND, and
-# their number is bounded and reported.  Depth/acc never depend on the normal
+# the number of rays above 1e-4 is capped at max(3, 0.2 %) and recorded (measured:
+# 2 of 12 288 rays of the 512x512x64 frame, worst 2.2e-4; profiles/r02_parity.json).  Depth/acc never depend on the normal
 # and are held to 1e-4 everywhere.
 KINK_MARGIN = 2e-6
-KINK_RGB_BOUND = 2e-2
+KINK_RGB_BOUND = 5e-3
 
 
 def golden(name):
@@ -80,7 +81,7 @@ def check_rays(out, ref, kink_ray=None, tol=TOL, what="", strict=False):
         unexplained = bad & ~kink_ray
         assert not unexplained.any(), f"{what} rgb err {col[unexplained].max():.3e} on {unexplained.sum()} rays with no ReLU kink"
         assert col.max() <= KINK_RGB_BOUND, f"{what} rgb err {col.max():.3e} exceeds the kink bound"
-        assert bad.sum() <= max(3, 0.02 * len(col)), f"{what} too many kink rays over tolerance: {bad.sum()}"
+        assert bad.sum() <= max(3, 0.002 * len(col)), f"{what} too many kink rays over tolerance: {bad.sum()}"
         stats["rgb_max_nokink"] = float(col[~kink_ray].max()) if (~kink_ray).any() else 0.0
     if strict:
         stats["kink_rays"] = n_kink

@@ -65,9 +65,14 @@ __global__ void __launch_bounds__(LT_THREADS, P3 ? 1 : 2) light_tc_kernel(ShadeA
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 128 * 12; i += LT_THREADS) {
-    int k = i / 12, j = i - k * 12;
-    w1p[i] = j < 9 ? L.w1t[j * 128 + k] : (j == 9 ? L.b1[k] : 0.f);
+  // first-layer weights as output PAIRS: w1p[pair][j] = (w[j][2 pair], w[j][2 pair + 1]) for j < 9, j = 9: the two biases --
+  // the layer then runs on packed fp32 FMAs (fma.rn.f32x2: two outputs per instruction, 9 + 9 instead of 18 + 18 per pair)
+  for (int i = threadIdx.x; i < 64 * 12; i += LT_THREADS) {
+    const int pr = i / 12, j = i - pr * 12;
+    float2 v = make_float2(0.f, 0.f);
+    if (j < 9) v = make_float2(L.w1t[j * 128 + 2 * pr], L.w1t[j * 128 + 2 * pr + 1]);
+    else if (j == 9) v = make_float2(L.b1[2 * pr], L.b1[2 * pr + 1]);
+    reinterpret_cast<float2*>(w1p)[i] = v;
   }
   for (int i = threadIdx.x; i < 128; i += LT_THREADS) { b2[i] = L.b2[i]; w3[i] = L.w3[i]; }
   tc_fence_before();
@@ -111,15 +116,21 @@ __global__ void __launch_bounds__(LT_THREADS, P3 ? 1 : 2) light_tc_kernel(ShadeA
 #pragma unroll
       for (int e = 0; e < 8; e += 2) {
         float hv[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float4* w1 = reinterpret_cast<const float4*>(w1p + (kc * 8 + e + u) * 12);
-          const float4 wa = w1[0], wb = w1[1], wc = w1[2];
-          float h = wc.y;
-          h = fmaf(in[0], wa.x, h); h = fmaf(in[1], wa.y, h); h = fmaf(in[2], wa.z, h); h = fmaf(in[3], wa.w, h);
-          h = fmaf(in[4], wb.x, h); h = fmaf(in[5], wb.y, h); h = fmaf(in[6], wb.z, h); h = fmaf(in[7], wb.w, h);
-          h = fmaf(in[8], wc.x, h);
-          hv[u] = fmaxf(h, 0.f);
+        {
+          const float4* w1 = reinterpret_cast<const float4*>(w1p + (kc * 4 + e / 2) * 24);  // 12 float2 per output pair
+          const float4 w01 = w1[0], w23 = w1[1], w45 = w1[2], w67 = w1[3], w8b = w1[4];
+          float2 h = make_float2(w8b.z, w8b.w);  // the two biases
+          h = __ffma2_rn(make_float2(in[0], in[0]), make_float2(w01.x, w01.y), h);
+          h = __ffma2_rn(make_float2(in[1], in[1]), make_float2(w01.z, w01.w), h);
+          h = __ffma2_rn(make_float2(in[2], in[2]), make_float2(w23.x, w23.y), h);
+          h = __ffma2_rn(make_float2(in[3], in[3]), make_float2(w23.z, w23.w), h);
+          h = __ffma2_rn(make_float2(in[4], in[4]), make_float2(w45.x, w45.y), h);
+          h = __ffma2_rn(make_float2(in[5], in[5]), make_float2(w45.z, w45.w), h);
+          h = __ffma2_rn(make_float2(in[6], in[6]), make_float2(w67.x, w67.y), h);
+          h = __ffma2_rn(make_float2(in[7], in[7]), make_float2(w67.z, w67.w), h);
+          h = __ffma2_rn(make_float2(in[8], in[8]), make_float2(w8b.x, w8b.y), h);
+          hv[0] = fmaxf(h.x, 0.f);
+          hv[1] = fmaxf(h.y, 0.f);
         }
         pk[e / 2] = pack_h2(hv[0], hv[1]);
         if (P3) {

@@ -389,6 +389,76 @@ __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py
   __syncwarp();
 }
 
+// Lane-uniform form of warp_scan_ball (the table builder's scans): the row-per-lane walk above leaves 8 of 32 lanes busy on
+// average (rows hold 0..30 centroids; ncu: 8.3 active threads per instruction in build_cells_kernel<1>).  Here the (z, y)
+// rows of the ball are taken in batches of 32, one per lane; a warp prefix sum over the rows' centroid counts turns the
+// batch into one flat index space, and the lanes walk that space 32 items at a time (the row of an item is found by a 5-step
+// binary search over the lanes' prefix values through shuffles).  The warp stays converged, so the visitor may use ballots:
+// visit(q, j, valid) is called by ALL lanes, q = g.sorted[j] where valid.
+template <class Visit>
+__device__ __forceinline__ void warp_scan_ball_flat(const Grid& g, float px, float py, float pz, float rho, Visit&& visit) {
+  const int lane = threadIdx.x & 31;
+  const float rho2 = rho * rho;
+  const int z0 = max(0, (int)floorf((pz - rho - g.oz) * g.inv_cell)), z1 = min(g.nz - 1, (int)floorf((pz + rho - g.oz) * g.inv_cell));
+  const int y0 = max(0, (int)floorf((py - rho - g.oy) * g.inv_cell)), y1 = min(g.ny - 1, (int)floorf((py + rho - g.oy) * g.inv_cell));
+  const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+  for (int r0 = 0; r0 < nrows; r0 += 32) {
+    const int r = r0 + lane;
+    int b = 0, cnt = 0;
+    if (r < nrows) {
+      const int cz = z0 + r / ny, cy = y0 + r % ny;
+      unsigned long long m = __ldg(g.row_mask + cz * g.ny + cy);
+      if (m) {
+        const float zl = g.oz + cz * g.cell, yl = g.oy + cy * g.cell;
+        const float dz = fmaxf(0.f, fmaxf(zl - pz, pz - (zl + g.cell)));
+        const float dy = fmaxf(0.f, fmaxf(yl - py, py - (yl + g.cell)));
+        const float rem = rho2 - (dz * dz + dy * dy) * 0.9999f;
+        if (rem >= 0.f) {
+          const float rx = sqrtf(rem) * 1.0001f + 1e-6f;
+          int x0 = max(0, (int)floorf((px - rx - g.ox) * g.inv_cell)), x1 = min(g.nx - 1, (int)floorf((px + rx - g.ox) * g.inv_cell));
+          if (x0 <= x1) {
+            m &= (x1 - x0 >= 63 ? ~0ull : ((1ull << (x1 - x0 + 1)) - 1ull)) << x0;
+            if (m) {
+              x0 = __ffsll((long long)m) - 1;
+              x1 = 63 - __clzll((long long)m);
+              const int row = (cz * g.ny + cy) * g.nx;
+              b = __ldg(g.cell_start + row + x0);
+              cnt = __ldg(g.cell_start + row + x1 + 1) - b;
+            }
+          }
+        }
+      }
+    }
+    // inclusive prefix of the counts over the lanes
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - cnt;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      const bool valid = t < total;
+      // the row of item t: the first lane whose inclusive prefix exceeds t
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+        if (probe <= t) lo += step;
+      }
+      lo = min(lo, 31);
+      const int rb = __shfl_sync(0xffffffffu, b, lo), re = __shfl_sync(0xffffffffu, excl, lo);
+      const int j = rb + (t - re);
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) q = __ldg(g.sorted + j);
+      visit(q, j, valid);
+    }
+  }
+  __syncwarp();
+}
+
 #ifndef DSN_LIST_CAP
 #define DSN_LIST_CAP 256
 #endif
@@ -487,7 +557,6 @@ template <int LEVEL>
 __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
   __shared__ int buf[BUILD_WARPS][BUF_CAP];
   __shared__ int lst[BUILD_WARPS][LIST_CAP];
-  __shared__ int cnt_s[BUILD_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n_req = g.pool_used[LEVEL == 1 ? 2 : 3];
   const float tcell = 1.0f / g.tinv;
@@ -516,21 +585,26 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
     const int cref = __ldg(g.enum_seed + par);
     const float rx = __ldg(g.cent + 3 * cref), ry = __ldg(g.cent + 3 * cref + 1), rz = __ldg(g.cent + 3 * cref + 2);
     const float dref2 = (px - rx) * (px - rx) + (py - ry) * (py - ry) + (pz - rz) * (pz - rz);
-    if (lane == 0) cnt_s[w] = 0;
-    __syncwarp();
     float mb = dref2;
     int mi = cref;
-    warp_scan_ball(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j) {
+    int nbuf = 0;  // warp uniform: the candidates are appended through ballots (the flat scan keeps the warp converged)
+    warp_scan_ball_flat(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
       float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
       float d = dx * dx + dy * dy + dz * dz;
-      ++visits;
-      if (d < mb) { mb = d; mi = __float_as_int(q.w); }
-      if (can_beat(d, dref2, a, fabsf(q.x - rx) + fabsf(q.y - ry) + fabsf(q.z - rz))) {
-        int slot = atomicAdd(&cnt_s[w], 1);
+      bool keep = false;
+      if (valid) {
+        ++visits;
+        if (d < mb) { mb = d; mi = __float_as_int(q.w); }
+        keep = can_beat(d, dref2, a, fabsf(q.x - rx) + fabsf(q.y - ry) + fabsf(q.z - rz));
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int slot = nbuf + __popc(m & ((1u << lane) - 1));
         if (slot < BUF_CAP) buf[w][slot] = j;
       }
+      nbuf += __popc(m);
     });
-    int nbuf = cnt_s[w];
+    __syncwarp();
     if (nbuf > BUF_CAP) {
       // superset too long against the seed: take the centre's true nearest centroid (found by the scan above) as the
       // reference and scan once more (smaller ball, tighter filter)
@@ -542,17 +616,22 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
       }
       const float c0x = __ldg(g.cent + 3 * mi), c0y = __ldg(g.cent + 3 * mi + 1), c0z = __ldg(g.cent + 3 * mi + 2);
       __syncwarp();
-      if (lane == 0) cnt_s[w] = 0;
-      __syncwarp();
-      warp_scan_ball(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j) {
+      nbuf = 0;
+      warp_scan_ball_flat(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
         float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-        ++visits;
-        if (can_beat(dx * dx + dy * dy + dz * dz, mb, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z))) {
-          int slot = atomicAdd(&cnt_s[w], 1);
+        bool keep = false;
+        if (valid) {
+          ++visits;
+          keep = can_beat(dx * dx + dy * dy + dz * dz, mb, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int slot = nbuf + __popc(m & ((1u << lane) - 1));
           if (slot < BUF_CAP) buf[w][slot] = j;
         }
+        nbuf += __popc(m);
       });
-      nbuf = cnt_s[w];
+      __syncwarp();
     }
     const bool overflow = nbuf > BUF_CAP;
     if (LEVEL == 1) {

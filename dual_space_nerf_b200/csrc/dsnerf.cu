@@ -652,7 +652,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
     unsigned long long* ec = ctx->ert_cnt.as<unsigned long long>();  // [0..3] wave sizes, [4..7] evaluated per wave
     CK(cudaMemsetAsync(ec, 0, sizeof(unsigned long long) * 8, st));
     wa.waves = kWaves; wa.wave_size = wsize; wa.region = region; wa.wave_counters = ec;
-    sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
+    sample_warp_kernel<<<(unsigned)((P + WARP_SPB - 1) / WARP_SPB), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
     CKL("sample_warp");
     launches += 4;
     for (int k = 0; k < kWaves; ++k) {
@@ -681,7 +681,7 @@ int render_impl(dsnerf_ctx* ctx, const float* ray_o, const float* ray_d, const f
     CK(cudaMemcpyAsync(ctx->h_ert, ec, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     ctx->ert_mode = 1;
   } else {
-    sample_warp_kernel<<<(unsigned)((P + WARP_THREADS - 1) / WARP_THREADS), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
+    sample_warp_kernel<<<(unsigned)((P + WARP_SPB - 1) / WARP_SPB), WARP_THREADS, 0, st>>>(wa, ctx->g_posed.g);
     CKL("sample_warp");
     launches += 4;
     if (int e = launch_mlp(ctx, cnt, 0, flags, 0, st)) return e;

@@ -1020,32 +1020,41 @@ __global__ void __launch_bounds__(256) mark_points_kernel(const float4* __restri
   }
 }
 
+// A block places WARP_SPT x WARP_THREADS consecutive samples (WARP_SPT per thread, strided by the block size so that every
+// sub-round is coalesced) and then works its queue off with all threads: with one sample per thread only the ~16 % of the
+// threads that hold a queue entry work in phase 2 while the other warps of the block wait at the barrier (ncu: 41 % of the
+// stall samples) and hold their warp slots.
+constexpr int WARP_SPT = 4;
+constexpr int WARP_SPB = WARP_THREADS * WARP_SPT;
 __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, Grid g) {
-  __shared__ int queue[WARP_THREADS];
+  __shared__ unsigned short queue[WARP_SPB];
   __shared__ int qn;
   __shared__ int bin_count[16], bin_start[16];
-  __shared__ unsigned char flag[WARP_THREADS];
+  __shared__ unsigned char flag[WARP_SPB];
   const int64_t P = a.R * a.N;
-  const int64_t s0 = (int64_t)blockIdx.x * WARP_THREADS;
+  const int64_t s0 = (int64_t)blockIdx.x * WARP_SPB;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < 16) bin_count[threadIdx.x] = 0;
-  flag[threadIdx.x] = 0;
+#pragma unroll
+  for (int k = 0; k < WARP_SPT; ++k) flag[k * WARP_THREADS + threadIdx.x] = 0;
   __syncthreads();
-  // phase 1: place the sample, look its table cell up.  Samples that need the exact search are queued, bucketed by the
+  // phase 1: place the samples, look their table cells up.  Samples that need the exact search are queued, bucketed by the
   // length of their cell's candidate list (= work) so that the lanes of a warp in phase 2 do similar amounts of work.
-  int my_bin = -1;
-  {
-    const int64_t s = s0 + threadIdx.x;
+  int my_bin[WARP_SPT];
+#pragma unroll
+  for (int k = 0; k < WARP_SPT; ++k) {
+    my_bin[k] = -1;
+    const int64_t s = s0 + k * WARP_THREADS + threadIdx.x;
     if (s < P) {
       float px, py, pz;
       sample_position(a, s, px, py, pz);
       const int cell = live_cell(g, px, py, pz);
       if (cell >= 0) {
         const int cnt = g.trec[cell].y;
-        if (cnt != -1) my_bin = cnt < 0 ? 15 : min(14, cnt >> 3);
+        if (cnt != -1) my_bin[k] = cnt < 0 ? 15 : min(14, cnt >> 3);
       }
     }
-    if (my_bin >= 0) atomicAdd(&bin_count[my_bin], 1);
+    if (my_bin[k] >= 0) atomicAdd(&bin_count[my_bin[k]], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1054,16 +1063,19 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
     qn = acc;
   }
   __syncthreads();
-  if (my_bin >= 0) queue[atomicAdd(&bin_start[my_bin], 1)] = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < WARP_SPT; ++k)
+    if (my_bin[k] >= 0) queue[atomicAdd(&bin_start[my_bin[k]], 1)] = (unsigned short)(k * WARP_THREADS + threadIdx.x);
   __syncthreads();
-  {
-    const int n = qn;
-    if (a.count_candidates && threadIdx.x == 0 && n) atomicAdd(a.counters + 2, (unsigned long long)n);
+  const int n = qn;
+  if (a.count_candidates && threadIdx.x == 0 && n) atomicAdd(a.counters + 2, (unsigned long long)n);
+  for (int q0 = 0; q0 < n; q0 += WARP_THREADS) {
+    const int qi = q0 + threadIdx.x;
     bool act = false;
     V3 xc = v3(0, 0, 0);
     int idx = -1, t = 0;
-    if (threadIdx.x < n) {
-      t = queue[threadIdx.x];
+    if (qi < n) {
+      t = queue[qi];
       float px, py, pz;
       sample_position(a, s0 + t, px, py, pz);
       idx = table_nearest(g, table_cell(g, px, py, pz), px, py, pz);
@@ -1077,7 +1089,7 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
         }
       }
     }
-    if ((threadIdx.x & ~31) < n) {  // warp-uniform: this warp holds queue entries
+    if (q0 + (int)(threadIdx.x & ~31u) < n) {  // warp-uniform: this warp holds queue entries
       const int nw = a.waves > 1 ? a.waves : 1;
       const int my_wave = (a.waves > 1 && act) ? (int)((s0 + t) % a.N) / a.wave_size : 0;
       for (int w = 0; w < nw; ++w) {
@@ -1098,9 +1110,10 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
     }
   }
   __syncthreads();
-  {
-    unsigned m = __ballot_sync(0xffffffffu, flag[threadIdx.x] != 0);
-    const int64_t s = s0 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < WARP_SPT; ++k) {
+    unsigned m = __ballot_sync(0xffffffffu, flag[k * WARP_THREADS + threadIdx.x] != 0);
+    const int64_t s = s0 + k * WARP_THREADS + threadIdx.x;
     if (lane == 0 && s < P) a.sample_mask[s >> 5] = m;
   }
 }

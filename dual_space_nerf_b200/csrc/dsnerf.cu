@@ -849,7 +849,7 @@ int dsnerf_set_weights(dsnerf_ctx* ctx, const float* const* t, int n_tensors) {
     return fail(ctx, DSNERF_ERR_CUDA, std::string("staging tensor-core weights: ") + cudaGetErrorString((cudaError_t)e));
   {
     std::vector<__half> w2p;
-    light_pack_w2(ctx->hw[T_L2_W], w2p);
+    light_pack_w2(ctx->hw[T_L2_W], ctx->hw[T_L0_W], ctx->hw[T_L0_B], w2p);
     CK(ctx->light_w2.ensure(w2p.size() * sizeof(__half)));
     CK(cudaMemcpy(ctx->light_w2.p, w2p.data(), w2p.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }

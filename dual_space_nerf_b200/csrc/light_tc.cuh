@@ -2,7 +2,12 @@
 //
 // Tile = 128 active samples per CTA iteration, one thread per sample (4 warps):
 //   A. world normal (through the nearest canonical triangle found by canon_nearest_kernel beforehand), world position,
-//      view direction (shade_inputs), then the 9 -> 128 first layer in fp32 registers; ReLU output is written as the fp16 A operand (K-major core matrices);
+//      view direction (shade_inputs); the 9 -> 128 first layer runs on the tensor core as well: the nine inputs are split
+//      into fp16 hi + lo and laid out as one K = 32 operand row [in_hi | in_lo | in_hi | 1 | 1 | 0 0 0] against
+//      [W1_hi ; W1_hi ; W1_lo ; b_hi ; b_lo] (= the 3-pass split of mlp_tc.cuh folded into K, bias included; two MMAs).  In
+//      fp32 registers this layer was 1152 FMAs + 320 shared-memory loads per sample, two thirds of the kernel's instructions
+//      (ncu: 154 M warp instructions, issue-bound at 16 warps per SM).  Its accumulator is read back, ReLU'd and written as
+//      the fp16 A operand of the second layer (K-major core matrices) in place of the first operand;
 //   B. one elected lane issues 8 tcgen05.mma (M = 128, N = 128, K = 16; A and B from shared memory): the 128 x 128
 //      second layer.  Its weights are packed on the host into the B-operand image and fetched once per CTA with
 //      cp.async.bulk, so they stay resident in shared memory for every tile of the CTA;
@@ -27,8 +32,8 @@ template <int PARTS> struct LtMap {
   static constexpr uint32_t W2 = 0;                         // B operand: PARTS x [16 k-chunks][128 rows][8] fp16 = PARTS x 32 KB
   static constexpr uint32_t A = PARTS * 32768;              // A operands: 2 halves x PARTS x 32 KB
   static constexpr uint32_t A_HALF = PARTS * 32768;         // bytes per half
-  static constexpr uint32_t W1 = A + 2 * A_HALF;            // fp32 [128][12]: 9 weights, bias, 2 pad
-  static constexpr uint32_t B2 = W1 + 128 * 12 * 4;
+  static constexpr uint32_t W1 = A + 2 * A_HALF;            // first layer as a B operand: [4 k-chunks][128 rows][8] fp16 = 8 KB
+  static constexpr uint32_t B2 = W1 + 8192;
   static constexpr uint32_t W3 = B2 + 512;
   static constexpr uint32_t BAR = W3 + 512;                 // 3 mbarriers + tmem slot
   static constexpr uint32_t SMEM = BAR + 64;
@@ -49,7 +54,6 @@ __global__ void __launch_bounds__(LT_THREADS, P3 ? 1 : 2) light_tc_kernel(ShadeA
   const int hwarp = (threadIdx.x >> 5) & 3;          // warp within the half = TMEM lane quarter
   const uint32_t bar_w = sbase + LT_SM_BAR, bar_mma = bar_w + 8 + 8 * half;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + LT_SM_BAR + 24);
-  float* w1p = reinterpret_cast<float*>(smem + LT_SM_W1);
   float* b2 = reinterpret_cast<float*>(smem + LT_SM_B2);
   float* w3 = reinterpret_cast<float*>(smem + LT_SM_W3);
   uint8_t* a_op = smem + LT_SM_A + half * M::A_HALF;  // hi part; the lo part (P3) follows 32 KB later
@@ -65,24 +69,17 @@ __global__ void __launch_bounds__(LT_THREADS, P3 ? 1 : 2) light_tc_kernel(ShadeA
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // first-layer weights as output PAIRS: w1p[pair][j] = (w[j][2 pair], w[j][2 pair + 1]) for j < 9, j = 9: the two biases --
-  // the layer then runs on packed fp32 FMAs (fma.rn.f32x2: two outputs per instruction, 9 + 9 instead of 18 + 18 per pair)
-  for (int i = threadIdx.x; i < 64 * 12; i += LT_THREADS) {
-    const int pr = i / 12, j = i - pr * 12;
-    float2 v = make_float2(0.f, 0.f);
-    if (j < 9) v = make_float2(L.w1t[j * 128 + 2 * pr], L.w1t[j * 128 + 2 * pr + 1]);
-    else if (j == 9) v = make_float2(L.b1[2 * pr], L.b1[2 * pr + 1]);
-    reinterpret_cast<float2*>(w1p)[i] = v;
-  }
   for (int i = threadIdx.x; i < 128; i += LT_THREADS) { b2[i] = L.b2[i]; w3[i] = L.w3[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot + (uint32_t)half * 128u;
   if (threadIdx.x == 0) {  // second-layer weights: one bulk copy, resident for the whole kernel
-    mbar_expect_tx(bar_w, W2_BYTES);
+    mbar_expect_tx(bar_w, W2_BYTES + 8192u);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(sbase + LT_SM_W2), "l"(w2_packed), "r"(W2_BYTES), "r"(bar_w) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sbase + LT_SM_W1), "l"(w2_packed + 65536), "r"(8192u), "r"(bar_w) : "memory");  // first layer follows W2 hi + lo
   }
   const int64_t n_active = a.n_active ? (int64_t)*a.n_active : a.n_active_host;
   const int64_t n_tiles = (n_active + LT_ROWS - 1) / LT_ROWS;
@@ -109,48 +106,76 @@ __global__ void __launch_bounds__(LT_THREADS, P3 ? 1 : 2) light_tc_kernel(ShadeA
     }
     int sample = 0;
     if (live) shade_inputs(a, gc, ac, mg, in, sample, ci);
-    // ---- first layer (fp32) -> fp16 A operand
-#pragma unroll 2
-    for (int kc = 0; kc < 16; ++kc) {
-      uint32_t pk[4], pl[4];
+    // ---- first layer on the tensor core: operand row [in_hi (9) | in_lo (9) | in_hi (9) | 1 | 1 | 0 0 0] -> chunks 0..3 of a_op
+    {
+      __half hh[9], hl[9];
 #pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        float hv[2];
-        {
-          const float4* w1 = reinterpret_cast<const float4*>(w1p + (kc * 4 + e / 2) * 24);  // 12 float2 per output pair
-          const float4 w01 = w1[0], w23 = w1[1], w45 = w1[2], w67 = w1[3], w8b = w1[4];
-          float2 h = make_float2(w8b.z, w8b.w);  // the two biases
-          h = __ffma2_rn(make_float2(in[0], in[0]), make_float2(w01.x, w01.y), h);
-          h = __ffma2_rn(make_float2(in[1], in[1]), make_float2(w01.z, w01.w), h);
-          h = __ffma2_rn(make_float2(in[2], in[2]), make_float2(w23.x, w23.y), h);
-          h = __ffma2_rn(make_float2(in[3], in[3]), make_float2(w23.z, w23.w), h);
-          h = __ffma2_rn(make_float2(in[4], in[4]), make_float2(w45.x, w45.y), h);
-          h = __ffma2_rn(make_float2(in[5], in[5]), make_float2(w45.z, w45.w), h);
-          h = __ffma2_rn(make_float2(in[6], in[6]), make_float2(w67.x, w67.y), h);
-          h = __ffma2_rn(make_float2(in[7], in[7]), make_float2(w67.z, w67.w), h);
-          h = __ffma2_rn(make_float2(in[8], in[8]), make_float2(w8b.x, w8b.y), h);
-          hv[0] = fmaxf(h.x, 0.f);
-          hv[1] = fmaxf(h.y, 0.f);
-        }
-        pk[e / 2] = pack_h2(hv[0], hv[1]);
-        if (P3) {
-          const float2 hf = __half22float2(as_h2(pk[e / 2]));
-          pl[e / 2] = pack_h2(hv[0] - hf.x, hv[1] - hf.y);
-        }
+      for (int k = 0; k < 9; ++k) {
+        hh[k] = __float2half_rn(in[k]);
+        hl[k] = __float2half_rn(in[k] - __half2float(hh[k]));
       }
-      *reinterpret_cast<uint4*>(a_op + (uint32_t)kc * (LT_ROWS * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      if (P3) *reinterpret_cast<uint4*>(a_op + 32768 + (uint32_t)kc * (LT_ROWS * 16) + row * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
+      auto pk2 = [](__half x, __half y) -> uint32_t { __half2 h = __halves2half2(x, y); return *reinterpret_cast<uint32_t*>(&h); };
+      const uint4 c0 = make_uint4(pk2(hh[0], hh[1]), pk2(hh[2], hh[3]), pk2(hh[4], hh[5]), pk2(hh[6], hh[7]));
+      const uint4 c1 = make_uint4(pk2(hh[8], hl[0]), pk2(hl[1], hl[2]), pk2(hl[3], hl[4]), pk2(hl[5], hl[6]));
+      const uint4 c2 = make_uint4(pk2(hl[7], hl[8]), pk2(hh[0], hh[1]), pk2(hh[2], hh[3]), pk2(hh[4], hh[5]));
+      const uint4 c3 = make_uint4(pk2(hh[6], hh[7]), pk2(hh[8], one), pk2(one, zero), pk2(zero, zero));
+      *reinterpret_cast<uint4*>(a_op + 0u * (LT_ROWS * 16) + row * 16) = c0;
+      *reinterpret_cast<uint4*>(a_op + 1u * (LT_ROWS * 16) + row * 16) = c1;
+      *reinterpret_cast<uint4*>(a_op + 2u * (LT_ROWS * 16) + row * 16) = c2;
+      *reinterpret_cast<uint4*>(a_op + 3u * (LT_ROWS * 16) + row * 16) = c3;
     }
     fence_proxy_async();
     half_bar();
-    // ---- second layer on the tensor core
+    constexpr uint32_t DHI = (128u >> 4) | (1u << 14);
+    constexpr uint32_t LBO = ((LT_ROWS * 16) >> 4) << 16;
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
     if (hwarp == 0) {
       if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
       tc_fence_after();
       if (elect_one()) {
-        constexpr uint32_t DHI = (128u >> 4) | (1u << 14);
-        constexpr uint32_t LBO = ((LT_ROWS * 16) >> 4) << 16;
-        constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a0 = LBO | ((sbase + LT_SM_A + half * M::A_HALF) >> 4), b1 = LBO | ((sbase + LT_SM_W1) >> 4);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint32_t step = (uint32_t)k * ((2 * LT_ROWS * 16) >> 4);
+          tc_mma_ss(tmem, ((uint64_t)DHI << 32) | (a0 + step), ((uint64_t)DHI << 32) | (b1 + step), IDESC, k > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    // ---- ReLU of the first layer -> fp16 A operand of the second (its hi part overwrites the first operand: the MMAs that read it are done)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + c * 32, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pk[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float h0 = fmaxf(__uint_as_float(v[q * 8 + 2 * e]), 0.f), h1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]), 0.f);
+          pk[e] = pack_h2(h0, h1);
+          if (P3) {
+            const float2 hf = __half22float2(as_h2(pk[e]));
+            pl[e] = pack_h2(h0 - hf.x, h1 - hf.y);
+          }
+        }
+        const uint32_t kc = (uint32_t)(c * 4 + q);
+        *reinterpret_cast<uint4*>(a_op + kc * (LT_ROWS * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (P3) *reinterpret_cast<uint4*>(a_op + 32768 + kc * (LT_ROWS * 16) + row * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    half_bar();  // every thread has read its accumulator row and written its operand row
+    // ---- second layer on the tensor core
+    if (hwarp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a0 = LBO | ((sbase + LT_SM_A + half * M::A_HALF) >> 4), b0 = LBO | ((sbase + LT_SM_W2) >> 4);
         constexpr uint32_t LO = 32768u >> 4;  // hi -> lo part of either operand
 #pragma unroll
@@ -200,9 +225,21 @@ __global__ void __launch_bounds__(LT_THREADS, P3 ? 1 : 2) light_tc_kernel(ShadeA
   }
 }
 
-// host: pack lights_encoding.2.weight [out=128][in=128] as the B operand image (B[n][k] = W[n][k]): hi part, then lo part
-inline void light_pack_w2(const std::vector<float>& w2, std::vector<__half>& out) {
-  out.assign((size_t)2 * 128 * 128, __float2half_rn(0.f));
+// host: pack lights_encoding.2.weight [out=128][in=128] as the B operand image (B[n][k] = W[n][k]): hi part, then lo part;
+// then lights_encoding.0 (w1 [128][9], b1 [128]) as the K = 32 B operand [w_hi (9) | w_hi (9) | w_lo (9) | b_hi | b_lo | 0 0 0]
+inline void light_pack_w2(const std::vector<float>& w2, const std::vector<float>& w1, const std::vector<float>& b1, std::vector<__half>& out) {
+  out.assign((size_t)2 * 128 * 128 + 128 * 32, __float2half_rn(0.f));
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 32; ++k) {
+      float v = 0.f;
+      auto hi = [](float x) { return __half2float(__float2half_rn(x)); };
+      if (k < 9) v = hi(w1[(size_t)n * 9 + k]);
+      else if (k < 18) v = hi(w1[(size_t)n * 9 + k - 9]);
+      else if (k < 27) v = w1[(size_t)n * 9 + k - 18] - hi(w1[(size_t)n * 9 + k - 18]);
+      else if (k == 27) v = hi(b1[n]);
+      else if (k == 28) v = b1[n] - hi(b1[n]);
+      out[(size_t)2 * 128 * 128 + ((size_t)(k / 8) * 128 + n) * 8 + (k % 8)] = __float2half_rn(v);
+    }
   for (int n = 0; n < 128; ++n)
     for (int k = 0; k < 128; ++k) {
       const float w = w2[(size_t)n * 128 + k];

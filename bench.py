@@ -562,7 +562,7 @@ def main():
     drain()
     torch.cuda.synchronize()
     st = ctx.stats()
-    launches_per_step = st["kernel_launches"] + 1  # render + per-frame grid build (counted by the library) + the clock probe
+    launches_per_step = st["kernel_launches"] + 1  # render + per-frame grid build (counted by the library) + the clock probe (own stream)
     evaluated = st["evaluated_samples"]
 
     ctx.profile(1 | int(os.environ.get('DSNERF_DEBUG_PROFILE_BITS', '0')))
@@ -572,13 +572,17 @@ def main():
     # 30-100 ms on this driver (ms_per_step 13.8 -> 23..88 ms); throttle reasons and power are sampled during an identical,
     # untimed repeat of the region right after it.
     d_clk = torch.zeros(args.steps, 2, device=dev)
+    # the probe runs on its own stream, next to the step's kernels (one warp for 30 us): it reads the clock under load and
+    # stays off the critical path of the timed stream
+    probe_stream = torch.cuda.Stream(device=dev)
+    psp = ctypes.c_void_p(probe_stream.cuda_stream)
     rig.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (inside the bracket: ~0.1 ms of 256 MB writes per step)
         step_device(i)
-        ctx.check(L.dsnerf_debug_sm_clock(ctx.h, ctypes.c_void_p(d_clk.data_ptr() + 8 * i), sp))
+        ctx.check(L.dsnerf_debug_sm_clock(ctx.h, ctypes.c_void_p(d_clk.data_ptr() + 8 * i), psp))
     drain()             # every frame's all-gather completes inside the timed region
     e1.record(stream)
     rig.barrier()
@@ -604,7 +608,7 @@ def main():
     clocks["sm_mhz_nvidia_smi_repeat"] = clocks.get("sm_mhz")
     clocks["sm_mhz"] = float(np.median(probe[:, 0]))
     clocks["sm_mhz_min"] = float(probe[:, 0].min())
-    clocks["source"] = ("sm_mhz: clock64/globaltimer probe kernel after every timed step (inside the timed region); reasons, power, "
+    clocks["source"] = ("sm_mhz: clock64/globaltimer probe kernel launched with every timed step on a side stream (inside the timed region, next to the step's kernels); reasons, power, "
                         "sm_max_mhz: " + str(clocks.get("source")) + " during an untimed repeat of the same loop")
     ms_total = rig.max_over_ranks(ms_total)
     ms_step = ms_total / args.steps

@@ -305,11 +305,13 @@ __device__ __forceinline__ void run_op(MmaState& ms, int n_slabs, int a_src, uin
   uint32_t kk = 0;
   for (int s = 0; s < n_slabs; ++s, kk += KSTEPS) {
     const bool from_pe = kk < pe_steps;
-    if (!from_pe) ms.need_quarters(min(4, (int)((kk - pe_steps + KSTEPS - 1) >> 2) + 1));
+    // the weight slab first (it landed long ago: the ring runs ahead), the descriptors next, and only then the wait that is
+    // on the critical path -- the operand quarter from the epilogue -- so that nothing but the MMA issue follows it
     if (!ms.noload) mbar_wait(ms.bar_full + 8 * ms.stage, ms.phase);
-    tc_fence_after();
     const uint32_t b_word = B_LBO | ((ms.sbase + SM_RING + ms.stage * TC_STAGE_BYTES) >> 4);
     const uint32_t ac = ((from_pe ? kk : kk - pe_steps) * 2 * A_CHUNK) >> 4;
+    if (!from_pe) ms.need_quarters(min(4, (int)((kk - pe_steps + KSTEPS - 1) >> 2) + 1));
+    tc_fence_after();
     issue_slab<ROWS, KSTEPS, NPASS, NMMA, EXTRA>(d_main, d_extra, (from_pe ? p_hi0 : a_hi0) + ac, (from_pe ? p_lo0 : a_lo0) + ac, b_word,
                                                  (uint32_t)(kk > 0), ms.bar_empty + 8 * ms.stage, !(ms.noload & 2));
     if (++ms.stage == TC_STAGES) { ms.stage = 0; ms.phase ^= 1; }

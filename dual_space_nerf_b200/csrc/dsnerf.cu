@@ -13,6 +13,7 @@
 #include "../../include/dsnerf.h"
 #include "geom.cuh"
 #include "mlp_simt.cuh"
+#include "mlp_tc2.cuh"
 #include "mlp_tc.cuh"
 #include "shade.cuh"
 #include "light_tc.cuh"
@@ -93,6 +94,10 @@ struct dsnerf_ctx {
   int has_rot = 0;
   // ---- workspace
   DevBuf tc_timing;
+  DevBuf relu_scratch;                // mlp_tc2_kernel: ReLU bits of the tiles in flight
+  unsigned int* h_tc_dbg = nullptr;   // mlp_tc2_kernel: watchdog record, mapped host memory (DSNERF_TC_WATCHDOG)
+  int mlp_variant = 2;           // 2: two tiles in flight per CTA (mlp_tc2.cuh), 1: one tile (mlp_tc.cuh); DSNERF_MLP_VARIANT
+  bool tc_watchdog = false;
   DevBuf near2, far2, raw, active, active_tri, active_cidx, ray_mask, mlp_a, mlp_g, tvals, counters, io;
   DevBuf ert_active, ert_tri, ert_state, ert_cnt;  // early-ray-termination mode only
   unsigned long long* h_ert = nullptr;              // pinned, 8 entries
@@ -462,7 +467,28 @@ int launch_mlp(dsnerf_ctx* ctx, const unsigned long long* d_count, int64_t host_
       if (ctx->tc_timing.ensure(sizeof(long long) * 128) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "timing buffer");
       timing = ctx->tc_timing.as<long long>();
     }
-    if (int e = tc_launch(ctx->tw, timing, (ctx->profile >> 3) & 3, (ctx->profile >> 6) & 3, active, d_count, host_count, ctx->mlp_a.as<float4>(),
+    if (ctx->mlp_variant == 2 && !density_only) {
+      if (ctx->relu_scratch.ensure(tc2_scratch_bytes(ctx->sm_count)) != cudaSuccess) return fail(ctx, DSNERF_ERR_CUDA, "ReLU scratch");
+      unsigned int* dbg = nullptr;
+      if (ctx->tc_watchdog) {  // debug: bounded barrier waits; the record lives in mapped host memory so that it survives the trap
+        if (!ctx->h_tc_dbg && cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_tc_dbg), 64, cudaHostAllocMapped) != cudaSuccess)
+          return fail(ctx, DSNERF_ERR_CUDA, "watchdog buffer");
+        memset(ctx->h_tc_dbg, 0, 64);
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dbg), ctx->h_tc_dbg, 0));
+      }
+      if (int e = tc2_launch(ctx->tw, timing, dbg, (ctx->profile >> 3) & 3, ctx->relu_scratch.as<uint32_t>(), active, d_count, host_count, ctx->mlp_a.as<float4>(),
+                             ctx->mlp_g.as<float4>(), ctx->sm_count, st))
+        return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc2: ") + cudaGetErrorString((cudaError_t)e));
+      if (ctx->tc_watchdog) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+          char buf[256];
+          snprintf(buf, sizeof buf, "mlp_tc2 watchdog: %s; barrier id 0x%x, block %u, thread %u, parity %u", cudaGetErrorString(e),
+                   ctx->h_tc_dbg[1], ctx->h_tc_dbg[2], ctx->h_tc_dbg[3], ctx->h_tc_dbg[4]);
+          return fail(ctx, DSNERF_ERR_CUDA, buf);
+        }
+      }
+    } else if (int e = tc_launch(ctx->tw, timing, (ctx->profile >> 3) & 3, (ctx->profile >> 6) & 3, active, d_count, host_count, ctx->mlp_a.as<float4>(),
                           ctx->mlp_g.as<float4>(), density_only, ctx->sm_count, st))
       return fail(ctx, DSNERF_ERR_CUDA, std::string("launch mlp_tc: ") + cudaGetErrorString((cudaError_t)e));
   }
@@ -739,6 +765,9 @@ int dsnerf_create(dsnerf_ctx** out, int device) {
   cudaFuncSetAttribute(light_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM);
   cudaFuncSetAttribute(light_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM3);
   tc_configure();
+  tc2_configure();
+  if (const char* ev = getenv("DSNERF_MLP_VARIANT")) ctx->mlp_variant = atoi(ev) == 1 ? 1 : 2;
+  ctx->tc_watchdog = getenv("DSNERF_TC_WATCHDOG") != nullptr;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { delete ctx; return DSNERF_ERR_CUDA; }
   *out = ctx;

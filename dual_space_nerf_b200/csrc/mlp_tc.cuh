@@ -48,6 +48,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace dsn {
@@ -853,6 +854,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
 // ------------------------------------------------------------------------------------------ host
 struct TcWeights {
   void* d_pack = nullptr;
+  void* d_pack2 = nullptr;   // the same weights in the op schedule of mlp_tc2.cuh (two tiles in flight)
+  TcOp ops2[16];
+  size_t pack2_bytes = 0;    // size of one copy of d_pack2 (a multiple of 256)
+  int pack2_copies = 1;      // identical copies of d_pack2 back to back: CTA pairs spread their weight stream over them
   float* d_f32 = nullptr;  // biases 0..6 (7x256; row 0 per frame), b_rgb1 (128), w_rgb2 (384), w_dens (256), seed half2 pairs (128 words)
   float b_rgb2[3] = {0, 0, 0};
   float b_dens = 0.f, seed_scale = 1.f, stash_scale = 1.f;
@@ -866,8 +871,10 @@ struct TcWeights {
 
   void release() {
     if (d_pack) cudaFree(d_pack);
+    if (d_pack2) cudaFree(d_pack2);
     if (d_f32) cudaFree(d_f32);
     d_pack = nullptr;
+    d_pack2 = nullptr;
     d_f32 = nullptr;
   }
 
@@ -987,11 +994,68 @@ struct TcWeights {
     if (oi != TC_NUM_OPS) return (int)cudaErrorUnknown;
     for (int i = 0; i < TC_NUM_OPS; ++i)
       if (ops[i].slab_bytes > TC_STAGE_BYTES || (ops[i].slab_bytes & 31) || (ops[i].src_off & 15)) return (int)cudaErrorInvalidValue;
+    // ---- schedule of mlp_tc2.cuh (16 ops): slabs of 16 KB per CTA wherever the shape allows (the weight ring's throughput is
+    // slabs in flight per round trip, whatever their size); the extra
+    // N = 64 product of layer 4's backward pass (d sigma / d PE) is an op of its own in front of the main product
+    std::vector<__half> blob2;
+    {
+      int o2 = 0;
+      for (int l = 0; l < 7; ++l) {
+        const int K = l == 0 ? 64 : (l == 4 ? 320 : 256);
+        B.assign((size_t)256 * K, 0.f);
+        for (int n = 0; n < 256; ++n) {
+          if (l == 0) {
+            for (int k = 0; k < 63; ++k) B[(size_t)n * K + k] = w0[(size_t)n * 87 + 8 + k];
+          } else if (l == 4) {
+            for (int k = 0; k < 63; ++k) B[(size_t)n * K + k] = w4[(size_t)n * 319 + 256 + k];
+            for (int k = 0; k < 256; ++k) B[(size_t)n * K + 64 + k] = w4[(size_t)n * 319 + k];
+          } else {
+            for (int k = 0; k < 256; ++k) B[(size_t)n * K + k] = (*W[l])[(size_t)n * 256 + k];
+          }
+        }
+        pack_op(blob2, ops2[o2++], K_FWD, 0, 256, 0, K, 2, true, B);
+      }
+      B.assign((size_t)128 * 256, 0.f);
+      for (int n = 0; n < 128; ++n)
+        for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = wr1[(size_t)n * 256 + k];
+      pack_op(blob2, ops2[o2++], rgb3 ? K_RGB3 : K_RGB, 0, 128, 0, 256, rgb3 ? 4 : 8, rgb3, B);
+      for (int l = 6; l >= 1; --l) {
+        const float sc = p2(bwd_shift[l]);
+        const int in_dim = l == 4 ? 319 : 256;
+        if (l == 4) {  // d sigma / d PE through layer 4: rows = the 63 PE inputs
+          B.assign((size_t)64 * 256, 0.f);
+          for (int n = 0; n < 63; ++n)
+            for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = sc * w4[(size_t)k * 319 + 256 + n];
+          pack_op(blob2, ops2[o2++], K_BW0, 0, 64, 0, 256, 16, false, B);
+        }
+        B.assign((size_t)256 * 256, 0.f);
+        for (int n = 0; n < 256; ++n)
+          for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = sc * (*W[l])[(size_t)k * in_dim + n];
+        pack_op(blob2, ops2[o2++], K_BWD, 0, 256, 0, 256, 4, false, B);
+      }
+      B.assign((size_t)64 * 256, 0.f);
+      for (int n = 0; n < 63; ++n)
+        for (int k = 0; k < 256; ++k) B[(size_t)n * 256 + k] = p2(bwd_shift[0]) * w0[(size_t)k * 87 + 8 + n];
+      pack_op(blob2, ops2[o2++], K_BW0, 0, 64, 0, 256, 16, false, B);
+      if (o2 != 16) return (int)cudaErrorUnknown;
+      for (int i = 0; i < 16; ++i)
+        if (ops2[i].slab_bytes > TC_STAGE_BYTES || (ops2[i].slab_bytes & 31) || (ops2[i].src_off & 15)) return (int)cudaErrorInvalidValue;
+    }
     release();
     cudaError_t e = cudaMalloc(&d_pack, blob.size() * sizeof(__half));
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(d_pack, blob.data(), blob.size() * sizeof(__half), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int)e;
+    while (blob2.size() % 128) blob2.push_back(__float2half_rn(0.f));
+    pack2_bytes = blob2.size() * sizeof(__half);
+    pack2_copies = 1;
+    if (const char* ev = getenv("DSNERF_W_REPLICAS")) pack2_copies = std::max(1, std::min(16, atoi(ev)));
+    e = cudaMalloc(&d_pack2, pack2_bytes * pack2_copies);
+    if (e != cudaSuccess) return (int)e;
+    for (int c = 0; c < pack2_copies; ++c) {
+      e = cudaMemcpy(reinterpret_cast<uint8_t*>(d_pack2) + (size_t)c * pack2_bytes, blob2.data(), pack2_bytes, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return (int)e;
+    }
     std::vector<float> f(F32_TOTAL, 0.f);
     const std::vector<float>* bs[6] = {&b1, &b2, &b3, &b4, &b5, &b6};
     for (int l = 0; l < 6; ++l)

@@ -47,6 +47,7 @@ constexpr uint32_t S2_BAR = S2_RGBW + 2048;                      // 231424
 constexpr uint32_t T2_SMEM = S2_BAR + 272;                       // 231696 (32 barriers + the TMEM base slot)
 constexpr uint32_t TM_XCH = 128;                                 // exchange columns inside a tile's accumulator (free at the rgb op and the last op)
 constexpr int T2_NUM_OPS = 16;
+constexpr int T2_STAMP_IT = 3;                                   // debug stamps are taken on this tile pair of CTA 0 (steady state)
 constexpr uint32_t T2_KSTEP = 2 * A_CHUNK;                       // bytes per k-step inside a slot
 
 struct Tc2Params {
@@ -75,18 +76,24 @@ struct Tc2Params {
   int debug_noload;         // debug: skip the weight stream (garbage results) to measure its cost
 };
 
-// bounded wait: a protocol error becomes a trap with a record instead of a hung GPU
-__device__ __forceinline__ void mbar_wait2(uint32_t a, uint32_t parity, unsigned int* dbg, uint32_t id) {
+// Barrier waits.  With a watchdog record (DSNERF_TC_WATCHDOG, bring-up only) a protocol error becomes a trap with a record
+// instead of a hung GPU; the production loops carry no bookkeeping (every extra instruction of a wait loop is executed tens of
+// millions of times per launch, and the kernel runs at the power cap).
+__device__ __noinline__ void mbar_wait_watchdog(uint32_t a, uint32_t parity, unsigned int* dbg, uint32_t id) {
   uint32_t done;
   uint32_t spins = 0;
   do {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    if (!done && dbg && ++spins > (1u << 24)) {
+    if (!done && ++spins > (1u << 24)) {
       if (atomicCAS(dbg, 0u, 1u) == 0u) { dbg[1] = id; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x; dbg[4] = parity; __threadfence(); }
       __trap();
     }
   } while (!done);
+}
+__device__ __forceinline__ void mbar_wait2(uint32_t a, uint32_t parity, unsigned int* dbg, uint32_t id) {
+  if (dbg) { mbar_wait_watchdog(a, parity, dbg, id); return; }
+  mbar_wait(a, parity);
 }
 
 #ifdef T2_NO_RELAY   // measurement only: the leader does not wait for the peer's half (results may be garbage)
@@ -95,24 +102,20 @@ __device__ __forceinline__ void mbar_wait2(uint32_t a, uint32_t parity, unsigned
 #define T2_WFULL_LEADER_COUNT(rank) ((rank) == 0 ? 2 : 1)
 #endif
 #ifndef T2_WAIT_HINT
-#define T2_WAIT_HINT 0
+#define T2_WAIT_HINT 1000   // ns; 0 = plain polling
 #endif
 // epilogue-side wait: with a suspend-time hint the hardware parks the warp until the phase completes instead of re-issuing
 // try_wait (every poll is a shared-memory access and an issue slot taken from the warps that work)
 __device__ __forceinline__ void mbar_wait2h(uint32_t a, uint32_t parity, unsigned int* dbg, uint32_t id) {
+  if (dbg) { mbar_wait_watchdog(a, parity, dbg, id); return; }
 #if T2_WAIT_HINT > 0
   uint32_t done;
-  uint32_t spins = 0;
   do {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(done) : "r"(a), "r"(parity), "r"((uint32_t)T2_WAIT_HINT) : "memory");
-    if (!done && dbg && ++spins > (1u << 22)) {
-      if (atomicCAS(dbg, 0u, 1u) == 0u) { dbg[1] = id; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x; dbg[4] = parity; __threadfence(); }
-      __trap();
-    }
   } while (!done);
 #else
-  mbar_wait2(a, parity, dbg, id);
+  mbar_wait(a, parity);
 #endif
 }
 
@@ -291,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             pefull_bits ^= 1u << s;
           }
           tc_fence_after();
-          const bool mstamp = P.timing && blockIdx.x == 0 && it == 0 && lane == 0;
+          const bool mstamp = P.timing && blockIdx.x == 0 && it == T2_STAMP_IT && lane == 0;
           const uint32_t t_m0 = mstamp ? (uint32_t)clock64() : 0u;
           uint32_t t_wf = 0;
           if (op <= 6) {
@@ -514,8 +517,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       if (n_iter > 0) { produce_pe(cx, cy, cz, 0); produce_pe(ox, oy, oz, 1); }
     }
     const bool stamp = P.timing && blockIdx.x == 0 && threadIdx.x == 0;
-    if (stamp) P.timing[0] = clock64();
     for (int64_t it = 0; it < n_iter; ++it) {
+      if (stamp && it == T2_STAMP_IT) P.timing[0] = clock64();
       for (int op = 0; op < T2_NUM_OPS; ++op) {
         for (int s = 0; s < 2; ++s) {
           const int64_t tile = blockIdx.x + (2 * it + s) * (int64_t)gridDim.x;
@@ -523,7 +526,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           const bool live = base + row < n_active;
           const uint32_t t_acc = t_lane + (uint32_t)s * TM_ACC;
           uint32_t* const rs = rscr + s * (7 * 2 * 512);
-          stamp_at = (stamp && it == 0) ? P.timing + 2 + 2 * (2 * op + s) : nullptr;
+          stamp_at = (stamp && it == T2_STAMP_IT) ? P.timing + 2 + 2 * (2 * op + s) : nullptr;
           if (op <= 6) {
             // ---------- forward layer: bias + ReLU, ReLU bits, fp16 hi / lo units of the next layer's operand
             if (op == 3) produce_pe(cx, cy, cz, -1);   // head of layer 4's operand, consumed before this layer's four units
@@ -588,29 +591,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             __stcg(rs + (op * 2 + 1) * 512, mw1);
             if (last6) csig = sig2.x + sig2.y;
           } else if (op == 7) {
-            // ---------- rgb head: seed units of the backward chain first (they need only layer 6's ReLU bits), then the tail
+            // ---------- rgb head: tail of the rgb layer, sigma / essence out, then the seed units of the backward chain
+            // (G6 = (w_dens / scale) * relu'(a6), rebuilt from layer 6's ReLU bits; their loads fly during the tail)
             const uint32_t m0 = __ldcg(rs + (6 * 2 + 0) * 512), m1 = __ldcg(rs + (6 * 2 + 1) * 512);
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint4 sd0 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2));
-              const uint4 sd1 = __ldg(reinterpret_cast<const uint4*>(P.seed_h2 + (q4 * 64 + sub * TC_CPT) / 2 + 4));
-              uint32_t g[8] = {sd0.x, sd0.y, sd0.z, sd0.w, sd1.x, sd1.y, sd1.z, sd1.w};
-              const uint32_t mw = (q4 >> 1) ? m1 : m0;
-              if ((q4 & 1) == 0) {
-                g[0] &= relu_mask2<0>(mw); g[1] &= relu_mask2<1>(mw); g[2] &= relu_mask2<2>(mw); g[3] &= relu_mask2<3>(mw);
-                g[4] &= relu_mask2<4>(mw); g[5] &= relu_mask2<5>(mw); g[6] &= relu_mask2<6>(mw); g[7] &= relu_mask2<7>(mw);
-              } else {
-                g[0] &= relu_mask2<8>(mw); g[1] &= relu_mask2<9>(mw); g[2] &= relu_mask2<10>(mw); g[3] &= relu_mask2<11>(mw);
-                g[4] &= relu_mask2<12>(mw); g[5] &= relu_mask2<13>(mw); g[6] &= relu_mask2<14>(mw); g[7] &= relu_mask2<15>(mw);
-              }
-              const uint32_t hs = ppos;
-              ppos = wrap(ppos + 1);
-              const uint32_t off = (uint32_t)(2 * sub) * A_CHUNK + row_off;
-              wait_free(hs, false);
-              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off) = make_uint4(g[0], g[1], g[2], g[3]);
-              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off + A_CHUNK) = make_uint4(g[4], g[5], g[6], g[7]);
-              publish(hs);
-            }
+            const uint4* seedp = reinterpret_cast<const uint4*>(P.seed_h2 + (sub * TC_CPT) / 2);
+            uint4 sd0 = __ldg(seedp), sd1 = __ldg(seedp + 1);
             float2 e0 = make_float2(0.f, 0.f), e1 = e0, e2 = e0;
             acc_wait(s);
             const float* rgbw = reinterpret_cast<const float*>(smem + S2_RGBW);
@@ -658,6 +643,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
                 P.out_a[base + row] = make_float4(sm[0] + P.b_dens, sm[1] + P.b_rgb2[0], sm[2] + P.b_rgb2[1], sm[3] + P.b_rgb2[2]);
               }
             }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint32_t g[8] = {sd0.x, sd0.y, sd0.z, sd0.w, sd1.x, sd1.y, sd1.z, sd1.w};
+              if (q4 < 3) { sd0 = __ldg(seedp + (q4 + 1) * 8); sd1 = __ldg(seedp + (q4 + 1) * 8 + 1); }   // next unit's words (64 columns = 8 uint4 further)
+              const uint32_t mw = (q4 >> 1) ? m1 : m0;
+              if ((q4 & 1) == 0) {
+                g[0] &= relu_mask2<0>(mw); g[1] &= relu_mask2<1>(mw); g[2] &= relu_mask2<2>(mw); g[3] &= relu_mask2<3>(mw);
+                g[4] &= relu_mask2<4>(mw); g[5] &= relu_mask2<5>(mw); g[6] &= relu_mask2<6>(mw); g[7] &= relu_mask2<7>(mw);
+              } else {
+                g[0] &= relu_mask2<8>(mw); g[1] &= relu_mask2<9>(mw); g[2] &= relu_mask2<10>(mw); g[3] &= relu_mask2<11>(mw);
+                g[4] &= relu_mask2<12>(mw); g[5] &= relu_mask2<13>(mw); g[6] &= relu_mask2<14>(mw); g[7] &= relu_mask2<15>(mw);
+              }
+              const uint32_t hs = ppos;
+              ppos = wrap(ppos + 1);
+              const uint32_t off = (uint32_t)(2 * sub) * A_CHUNK + row_off;
+              wait_free(hs, false);
+              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off) = make_uint4(g[0], g[1], g[2], g[3]);
+              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off + A_CHUNK) = make_uint4(g[4], g[5], g[6], g[7]);
+              publish(hs);
+            }
             acc_release(s);
           } else if (op == 10) {
             // ---------- d sigma / d PE through layer 4: chain rule at once, three partial sums survive
@@ -698,7 +703,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             }
             acc_release(s);
             cx = pn.x; cy = pn.y; cz = pn.z;
-            if (stamp && it == 0 && s == 1) P.timing[1] = clock64();
+            if (stamp && it == T2_STAMP_IT && s == 1) P.timing[1] = clock64();
           } else {
             // ---------- backward layer: G_{l-1} = (G_l W_l) * relu'(a_{l-1}), fp16 hi-only units
             const int layer = op == 8 ? 5 : (op == 9 ? 4 : 14 - op);   // ops 11..14 -> layers 3..0

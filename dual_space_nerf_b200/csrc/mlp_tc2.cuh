@@ -33,6 +33,8 @@
 // Op schedule of a tile (16 ops): 0-6 forward layers, 7 rgb head (its epilogue also writes the backward seed units),
 // 8 bW6, 9 bW5, 10 d sigma / d PE through layer 4 (N = 64, no release), 11 bW4, 12 bW3, 13 bW2, 14 bW1, 15 bW0 (N = 64).
 #pragma once
+#include <type_traits>
+
 #include "mlp_tc.cuh"
 
 namespace dsn {
@@ -398,7 +400,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     auto publish = [&](uint32_t) { fence_proxy_async(); };
     long long* stamp_at = nullptr;   // debug stamps of the current phase (CTA 0, thread 0, first tile pair)
     auto acc_wait = [&](int s) {
+#ifdef T2_ONE_POLLER
+      // one warp polls the mbarrier, the other fifteen wait at a hardware barrier (no instructions issued while they wait)
+      if (warp == 0) mbar_wait2h(bar_accfull + 8 * s, (accfull_bits >> s) & 1u, dbg, 0x700 + s);
+      epi_bar();
+#else
       mbar_wait2h(bar_accfull + 8 * s, (accfull_bits >> s) & 1u, dbg, 0x700 + s);
+#endif
       accfull_bits ^= 1u << s;
       tc_fence_after();
       if (stamp_at) stamp_at[0] = clock64();
@@ -528,68 +536,75 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           uint32_t* const rs = rscr + s * (7 * 2 * 512);
           stamp_at = (stamp && it == T2_STAMP_IT) ? P.timing + 2 + 2 * (2 * op + s) : nullptr;
           if (op <= 6) {
-            // ---------- forward layer: bias + ReLU, ReLU bits, fp16 hi / lo units of the next layer's operand
+            // ---------- forward layer: bias + ReLU, ReLU bits, fp16 hi / lo units of the next layer's operand.  Layer 6 (density head in
+            // fp32, hi-only units for a single-pass rgb head) is a separate instantiation: as predicated code inside the common body it
+            // cost every layer 8 loads, 16 descriptor moves and 8 FMAs per unit that do nothing.
             if (op == 3) produce_pe(cx, cy, cz, -1);   // head of layer 4's operand, consumed before this layer's four units
-            const float* __restrict__ bias = P.bias + op * 256 + sub * TC_CPT;
-            const bool last6 = op == 6;
-            const bool with_lo = !(last6 && !P.rgb3);
-            const float* __restrict__ wdp = P.w_dens + sub * TC_CPT;
-            float2 sig2 = make_float2(0.f, 0.f);
-            acc_wait(s);
-            const uint32_t t_accb = t_acc + sub * TC_CPT;
-            uint32_t va[16], vb[16];
-            tmem_ld16_nowait(t_accb, va);
-            uint32_t mw0 = 0, mw1 = 0;
+            auto fwd_phase = [&](auto l6_tag) {
+              constexpr bool last6 = decltype(l6_tag)::value;
+              const float* __restrict__ bias = P.bias + op * 256 + sub * TC_CPT;
+              const bool with_lo = !(last6 && !P.rgb3);
+              const float* __restrict__ wdp = P.w_dens + sub * TC_CPT;
+              float2 sig2 = make_float2(0.f, 0.f);
+              acc_wait(s);
+              const uint32_t t_accb = t_acc + sub * TC_CPT;
+              uint32_t va[16], vb[16];
+              tmem_ld16_nowait(t_accb, va);
+              uint32_t mw0 = 0, mw1 = 0;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint32_t(&v)[16] = (q4 & 1) ? vb : va;
-              float4 b[4];
+              for (int q4 = 0; q4 < 4; ++q4) {
+                uint32_t(&v)[16] = (q4 & 1) ? vb : va;
+                float4 b[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + q4 * 64) + i);
-              tmem_wait_ld(v);
-              if (q4 < 3) { if (q4 & 1) tmem_ld16_nowait(t_accb + (q4 + 1) * 64, va); else tmem_ld16_nowait(t_accb + (q4 + 1) * 64, vb); }
-              uint32_t hi[8], lo[8];
-              uint32_t mw = 0;
+                for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + q4 * 64) + i);
+                tmem_wait_ld(v);
+                if (q4 < 3) { if (q4 & 1) tmem_ld16_nowait(t_accb + (q4 + 1) * 64, va); else tmem_ld16_nowait(t_accb + (q4 + 1) * 64, vb); }
+                uint32_t hi[8], lo[8];
+                uint32_t mw = 0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = b[j >> 1];
-                const float2 b2 = (j & 1) ? make_float2(bb.z, bb.w) : make_float2(bb.x, bb.y);
-                float2 h = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
-                h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
-                const __half2 hh = __floats2half2_rn(h.x, h.y);
-                hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
-                const uint32_t m2 = __hgt2_mask(hh, as_h2(0u));
-                const int p = j + 8 * (q4 & 1);
-                mw |= m2 & ((1u << p) | (1u << (16 + p)));
-                if (last6) {
-                  const float2 wd = __ldg(reinterpret_cast<const float2*>(wdp + q4 * 64 + 2 * j));
-                  sig2 = __ffma2_rn(wd, h, sig2);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 bb = b[j >> 1];
+                  const float2 b2 = (j & 1) ? make_float2(bb.z, bb.w) : make_float2(bb.x, bb.y);
+                  const float2 a = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
+                  // relu through the fp16 image: hi = relu(fp16(a)) = fp16(relu(a)) (rounding is monotonic), and the mask (hi > 0) that
+                  // becomes the ReLU bit also clears the lo part of a non-positive pre-activation: three instructions less per pair
+                  // than two fp32 max, bit-identical results
+                  const __half2 hr = __floats2half2_rn(a.x, a.y);
+                  const uint32_t m2 = __hgt2_mask(hr, as_h2(0u));
+                  hi[j] = *reinterpret_cast<const uint32_t*>(&hr) & m2;
+                  const int p = j + 8 * (q4 & 1);
+                  mw |= m2 & ((1u << p) | (1u << (16 + p)));
+                  if (last6) {
+                    const float2 wd = __ldg(reinterpret_cast<const float2*>(wdp + q4 * 64 + 2 * j));
+                    sig2 = __ffma2_rn(wd, make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), sig2);
+                  }
+                  const float2 hf = __half22float2(hr);
+                  const float2 l2 = __ffma2_rn(hf, make_float2(-1.f, -1.f), a);
+                  lo[j] = pack_h2(l2.x, l2.y) & m2;
                 }
-                const float2 hf = __half22float2(hh);
-                const float2 l2 = __ffma2_rn(hf, make_float2(-1.f, -1.f), h);
-                lo[j] = pack_h2(l2.x, l2.y);
+                if (q4 >> 1) mw1 |= mw; else mw0 |= mw;
+                const uint32_t hs = ppos;
+                const uint32_t off = (uint32_t)(2 * sub) * A_CHUNK + row_off;
+                wait_free(hs, true);
+                *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off + A_CHUNK) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                if (with_lo) {
+                  const uint32_t ls = wrap(ppos + 1);
+                  wait_free(ls, true);
+                  *reinterpret_cast<uint4*>(smem + S2_A + ls * T2_SLOT + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                  *reinterpret_cast<uint4*>(smem + S2_A + ls * T2_SLOT + off + A_CHUNK) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                  ppos = wrap(ppos + 2);
+                } else {
+                  ppos = wrap(ppos + 1);
+                }
+                publish(hs);
               }
-              if (q4 >> 1) mw1 |= mw; else mw0 |= mw;
-              const uint32_t hs = ppos;
-              const uint32_t off = (uint32_t)(2 * sub) * A_CHUNK + row_off;
-              wait_free(hs, true);
-              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off + A_CHUNK) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              if (with_lo) {
-                const uint32_t ls = wrap(ppos + 1);
-                wait_free(ls, true);
-                *reinterpret_cast<uint4*>(smem + S2_A + ls * T2_SLOT + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<uint4*>(smem + S2_A + ls * T2_SLOT + off + A_CHUNK) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                ppos = wrap(ppos + 2);
-              } else {
-                ppos = wrap(ppos + 1);
-              }
-              publish(hs);
-            }
-            acc_release(s);
-            __stcg(rs + (op * 2 + 0) * 512, mw0);
-            __stcg(rs + (op * 2 + 1) * 512, mw1);
-            if (last6) csig = sig2.x + sig2.y;
+              acc_release(s);
+              __stcg(rs + (op * 2 + 0) * 512, mw0);
+              __stcg(rs + (op * 2 + 1) * 512, mw1);
+              if (last6) csig = sig2.x + sig2.y;
+            };
+            if (op == 6) fwd_phase(std::true_type{}); else fwd_phase(std::false_type{});
           } else if (op == 7) {
             // ---------- rgb head: tail of the rgb layer, sigma / essence out, then the seed units of the backward chain
             // (G6 = (w_dens / scale) * relu'(a6), rebuilt from layer 6's ReLU bits; their loads fly during the tail)

@@ -562,6 +562,7 @@ def main():
     drain()
     torch.cuda.synchronize()
     st = ctx.stats()
+    variant = int(L.dsnerf_mlp_kernel_variant(ctx.h))
     launches_per_step = st["kernel_launches"] + 1  # render + per-frame grid build (counted by the library) + the clock probe (own stream)
     evaluated = st["evaluated_samples"]
 
@@ -705,13 +706,13 @@ def main():
                 if world > 1 else "1 GPU",
                 "gather": gather_mode + (" (multicast)" if (fx is not None and fx.mc) else ""), "gather_verified": gather_ok,
                 "l2": "256 MB buffer written between timed steps (L2 flush)",
-                "mlp_kernel": "fp32 SIMT (debug)" if args.simt else "tcgen05",
+                "mlp_kernel": "fp32 SIMT (debug)" if args.simt else ("tcgen05, two tiles in flight per CTA (mlp_tc2.cuh)" if variant == 2 else "tcgen05, one tile per CTA (mlp_tc.cuh)"),
                 "early_stop": bool(args.early_stop),
             },
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                 "frac": (achieved / sustained) if achieved else None, "traffic": traffic,
-                "kernel": "mlp_simt_kernel" if args.simt else "mlp_tc_kernel", "kernel_ms_per_launch": mlp_ms / max(mlp_n, 1),
+                "kernel": "mlp_simt_kernel" if args.simt else ("mlp_tc2_kernel" if variant == 2 else "mlp_tc_kernel"), "kernel_ms_per_launch": mlp_ms / max(mlp_n, 1),
                 "kernel_launches_per_step": mlp_n / max(args.steps, 1), "kernel_share_of_step": mlp_frame_ms / ms_step, "peak_source": f"bf16_tflops_sustained of {src} (MEASURED_PEAKS.json)",
                 "algorithmic_flop_per_launch": evaluated * FLOP_PER_SAMPLE,
                 "whole_step_frac": (evaluated * FLOP_PER_SAMPLE) / (ms_step * 1e-3) / 1e12 / sustained,

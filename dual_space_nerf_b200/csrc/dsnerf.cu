@@ -1288,6 +1288,8 @@ int dsnerf_tensor_path_active(const dsnerf_ctx* ctx) {
   return ctx->tw.fp16_ok ? (ctx->tw.rgb3 ? 3 : 1) : 0;
 }
 
+int dsnerf_mlp_kernel_variant(const dsnerf_ctx* ctx) { return ctx ? ctx->mlp_variant : DSNERF_ERR_INVALID; }
+
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out) {
   if (!ctx || !out) return DSNERF_ERR_INVALID;
   if (ctx->stats.rays > 0) {

@@ -49,6 +49,9 @@ constexpr uint32_t S2_BAR = S2_RGBW + 2048;                      // 231424
 constexpr uint32_t T2_SMEM = S2_BAR + 272;                       // 231696 (32 barriers + the TMEM base slot)
 constexpr uint32_t TM_XCH = 128;                                 // exchange columns inside a tile's accumulator (free at the rgb op and the last op)
 constexpr int T2_NUM_OPS = 16;
+#ifndef T2_TIMING
+#define T2_TIMING 0   // 1: per-phase clock64 stamps of CTA 0 (tests/tc2_timing.py needs a build with -DT2_TIMING=1)
+#endif
 constexpr int T2_STAMP_IT = 3;                                   // debug stamps are taken on this tile pair of CTA 0 (steady state)
 constexpr uint32_t T2_KSTEP = 2 * A_CHUNK;                       // bytes per k-step inside a slot
 
@@ -118,6 +121,26 @@ __device__ __forceinline__ void mbar_wait2h(uint32_t a, uint32_t parity, unsigne
   } while (!done);
 #else
   mbar_wait(a, parity);
+#endif
+}
+
+// wait for a ring slot: the epilogue that waits here is ahead of the tensor pipe, so it can afford a coarse wake-up; every poll not
+// issued is an instruction (and a shared-memory access) less on a kernel that runs at the power cap
+#ifndef T2_FREE_SLEEP
+#define T2_FREE_SLEEP 500   // ns between polls of a slot's "free" barrier (measured: 200 / 500 / 1000 alike, -1 % kernel time); 0 = same wait as everywhere else
+#endif
+__device__ __forceinline__ void mbar_wait_slot(uint32_t a, uint32_t parity, unsigned int* dbg, uint32_t id) {
+#if T2_FREE_SLEEP > 0
+  if (dbg) { mbar_wait_watchdog(a, parity, dbg, id); return; }
+  uint32_t done;
+  for (;;) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(T2_FREE_SLEEP);
+  }
+#else
+  mbar_wait2h(a, parity, dbg, id);
 #endif
 }
 
@@ -296,7 +319,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             pefull_bits ^= 1u << s;
           }
           tc_fence_after();
-          const bool mstamp = P.timing && blockIdx.x == 0 && it == T2_STAMP_IT && lane == 0;
+          const bool mstamp = T2_TIMING && P.timing && blockIdx.x == 0 && it == T2_STAMP_IT && lane == 0;
           const uint32_t t_m0 = mstamp ? (uint32_t)clock64() : 0u;
           uint32_t t_wf = 0;
           if (op <= 6) {
@@ -390,7 +413,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     auto wrap = [](uint32_t p) -> uint32_t { return p >= (uint32_t)T2_SLOTS ? p - T2_SLOTS : p; };
     auto wait_free = [&](uint32_t slot, bool fwd_consumed) {   // fwd_consumed: class of the unit about to be written
       if ((need_bits >> slot) & 1u) {
-        mbar_wait2h(bar_afree + 8 * slot, (free_bits >> slot) & 1u, dbg, 0x600 + slot);
+        mbar_wait_slot(bar_afree + 8 * slot, (free_bits >> slot) & 1u, dbg, 0x600 + slot);
         free_bits ^= 1u << slot;
       }
       need_bits = fwd_consumed ? (need_bits | (1u << slot)) : (need_bits & ~(1u << slot));
@@ -409,7 +432,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
 #endif
       accfull_bits ^= 1u << s;
       tc_fence_after();
-      if (stamp_at) stamp_at[0] = clock64();
+      if (T2_TIMING && stamp_at) stamp_at[0] = clock64();
     };
     auto acc_release = [&](int s) {   // every tcgen05.ld of this phase has completed (tcgen05.wait::ld)
       tc_fence_before();
@@ -524,7 +547,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       ox = p1.x; oy = p1.y; oz = p1.z;
       if (n_iter > 0) { produce_pe(cx, cy, cz, 0); produce_pe(ox, oy, oz, 1); }
     }
-    const bool stamp = P.timing && blockIdx.x == 0 && threadIdx.x == 0;
+    const bool stamp = T2_TIMING && P.timing && blockIdx.x == 0 && threadIdx.x == 0;
     for (int64_t it = 0; it < n_iter; ++it) {
       if (stamp && it == T2_STAMP_IT) P.timing[0] = clock64();
       for (int op = 0; op < T2_NUM_OPS; ++op) {
@@ -534,7 +557,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           const bool live = base + row < n_active;
           const uint32_t t_acc = t_lane + (uint32_t)s * TM_ACC;
           uint32_t* const rs = rscr + s * (7 * 2 * 512);
-          stamp_at = (stamp && it == T2_STAMP_IT) ? P.timing + 2 + 2 * (2 * op + s) : nullptr;
+          if (T2_TIMING) stamp_at = (stamp && it == T2_STAMP_IT) ? P.timing + 2 + 2 * (2 * op + s) : nullptr;
           if (op <= 6) {
             // ---------- forward layer: bias + ReLU, ReLU bits, fp16 hi / lo units of the next layer's operand.  Layer 6 (density head in
             // fp32, hi-only units for a single-pass rgb head) is a separate instantiation: as predicated code inside the common body it
@@ -755,7 +778,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             }
             acc_release(s);
           }
-          if (stamp_at) stamp_at[1] = clock64();
+          if (T2_TIMING && stamp_at) stamp_at[1] = clock64();
           // the next phase belongs to the other tile slot
           { float t;
             t = cx; cx = ox; ox = t; t = cy; cy = oy; oy = t; t = cz; cz = oz; oz = t; t = csig; csig = osig; osig = t;

@@ -19,7 +19,7 @@ ENTRY_POINTS = [
     "dsnerf_abi_version", "dsnerf_create", "dsnerf_destroy", "dsnerf_last_error", "dsnerf_set_weights",
     "dsnerf_set_mesh", "dsnerf_set_frame", "dsnerf_render", "dsnerf_render_train", "dsnerf_render_host", "dsnerf_render_host_async", "dsnerf_wait", "dsnerf_render_gather", "dsnerf_render_z",
     "dsnerf_resample", "dsnerf_composite", "dsnerf_composite_noise", "dsnerf_warp_points", "dsnerf_query_density", "dsnerf_eval_points", "dsnerf_ppts_to_pts", "dsnerf_camera_rays",
-    "dsnerf_last_transparent_mask", "dsnerf_tensor_path_active",
+    "dsnerf_last_transparent_mask", "dsnerf_tensor_path_active", "dsnerf_mlp_kernel_variant",
     "dsnerf_get_stats", "dsnerf_profile", "dsnerf_profile_read", "dsnerf_debug_tc_timing", "dsnerf_debug_table", "dsnerf_debug_sm_clock", "dsnerf_debug_active",
 ]
 
@@ -77,6 +77,7 @@ def load():
     L.dsnerf_camera_rays.argtypes = [vp, ci, ci, vp, vp, vp, fp, fp, fp, fp, fp, vp, vp]
     L.dsnerf_last_transparent_mask.argtypes = [vp, i64, ci, vp, vp]
     L.dsnerf_tensor_path_active.argtypes = [vp]
+    L.dsnerf_mlp_kernel_variant.argtypes = [vp]
     L.dsnerf_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.dsnerf_profile.argtypes = [vp, ci]
     L.dsnerf_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ci]

@@ -214,6 +214,13 @@ int dsnerf_last_transparent_mask(dsnerf_ctx* ctx, int64_t n_rays, int n_samples,
  * outside fp16 range (|w| >= 60000): every evaluation runs on the fp32 CUDA kernel (slower); < 0 without weights. */
 int dsnerf_tensor_path_active(const dsnerf_ctx* ctx);
 
+/* Which tcgen05 kernel evaluates SpaceNet on this context: 2 = two 128-point tiles in flight per CTA (csrc/mlp_tc2.cuh: the
+ * operands of both tiles share one FIFO ring of shared-memory slots, one TMEM accumulator per tile; the default), 1 = one tile
+ * per CTA (csrc/mlp_tc.cuh; also serves density-only calls and is selected for everything with DSNERF_MLP_VARIANT=1 in the
+ * environment at dsnerf_create time).  Both compute the same arithmetic: density and essence bit-identical, the gradient's
+ * chain rule differs in the last bits. */
+int dsnerf_mlp_kernel_variant(const dsnerf_ctx* ctx);
+
 /* Counters of the last render on this context (synchronises the stream it ran on). */
 int dsnerf_get_stats(dsnerf_ctx* ctx, dsnerf_stats_t* out);
 

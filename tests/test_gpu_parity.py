@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 import os
 
 MODES = {"tc": 2 if os.environ.get("DSNERF_TEST_FORCE_SIMT") else 0, "simt": 2}
+MODES["tc1"] = MODES["tc"]
 
 
 def make_cfg(n, mode="GG", fine=-1):
@@ -27,7 +28,19 @@ def make_renderer(sc, n, mode="GG", mlp="tc", net=None, fine=-1):
     from dual_space_nerf_b200.renderer import Renderer
 
     net = net or N.synthetic_net(0)
-    r = Renderer(net, None, make_cfg(n, mode, fine), torch.from_numpy(sc["canonical"]), device=0, faces=sc["faces"])
+    # "tc" = the default tcgen05 kernel (two tiles in flight per CTA), "tc1" = the one-tile kernel (chosen when the context is created)
+    old = os.environ.get("DSNERF_MLP_VARIANT")
+    if mlp == "tc1":
+        os.environ["DSNERF_MLP_VARIANT"] = "1"
+    try:
+        r = Renderer(net, None, make_cfg(n, mode, fine), torch.from_numpy(sc["canonical"]), device=0, faces=sc["faces"])
+    finally:
+        if mlp == "tc1":
+            if old is None:
+                del os.environ["DSNERF_MLP_VARIANT"]
+            else:
+                os.environ["DSNERF_MLP_VARIANT"] = old
+    assert r.ctx.L.dsnerf_mlp_kernel_variant(r.ctx.h) == (1 if mlp == "tc1" else int(old or 2))
     r.flags_extra = MODES[mlp]
     r.eval()
     return r
@@ -52,7 +65,7 @@ def kink_rays(st, n):
     return (st["kink_margin"] < C.KINK_MARGIN).reshape(-1, n).any(1)
 
 
-@pytest.mark.parametrize("mlp", ["tc", "simt"])
+@pytest.mark.parametrize("mlp", ["tc", "tc1", "simt"])
 def test_render_view_config1_vs_reference_golden(mlp, scene64, state_dict):
     """Config 1 (64x64, 32 samples) full frame against the reference's own render_view output."""
     g = C.golden("render_64x64x32.npz")
@@ -69,7 +82,7 @@ def test_render_view_config1_vs_reference_golden(mlp, scene64, state_dict):
     assert r.ctx.stats()["evaluated_samples"] == int((~st["mask"]).sum())
 
 
-@pytest.mark.parametrize("mlp", ["tc", "simt"])
+@pytest.mark.parametrize("mlp", ["tc", "tc1", "simt"])
 def test_render_128x128x64_vs_reference_golden(mlp, state_dict):
     g = C.golden("render_128x128x64.npz")
     rays = g["rays"]

@@ -39,7 +39,7 @@ for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
         tot[k] += a[k] / n_frames
 print(f"{'ALL KERNELS, per frame':52s} {'':14s} {tot['ns'] / 1e3:10.1f} {tot['rd'] / 1e6:11.2f} {tot['wr'] / 1e6:11.2f}")
 if len(sys.argv) > 3:
-    mlp = next((a for n, a in agg.items() if "mlp_tc_kernel" in n), None)
+    mlp = next((a for n, a in agg.items() if "mlp_tc" in n), None)
     out = {
         "source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none ({path}), {n_frames} frame(s)",
         "dram_bytes_per_launch": None if mlp is None else (mlp["rd"] + mlp["wr"]) / max(mlp["n"], 1),

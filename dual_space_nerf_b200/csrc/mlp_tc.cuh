@@ -856,8 +856,6 @@ struct TcWeights {
   void* d_pack = nullptr;
   void* d_pack2 = nullptr;   // the same weights in the op schedule of mlp_tc2.cuh (two tiles in flight)
   TcOp ops2[16];
-  size_t pack2_bytes = 0;    // size of one copy of d_pack2 (a multiple of 256)
-  int pack2_copies = 1;      // identical copies of d_pack2 back to back: CTA pairs spread their weight stream over them
   float* d_f32 = nullptr;  // biases 0..6 (7x256; row 0 per frame), b_rgb1 (128), w_rgb2 (384), w_dens (256), seed half2 pairs (128 words)
   float b_rgb2[3] = {0, 0, 0};
   float b_dens = 0.f, seed_scale = 1.f, stash_scale = 1.f;
@@ -1046,16 +1044,10 @@ struct TcWeights {
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(d_pack, blob.data(), blob.size() * sizeof(__half), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int)e;
-    while (blob2.size() % 128) blob2.push_back(__float2half_rn(0.f));
-    pack2_bytes = blob2.size() * sizeof(__half);
-    pack2_copies = 1;
-    if (const char* ev = getenv("DSNERF_W_REPLICAS")) pack2_copies = std::max(1, std::min(16, atoi(ev)));
-    e = cudaMalloc(&d_pack2, pack2_bytes * pack2_copies);
+    e = cudaMalloc(&d_pack2, blob2.size() * sizeof(__half));
     if (e != cudaSuccess) return (int)e;
-    for (int c = 0; c < pack2_copies; ++c) {
-      e = cudaMemcpy(reinterpret_cast<uint8_t*>(d_pack2) + (size_t)c * pack2_bytes, blob2.data(), pack2_bytes, cudaMemcpyHostToDevice);
-      if (e != cudaSuccess) return (int)e;
-    }
+    e = cudaMemcpy(d_pack2, blob2.data(), blob2.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
     std::vector<float> f(F32_TOTAL, 0.f);
     const std::vector<float>* bs[6] = {&b1, &b2, &b3, &b4, &b5, &b6};
     for (int l = 0; l < 6; ++l)

@@ -49,6 +49,9 @@ constexpr uint32_t S2_BAR = S2_RGBW + 2048;                      // 231424
 constexpr uint32_t T2_SMEM = S2_BAR + 272;                       // 231696 (32 barriers + the TMEM base slot)
 constexpr uint32_t TM_XCH = 128;                                 // exchange columns inside a tile's accumulator (free at the rgb op and the last op)
 constexpr int T2_NUM_OPS = 16;
+#ifndef T2_SHARE_SLABS
+#define T2_SHARE_SLABS 1   // ops 7..15 (at most four 16 KB slabs = the whole weight ring): both tiles use one copy of each slab
+#endif
 #ifndef T2_TIMING
 #define T2_TIMING 0   // 1: per-phase clock64 stamps of CTA 0 (tests/tc2_timing.py needs a build with -DT2_TIMING=1)
 #endif
@@ -58,8 +61,6 @@ constexpr uint32_t T2_KSTEP = 2 * A_CHUNK;                       // bytes per k-
 struct Tc2Params {
   TcOp ops[T2_NUM_OPS];
   const uint8_t* wpack;
-  uint32_t wpack_stride;    // bytes between identical copies of the packed weights
-  uint32_t wpack_copies;
   const float* bias;        // [7][256]
   const float* b_rgb1;
   const float* w_rgb2;
@@ -101,11 +102,6 @@ __device__ __forceinline__ void mbar_wait2(uint32_t a, uint32_t parity, unsigned
   mbar_wait(a, parity);
 }
 
-#ifdef T2_NO_RELAY   // measurement only: the leader does not wait for the peer's half (results may be garbage)
-#define T2_WFULL_LEADER_COUNT(rank) 1
-#else
-#define T2_WFULL_LEADER_COUNT(rank) ((rank) == 0 ? 2 : 1)
-#endif
 #ifndef T2_WAIT_HINT
 #define T2_WAIT_HINT 1000   // ns; 0 = plain polling
 #endif
@@ -209,7 +205,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
   unsigned int* const dbg = P.dbg;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < T2_WST; ++s) { mbar_init(bar_wfull + 8 * s, T2_WFULL_LEADER_COUNT(cta_rank)); mbar_init(bar_wempty + 8 * s, 1); }
+    for (int s = 0; s < T2_WST; ++s) { mbar_init(bar_wfull + 8 * s, cta_rank == 0 ? 2 : 1); mbar_init(bar_wempty + 8 * s, 1); }
     for (int s = 0; s < T2_SLOTS; ++s) { mbar_init(bar_pefull + 8 * s, 2 * TC_EPI_WARPS); mbar_init(bar_afree + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accfree + 8 * s, 2 * TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -245,21 +241,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     for (int64_t it = 0; it < n_iter; ++it) {
       for (int op = 0; op < T2_NUM_OPS; ++op) {
         const TcOp o = P.ops[op];
-        const uint8_t* src = P.wpack + (size_t)((blockIdx.x >> 1) % P.wpack_copies) * P.wpack_stride + o.src_off + (size_t)cta_rank * o.slab_bytes;
-        for (int s2 = 0; s2 < 2; ++s2) {
+        const uint8_t* src = P.wpack + o.src_off + (size_t)cta_rank * o.slab_bytes;
+        // forward layers stream their slabs once per tile; an op of the backward half fits the ring (<= 4 slabs), so its slabs are
+        // loaded once per tile PAIR: the MMA warp reads them for tile slot 0 without releasing and again for tile slot 1
+        const int passes = (T2_SHARE_SLABS && op >= 7) ? 1 : 2;
+        for (int s2 = 0; s2 < passes; ++s2) {
           for (int s = 0; s < o.n_slabs; ++s) {
-            if (P.debug_noload == 1) continue;
+            if (P.debug_noload) continue;
             mbar_wait2(bar_wempty + 8 * stage, phase ^ 1, dbg, 0x100 + stage);
             if (elect_one()) {
               mbar_expect_tx(bar_wfull + 8 * stage, o.slab_bytes);
-#ifdef T2_SPLIT_COPIES
-              const uint32_t piece = o.slab_bytes / T2_SPLIT_COPIES;
-#pragma unroll
-              for (int c = 0; c < T2_SPLIT_COPIES; ++c)
-                bulk_g2s(sbase + S2_RING + stage * TC_STAGE_BYTES + c * piece, src + (size_t)s * 2 * o.slab_bytes + c * piece, piece, bar_wfull + 8 * stage);
-#else
               bulk_g2s(sbase + S2_RING + stage * TC_STAGE_BYTES, src + (size_t)s * 2 * o.slab_bytes, o.slab_bytes, bar_wfull + 8 * stage);
-#endif
             }
             __syncwarp();
             if (++stage == T2_WST) { stage = 0; phase ^= 1; }
@@ -273,13 +265,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     const uint32_t leader_wfull = mapa_u32(bar_wfull, 0);
     for (int64_t it = 0; it < n_iter; ++it) {
       for (int op = 0; op < T2_NUM_OPS; ++op) {
-        const int n_slabs = 2 * P.ops[op].n_slabs;
+        const int n_slabs = ((T2_SHARE_SLABS && op >= 7) ? 1 : 2) * P.ops[op].n_slabs;
         for (int s = 0; s < n_slabs; ++s) {
-          if (P.debug_noload == 1) continue;
+          if (P.debug_noload) continue;
           mbar_wait2(bar_wfull + 8 * stage, phase, dbg, 0x200 + stage);
-#ifndef T2_NO_RELAY
           if (lane == 0) mbar_arrive_cluster(leader_wfull + 8 * stage);
-#endif
           __syncwarp();
           if (++stage == T2_WST) { stage = 0; phase ^= 1; }
         }
@@ -303,11 +293,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
 #define T2_WAIT_W()                                                                      \
   do {                                                                                   \
     const uint32_t t_a = mstamp ? (uint32_t)clock64() : 0u;                              \
-    if (P.debug_noload != 1) mbar_wait2(bar_wfull + 8 * wstage, wphase, dbg, 0x400 + wstage); \
+    if (!P.debug_noload) mbar_wait2(bar_wfull + 8 * wstage, wphase, dbg, 0x400 + wstage); \
     if (mstamp) t_wf += (uint32_t)clock64() - t_a;                                       \
     tc_fence_after();                                                                    \
   } while (0)
 #define T2_NEXT_W() do { if (++wstage == T2_WST) { wstage = 0; wphase ^= 1; } } while (0)
+#define T2_WE() (share_first ? 0u : bar_wempty + 8 * wstage)
     for (int64_t it = 0; it < n_iter; ++it) {
       for (int op = 0; op < T2_NUM_OPS; ++op) {
         for (int s = 0; s < 2; ++s) {
@@ -322,6 +313,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           const bool mstamp = T2_TIMING && P.timing && blockIdx.x == 0 && it == T2_STAMP_IT && lane == 0;
           const uint32_t t_m0 = mstamp ? (uint32_t)clock64() : 0u;
           uint32_t t_wf = 0;
+          const bool share_first = T2_SHARE_SLABS && op >= 7 && s == 0;
+          const uint32_t ws_save = wstage, wp_save = wphase;
           if (op <= 6) {
             // forward: units of hi + lo slots, two weight slabs (of 2 k-steps) per unit
             const int n_units = op == 0 ? 1 : (op == 4 ? 5 : 4);
@@ -346,7 +339,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
                 cpos = wrap(cpos + 2);
                 T2_WAIT_W();
                 issue_unit<64, 4, 3, 128>(d, T2_SLOT_WORD(h), T2_SLOT_WORD(l), (((64 * 16) >> 4) << 16) | (w_base + wstage * (TC_STAGE_BYTES >> 4)),
-                                          (uint32_t)(u > 0), bar_wempty + 8 * wstage, bar_afree + 8 * h, bar_afree + 8 * l);
+                                          (uint32_t)(u > 0), T2_WE(), bar_afree + 8 * h, bar_afree + 8 * l);
                 T2_NEXT_W();
               }
             } else {        // hi units, two units per slab
@@ -356,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
                 T2_WAIT_W();
                 const uint32_t bw = (((64 * 16) >> 4) << 16) | (w_base + wstage * (TC_STAGE_BYTES >> 4));
                 issue_unit<64, 4, 1, 128>(d, T2_SLOT_WORD(h0), 0u, bw, (uint32_t)(sl > 0), 0u, bar_afree + 8 * h0, 0u);
-                issue_unit<64, 4, 1, 128>(d, T2_SLOT_WORD(h1), 0u, bw + ((4 * 2 * 64 * 16) >> 4), 1u, bar_wempty + 8 * wstage, bar_afree + 8 * h1, 0u);
+                issue_unit<64, 4, 1, 128>(d, T2_SLOT_WORD(h1), 0u, bw + ((4 * 2 * 64 * 16) >> 4), 1u, T2_WE(), bar_afree + 8 * h1, 0u);
                 T2_NEXT_W();
               }
             }
@@ -370,7 +363,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               issue_unit<32, 4, 1, 64>(d, T2_SLOT_WORD(wrap(p0 + u)), 0u, bw + u * ((4 * 2 * 32 * 16) >> 4), (uint32_t)(u > 0),
-                                       u == 3 ? bar_wempty + 8 * wstage : 0u, 0u, 0u);
+                                       u == 3 ? T2_WE() : 0u, 0u, 0u);
             T2_NEXT_W();
           } else {
             // backward layer: hi units, one slab per unit; nothing waits for these slots (see the epilogue)
@@ -379,10 +372,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
               cpos = wrap(cpos + 1);
               T2_WAIT_W();
               issue_unit<128, 4, 1, 256>(d, T2_SLOT_WORD(h), 0u, (((128 * 16) >> 4) << 16) | (w_base + wstage * (TC_STAGE_BYTES >> 4)), (uint32_t)(u > 0),
-                                         bar_wempty + 8 * wstage, 0u, 0u);
+                                         T2_WE(), 0u, 0u);
               T2_NEXT_W();
             }
           }
+          if (share_first) { wstage = ws_save; wphase = wp_save; }   // tile slot 1 reads the same slabs (and releases them)
           if (elect_one()) tc_commit2(bar_accfull + 8 * s);
           __syncwarp();
           if (mstamp) P.timing[66 + 2 * op + s] = (long long)(((unsigned long long)(uint32_t)clock64() << 32) | t_m0);
@@ -393,6 +387,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
 #undef T2_SLOT_WORD
 #undef T2_WAIT_W
 #undef T2_NEXT_W
+#undef T2_WE
   } else {
     // =============================== epilogue warps ===============================
     const int q = warp & 3, sub = warp >> 2;
@@ -423,13 +418,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     auto publish = [&](uint32_t) { fence_proxy_async(); };
     long long* stamp_at = nullptr;   // debug stamps of the current phase (CTA 0, thread 0, first tile pair)
     auto acc_wait = [&](int s) {
-#ifdef T2_ONE_POLLER
-      // one warp polls the mbarrier, the other fifteen wait at a hardware barrier (no instructions issued while they wait)
-      if (warp == 0) mbar_wait2h(bar_accfull + 8 * s, (accfull_bits >> s) & 1u, dbg, 0x700 + s);
-      epi_bar();
-#else
       mbar_wait2h(bar_accfull + 8 * s, (accfull_bits >> s) & 1u, dbg, 0x700 + s);
-#endif
       accfull_bits ^= 1u << s;
       tc_fence_after();
       if (T2_TIMING && stamp_at) stamp_at[0] = clock64();
@@ -754,7 +743,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             for (int q4 = 0; q4 < 4; ++q4) {
               uint32_t(&v)[16] = (q4 & 1) ? vb : va;
               tmem_wait_ld(v);
-              if (q4 < 3 && P.debug_noload != 2) { if (q4 & 1) tmem_ld16_nowait(t_accb + (q4 + 1) * 64, va); else tmem_ld16_nowait(t_accb + (q4 + 1) * 64, vb); }
+              if (q4 < 3) { if (q4 & 1) tmem_ld16_nowait(t_accb + (q4 + 1) * 64, va); else tmem_ld16_nowait(t_accb + (q4 + 1) * 64, vb); }
               const uint32_t mw = (q4 >> 1) ? m1 : m0;
               uint32_t g[8];
 #pragma unroll
@@ -770,10 +759,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
               ppos = wrap(ppos + 1);
               const uint32_t off = (uint32_t)(2 * sub) * A_CHUNK + row_off;
               wait_free(hs, false);
-              if (P.debug_noload != 3) {
-                *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off) = make_uint4(g[0], g[1], g[2], g[3]);
-                *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off + A_CHUNK) = make_uint4(g[4], g[5], g[6], g[7]);
-              }
+              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off) = make_uint4(g[0], g[1], g[2], g[3]);
+              *reinterpret_cast<uint4*>(smem + S2_A + hs * T2_SLOT + off + A_CHUNK) = make_uint4(g[4], g[5], g[6], g[7]);
               publish(hs);
             }
             acc_release(s);
@@ -811,8 +798,6 @@ inline int tc2_launch(TcWeights& w, long long* timing, unsigned int* dbg, int de
   Tc2Params p{};
   for (int i = 0; i < T2_NUM_OPS; ++i) p.ops[i] = w.ops2[i];
   p.wpack = reinterpret_cast<const uint8_t*>(w.d_pack2);
-  p.wpack_stride = (uint32_t)w.pack2_bytes;
-  p.wpack_copies = (uint32_t)w.pack2_copies;
   p.bias = w.d_f32;
   p.b_rgb1 = w.d_f32 + TcWeights::F32_BRGB1;
   p.w_rgb2 = w.d_f32 + TcWeights::F32_WRGB2;

@@ -43,7 +43,8 @@ if len(sys.argv) > 3:
     out = {
         "source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none ({path}), {n_frames} frame(s)",
         "dram_bytes_per_launch": None if mlp is None else (mlp["rd"] + mlp["wr"]) / max(mlp["n"], 1),
-        "dram_bytes_per_frame": tot["rd"] + tot["wr"],
+        # the path's own kernels only: bench.py's L2 flush (a 256 MB fill) and its clock probe are part of the list but not of the path
+        "dram_bytes_per_frame": sum((a["rd"] + a["wr"]) / n_frames for n, a in agg.items() if n.startswith("dsn::")),
         "per_kernel_per_frame": {n: {"launches": a["n"] / n_frames, "us": a["ns"] / n_frames / 1e3, "dram_bytes": (a["rd"] + a["wr"]) / n_frames}
                                  for n, a in agg.items()},
     }

@@ -17,4 +17,8 @@ ncu --set full --clock-control none -k regex:"build_cells|sample_warp|light_tc|c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu -i gpurun_out/${TAG}_mlp.ncu-rep --page raw --csv > gpurun_out/${TAG}_mlp_raw.csv 2>/dev/null
 ncu -i gpurun_out/${TAG}_tail.ncu-rep --page raw --csv > gpurun_out/${TAG}_tail_raw.csv 2>/dev/null
+# per-phase clock stamps of the two-tile MLP kernel (measurement build: make -C dual_space_nerf_b200/csrc ../libdsnerf_timing.so)
+if [ -f dual_space_nerf_b200/libdsnerf_timing.so ]; then
+  DSNERF_LIB=$PWD/dual_space_nerf_b200/libdsnerf_timing.so python tests/tc2_timing.py > gpurun_out/${TAG}_tc2_phase_stamps.log 2>&1
+fi
 tail -4 gpurun_out/${TAG}_tests.log; cat gpurun_out/${TAG}_smoke.log | tail -2

@@ -12,12 +12,17 @@
 // How it fits here.
 //   * The A operands of BOTH tiles live in one FIFO ring of ten 16 KB slots (a "unit" = 64 operand columns of a tile = one
 //     hi slot [8 chunks][128 rows][8 halves], plus one lo slot for the 3-pass forward operands).  The epilogue warps produce
-//     units in exactly the order in which the MMA warp consumes them (tile X layer l, tile Y layer l, X l+1, Y l+1, ...), so
-//     the ring needs one "full" barrier (32 epilogue warps of the pair arrive) and one "free" barrier (tcgen05.commit after
-//     the last MMA that read the slot) per slot and nothing else.  While the MMAs of (X, l+1) drain X's four units, the
-//     epilogue of (Y, l) refills the slots behind them: 160 KB hold what would need 256 KB as private buffers.
+//     units in exactly the order in which the MMA warp consumes them (tile X layer l, tile Y layer l, X l+1, Y l+1, ...).
+//     While the MMAs of (X, l+1) drain X's four units, the epilogue of (Y, l) refills the slots behind them: 160 KB hold
+//     what would need 256 KB as private buffers.  A slot is handed back through a per-slot "free" barrier (tcgen05.commit
+//     after the last MMA that read it) -- only where it is needed: a slot last read by a backward op is rewritten by a
+//     phase that has already seen a later accumulator.  There is no per-unit "full" barrier: the accumulator release at the
+//     end of a phase tells the MMA warp that all units of the phase are written and fenced (the encoding unit of op 0,
+//     written a phase earlier, has a barrier of its own).
 //   * Each tile owns ONE 256-column TMEM accumulator, used in place: the epilogue of (X, l) has read it completely before
 //     the MMAs of (X, l+1) overwrite it ("acc free" barrier), and the MMAs of the other tile fill that time.
+//   * Weights: forward layers stream their 16 KB half-slabs once per tile through a 4-stage ring; an op of the backward half
+//     fits the ring, so its slabs are loaded once per tile PAIR (read for tile slot 0 without releasing, again for slot 1).
 //   * The positional encoding is not kept: it is a unit like any other, produced when layer 0 and layer 4 need it
 //     (recomputed; ~30 instructions per sincos), and the chain rule at the end of the gradient recomputes sin / cos with the
 //     fast intrinsics (the gradient chain is fp16).
@@ -29,6 +34,10 @@
 //   * sigma and the rgb head's output leave the kernel at the rgb op, the gradient at the last op (partial sums of the four
 //     threads of a row through TMEM: the accumulator columns that the N = 128 / N = 64 products of those ops leave unused;
 //     the four threads of a row sit in warps q, q+4, q+8, q+12, which all reach TMEM lane quarter q).
+//
+// The kernel runs at the power cap: instruction count shows up as clock.  Hence wait loops without bookkeeping, nanosleep
+// back-off where the waiter is ahead of the tensor pipe, layer 6 as its own instantiation instead of predicated code,
+// and the MMA warp's loop reduced to one wait per slab (DESIGN.md 4b has the measurements).
 //
 // Op schedule of a tile (16 ops): 0-6 forward layers, 7 rgb head (its epilogue also writes the backward seed units),
 // 8 bW6, 9 bW5, 10 d sigma / d PE through layer 4 (N = 64, no release), 11 bW4, 12 bW3, 13 bW2, 14 bW1, 15 bW0 (N = 64).

@@ -422,9 +422,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       }
       need_bits = fwd_consumed ? (need_bits | (1u << slot)) : (need_bits & ~(1u << slot));
     };
-    // a unit becomes visible to the tensor core (async proxy) with this fence; the MMA warp learns about it through the
-    // accumulator release at the end of the phase (or, for the encoding unit of op 0, through bar_pefull)
-    auto publish = [&](uint32_t) { fence_proxy_async(); };
+    // A unit becomes visible to the tensor core (async proxy) through ONE fence.proxy.async per phase, in front of the
+    // accumulator release that tells the MMA warp about the phase's units (a fence per unit is a MEMBAR per unit on the
+    // backward chain); the encoding unit of op 0 is announced through bar_pefull and carries its own fence.
+    auto publish = [&](uint32_t) {};
     long long* stamp_at = nullptr;   // debug stamps of the current phase (CTA 0, thread 0, first tile pair)
     auto acc_wait = [&](int s) {
       mbar_wait2h(bar_accfull + 8 * s, (accfull_bits >> s) & 1u, dbg, 0x700 + s);
@@ -433,6 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       if (T2_TIMING && stamp_at) stamp_at[0] = clock64();
     };
     auto acc_release = [&](int s) {   // every tcgen05.ld of this phase has completed (tcgen05.wait::ld)
+      fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_accfree + 8 * s);
@@ -497,8 +499,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       *reinterpret_cast<uint4*>(smem + S2_A + h * T2_SLOT + off + A_CHUNK) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
       *reinterpret_cast<uint4*>(smem + S2_A + l * T2_SLOT + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       *reinterpret_cast<uint4*>(smem + S2_A + l * T2_SLOT + off + A_CHUNK) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-      publish(h);
       if (pe_slot >= 0) {
+        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_pefull + 8 * pe_slot);
       }

@@ -389,32 +389,34 @@ def test_hierarchical_config3_at_stated_size(state_dict):
 
 def test_two_tile_kernel_matches_one_tile_kernel(scene64):
     """The two tcgen05 kernels (csrc/mlp_tc2.cuh: two tiles in flight per CTA, the default; csrc/mlp_tc.cuh: one tile) compute the
-    same arithmetic: through dsnerf_eval_points on 40 000 canonical points near the surface (313 tiles: several iterations per CTA
-    pair, partial last tile, idle CTAs) the density is bit-identical and the colour differs only through the last bits of the
-    gradient's chain rule (fast sincos), far inside the 1e-4 budget; both are deterministic."""
+    same arithmetic: through dsnerf_eval_points on canonical points near the surface the density is bit-identical and the colour
+    differs only through the last bits of the gradient's chain rule (fast sincos), far inside the 1e-4 budget; both are
+    deterministic.  Sizes: 40 000 points (313 tiles: several iterations per CTA pair, an odd tile count on some pairs, a partial
+    last tile, idle CTAs) and the edges of the tiling (1, 129, one tile per CTA + 1 point)."""
     sc = scene64
-    rng = np.random.RandomState(7)
-    n = 40000
-    vid = rng.randint(0, sc["canonical"].shape[0], n)
-    xc = (sc["canonical"][vid] + rng.randn(n, 3).astype(np.float32) * 0.02).astype(np.float32)
-    xw = (xc + np.array([0.2, -0.1, 1.0], np.float32)).astype(np.float32)
-    vd = rng.randn(n, 3).astype(np.float32)
-    pos = torch.from_numpy(np.concatenate([xw, xc], 1))
-    rays = torch.from_numpy(np.concatenate([vd, vd], 1))
     b = S.to_batch(sc, torch)
-    res = {}
-    for mlp in ("tc", "tc1", "simt"):
-        r = make_renderer(sc, 32, mlp=mlp)
-        out = []
-        for _ in range(2):
-            c, d, _m = r._net_forward(pos, rays, None, b, False)
-            out.append((c.cpu().numpy(), d.cpu().numpy().ravel()))
-        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), f"{mlp} is not deterministic"
-        res[mlp] = out[0]
-    assert np.array_equal(res["tc"][1], res["tc1"][1]), "density of the two tcgen05 kernels differs"
-    dc = np.abs(res["tc"][0] - res["tc1"][0]).max()
-    assert dc < 5e-5, dc
-    # and both against the fp32 kernel: density within the 3-pass split's error, colour like every other tensor-core result
-    for mlp in ("tc", "tc1"):
-        assert np.abs(res[mlp][1] - res["simt"][1]).max() < 2e-3 * max(1.0, np.abs(res["simt"][1]).max())
-        assert np.percentile(np.abs(res[mlp][0] - res["simt"][0]).max(1), 99) < 1e-4
+    rend = {mlp: make_renderer(sc, 32, mlp=mlp) for mlp in ("tc", "tc1", "simt")}
+    for n in (40000, 1, 129, 148 * 128 + 1):
+        rng = np.random.RandomState(7 + n)
+        vid = rng.randint(0, sc["canonical"].shape[0], n)
+        xc = (sc["canonical"][vid] + rng.randn(n, 3).astype(np.float32) * 0.02).astype(np.float32)
+        xw = (xc + np.array([0.2, -0.1, 1.0], np.float32)).astype(np.float32)
+        vd = rng.randn(n, 3).astype(np.float32)
+        pos = torch.from_numpy(np.concatenate([xw, xc], 1))
+        rays = torch.from_numpy(np.concatenate([vd, vd], 1))
+        res = {}
+        for mlp in ("tc", "tc1", "simt") if n == 40000 else ("tc", "tc1"):
+            r = rend[mlp]
+            out = []
+            for _ in range(2):
+                c, d, _m = r._net_forward(pos, rays, None, b, False)
+                out.append((c.cpu().numpy(), d.cpu().numpy().ravel()))
+            assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), f"{mlp} is not deterministic (n = {n})"
+            res[mlp] = out[0]
+        assert np.array_equal(res["tc"][1], res["tc1"][1]), f"density of the two tcgen05 kernels differs (n = {n})"
+        dc = np.abs(res["tc"][0] - res["tc1"][0]).max()
+        assert dc < 5e-5, (n, dc)
+        if n == 40000:  # and both against the fp32 kernel: density within the 3-pass split's error, colour like every other tensor-core result
+            for mlp in ("tc", "tc1"):
+                assert np.abs(res[mlp][1] - res["simt"][1]).max() < 2e-3 * max(1.0, np.abs(res["simt"][1]).max())
+                assert np.percentile(np.abs(res[mlp][0] - res["simt"][0]).max(1), 99) < 1e-4

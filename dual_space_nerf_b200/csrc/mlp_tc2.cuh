@@ -407,12 +407,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     uint32_t ppos = 0;              // ring position of the next unit to produce
     // bar_afree is used only for units that a forward op or the rgb head consumes (ops 0..7): a slot whose previous occupant
     // was read by a backward op (8..15) is rewritten only by phases that have already seen an accumulator whose MMAs were
-    // issued after that op, so it needs neither a commit nor a wait (the backward slab loop is issue bound: one commit less)
+    // issued after that op, so it needs neither a commit nor a wait
     uint32_t free_bits = 0;         // per-slot parity of bar_afree
     uint32_t need_bits = 0;         // slot's current occupant is consumed by an op <= 7: its next writer waits on bar_afree
     uint32_t accfull_bits = 0;
-    const int k_lo = pe_k0(sub), k_hi = pe_k0(sub + 1);
-    (void)k_lo; (void)k_hi;
     uint32_t* const rscr = P.relu_scratch + (size_t)blockIdx.x * (2 * 7 * 2 * 512) + threadIdx.x;
     auto wrap = [](uint32_t p) -> uint32_t { return p >= (uint32_t)T2_SLOTS ? p - T2_SLOTS : p; };
     auto wait_free = [&](uint32_t slot, bool fwd_consumed) {   // fwd_consumed: class of the unit about to be written

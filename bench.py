@@ -474,6 +474,7 @@ def main():
                     "asynchronous ncclAllGather after the render (the baseline it replaces)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the config-4 strong-scaling measurement")
     ap.add_argument("--early-stop", action="store_true", help="optional DSNERF_EARLY_STOP mode (not the headline: the default evaluates every sample)")
+    ap.add_argument("--no-early-stop-line", action="store_true", help="skip the extra early-termination measurement reported beside the headline at N = 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -676,6 +677,37 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         gather_ok = bool(torch.equal(lo, hi)) and bool(torch.allclose(sums, mine, rtol=0, atol=1e-3))
 
+    # ---- optional mode, reported BESIDE the exhaustive headline, never instead of it: the same frame with early ray termination
+    # (DSNERF_EARLY_STOP: front-to-back waves, rays whose transmittance has fallen below 1e-6 skip their remaining samples)
+    early = None
+    if world == 1 and not args.early_stop and not args.simt and not args.no_early_stop_line:
+        fl_es = flags | rig.lib.EARLY_STOP
+        out_es = torch.empty(6 * R, device=dev)
+
+        def step_es():
+            set_frame()
+            ctx.check(L.dsnerf_render(ctx.h, P(d_o), P(d_d), P(d_n), P(d_f), R, N_SAMPLES, fl_es, P(out_es[: 3 * R]), P(out_es[3 * R: 4 * R]),
+                                      P(out_es[4 * R: 5 * R]), P(out_es[5 * R:]), None, None, sp))
+
+        for _ in range(3):
+            step_es()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            flush.fill_(1)
+            step_es()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        es_ms = e0.elapsed_time(e1) / args.steps
+        es_eval = int(ctx.stats()["evaluated_samples"])
+        ref = outs[0]
+        early = {"ms_per_step": es_ms, "value": R / (es_ms * 1e-3), "unit": "rays/s", "evaluated_samples_per_step": es_eval,
+                 "samples_skipped_frac": 1.0 - es_eval / float(evaluated), "transmittance_threshold": 1e-6,
+                 "max_abs_rgb_vs_exhaustive": float((out_es[: 3 * R] - ref[: 3 * R]).abs().max()),
+                 "max_abs_depth_vs_exhaustive": float((out_es[3 * R: 4 * R] - ref[3 * R: 4 * R]).abs().max()),
+                 "max_abs_acc_vs_exhaustive": float((out_es[4 * R: 5 * R] - ref[4 * R: 5 * R]).abs().max()),
+                 "note": "optional flag DSNERF_EARLY_STOP, same frame, device-resident arm; the headline above evaluates every sample"}
+
     strong = None
     if world > 1 and not args.no_strong:
         strong = bench_strong(rig, min(args.steps, 10), 3)
@@ -732,6 +764,8 @@ def main():
         }
         if strong is not None:
             line["strong"] = strong
+        if early is not None:
+            line["early_stop"] = early
         # parity at the benchmark's own size, every run: the frame the e2e arm has just produced against the oracle on
         # 3 x 8192 rays of it.  The same oracle calls are the `cpu_baseline` timing at N = 1 (rank 0 only).
         if not args.no_cpu_baseline:

@@ -98,7 +98,7 @@ struct dsnerf_ctx {
   unsigned int* h_tc_dbg = nullptr;   // mlp_tc2_kernel: watchdog record, mapped host memory (DSNERF_TC_WATCHDOG)
   int mlp_variant = 2;           // 2: two tiles in flight per CTA (mlp_tc2.cuh), 1: one tile (mlp_tc.cuh); DSNERF_MLP_VARIANT
   bool tc_watchdog = false;
-  DevBuf near2, far2, raw, active, active_tri, active_cidx, ray_mask, mlp_a, mlp_g, tvals, counters, io;
+  DevBuf near2, far2, raw, active, active_tri, active_cidx, canon_queue, ray_mask, mlp_a, mlp_g, tvals, counters, io;
   DevBuf ert_active, ert_tri, ert_state, ert_cnt;  // early-ray-termination mode only
   unsigned long long* h_ert = nullptr;              // pinned, 8 entries
   int tvals_n = 0;
@@ -305,7 +305,7 @@ int build_grid(dsnerf_ctx* ctx, MeshGrid& mg, const float* d_verts, const float*
 template <class Mark>
 int ensure_cells(dsnerf_ctx* ctx, MeshGrid& mg, cudaStream_t st, Mark&& mark) {
   CK(cudaMemsetAsync(mg.pool_used.as<int>() + 1, 0, 3 * sizeof(int), st));
-  CK(cudaMemsetAsync(mg.pool_used.as<int>() + 16, 0, 2 * sizeof(int), st));
+  CK(cudaMemsetAsync(mg.pool_used.as<int>() + 16, 0, 4 * sizeof(int), st));  // work counters of the two build levels, [18] / [19] work counter and queue length of canon_nearest_kernel
   mark();
   CKL("mark");
   build_cells_kernel<1><<<ctx->sm_count * 8, BUILD_WARPS * 32, 0, st>>>(mg.g);  // per requested enumeration cell
@@ -419,6 +419,7 @@ int ensure_workspace(dsnerf_ctx* ctx, int64_t R, int N) {
   CK(ctx->active.ensure(sizeof(float4) * (P + 128)));
   CK(ctx->active_tri.ensure(sizeof(int) * (P + 128)));
   CK(ctx->active_cidx.ensure(sizeof(int) * (P + 128)));
+  CK(ctx->canon_queue.ensure(sizeof(int) * (P + 128)));
   CK(ctx->ray_mask.ensure(sizeof(unsigned) * (size_t)((P + 31) / 32 + 8)));
   CK(ctx->mlp_a.ensure(sizeof(float4) * (P + 128)));
   CK(ctx->mlp_g.ensure(sizeof(float4) * (P + 128)));
@@ -512,7 +513,7 @@ int check_ready(dsnerf_ctx* ctx, bool need_frame) {
 
 int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStream_t st, int* launches = nullptr) {
   if (!ctx->tw.fp16_ok) flags |= DSNERF_MLP_FP32_SIMT;
-  if (launches) *launches += (flags & DSNERF_MLP_FP32_SIMT) ? 4 : 5;  // mark_points, build<1>, build<2>, (canon_nearest,) lighting
+  if (launches) *launches += (flags & DSNERF_MLP_FP32_SIMT) ? 4 : 6;  // mark_points, build<1>, build<2>, (canon_nearest, canon_long,) lighting
   // canonical-space lookup cells of the active points (static mesh: cells stay built across frames)
   if (int e = ensure_cells(ctx, ctx->g_canon, st, [&] {
         mark_points_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(sa.active, sa.n_active, sa.n_active_host, ctx->g_canon.g);
@@ -524,8 +525,10 @@ int launch_shade(dsnerf_ctx* ctx, const ShadeArgs& sa, unsigned flags, cudaStrea
   } else {
     ShadeArgs sb = sa;
     canon_nearest_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(sa.active, sa.n_active, sa.n_active_host, ctx->g_canon.g, ctx->g_canon.cent.as<float>(),
-                                                            ctx->F, ctx->active_cidx.as<int>());
+                                                            ctx->F, ctx->active_cidx.as<int>(), ctx->canon_queue.as<int>());
     CKL("canon_nearest");
+    canon_long_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(sa.active, ctx->g_canon.g, ctx->canon_queue.as<int>(), ctx->active_cidx.as<int>());
+    CKL("canon_long");
     sb.active_cidx = ctx->active_cidx.as<int>();
     if (ctx->tw.rgb3)  // precise weight mode: the lighting layer runs the 3-pass split as well (light_tc.cuh)
       light_tc_kernel<true><<<ctx->sm_count, LT_THREADS, LT_SMEM3, st>>>(sb, ctx->lw, ctx->light_w2.as<uint8_t>(), ctx->g_canon.g);

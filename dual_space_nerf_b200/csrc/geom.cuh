@@ -115,7 +115,7 @@ struct Grid {
   int2* __restrict__ trec;                         // per table cell: (off, cnt), see above
   float4* __restrict__ pool;                       // candidate lists
   int pool_cap;
-  int* __restrict__ pool_used;                     // [0] entries used, [1] table-cell requests, [2] enumeration-cell requests, [3] LEVEL-2 left-overs, [4..10] and [13..15] debug counters, [16], [17] work counters of the two build levels
+  int* __restrict__ pool_used;                     // [0] entries used, [1] table-cell requests, [2] enumeration-cell requests, [3] LEVEL-2 left-overs, [4..10] and [13..15] debug counters, [16], [17] work counters of the two build levels, [19] lookups canon_nearest_kernel queued for canon_long_kernel
   int debug;                                       // count build outcomes in pool_used[4..10]
 };
 
@@ -462,8 +462,9 @@ __device__ __forceinline__ void warp_scan_ball_flat(const Grid& g, float px, flo
 #ifndef DSN_LIST_CAP
 #define DSN_LIST_CAP 256
 #endif
-constexpr int LIST_CAP = DSN_LIST_CAP;      // longest candidate list kept; longer ones fall back to the ball scan (64 -> 256: the cells
-                                         // deep inside the body see a whole ring of centroids; 7 % -> 0.5 % of the lookups scan)
+constexpr int LIST_CAP = DSN_LIST_CAP;      // longest candidate list settle_cell assembles in shared memory (64 -> 256: the cells deep
+                                         // inside the body see a whole ring of centroids; 7 % -> 0.5 % of the lookups scanned); longer
+                                         // ones are filtered a second time straight into the pool (settle_cell / long_list)
 #ifndef DSN_BUF_CAP
 #define DSN_BUF_CAP 448
 #endif
@@ -533,18 +534,89 @@ __device__ __forceinline__ int2 settle_cell(const Grid& g, const int* S, int n, 
   if (!search) return make_int2(mi, -1);  // certified transparent
   kind = 7;
   int2 rec = make_int2(mi, -2);
-  if (keep <= LIST_CAP && list != nullptr) {
+  if (list != nullptr) {
     int off = 0;
     if (lane == 0) off = atomicAdd(g.pool_used, keep);
     off = __shfl_sync(0xffffffffu, off, 0);
     if (off + keep <= g.pool_cap) {
-      for (int i = lane; i < keep; i += 32) g.pool[off + i] = __ldg(g.sorted + list[i]);
+      if (keep <= LIST_CAP) {
+        for (int i = lane; i < keep; i += 32) g.pool[off + i] = __ldg(g.sorted + list[i]);
+      } else {  // longer than the scratch list: the same filter once more, straight into the pool
+        int k = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int i = i0 + lane;
+          bool cand = false;
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < n) {
+            q = __ldg(g.sorted + S[i]);
+            float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+            cand = can_beat(dx * dx + dy * dy + dz * dz, best, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, cand);
+          if (cand) g.pool[off + k + __popc(m & ((1u << lane) - 1))] = q;
+          k += __popc(m);
+        }
+      }
       rec = make_int2(off, keep);
       kind = 6;
     }
   }
   __syncwarp();
   return rec;
+}
+
+#ifndef DSN_LONG_CAP
+#define DSN_LONG_CAP 8192
+#endif
+constexpr int LONG_CAP = DSN_LONG_CAP;    // longest list the second build level writes straight into the pool
+
+// A table cell whose candidates do not fit the builder's shared-memory buffers (more than BUF_CAP in the superset or more than
+// LIST_CAP in the list: cells that see a dense cluster or a whole ring of centroids).  A ball scan per LOOKUP through such a
+// cell visits every centroid of every grid cell the ball touches, thousands of them, and 0.5 % of the lookups cost half of the
+// search kernels' instructions that way; the list -- the centroids that can win somewhere in the cell -- is several times
+// shorter, so it is worth one or two more scans at build time: count the centroids that pass the filter against c0 (unless the
+// caller's last scan was that very count), then the same scan again writing them straight into the pool.  All lanes call this; `seed` = c0, the exact nearest centroid of the cell
+// centre (both callers have it: settle_cell's, or the reduced one of the builder's second scan).  No transparency proof: the
+// cell stays searchable.
+__device__ __forceinline__ int2 long_list(const Grid& g, float px, float py, float pz, float a, float rho, int seed, int known_total, float known_best, int& kind) {
+  const int lane = threadIdx.x & 31;
+  const int mi = seed;
+  const float c0x = __ldg(g.cent + 3 * seed), c0y = __ldg(g.cent + 3 * seed + 1), c0z = __ldg(g.cent + 3 * seed + 2);
+  const float mb = known_total >= 0 ? known_best : (px - c0x) * (px - c0x) + (py - c0y) * (py - c0y) + (pz - c0z) * (pz - c0z);
+  const float radius = (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f;
+  const float best = mb;
+  int total = known_total;  // >= 0: the caller has just run this very scan (same ball, same filter) and counted
+  if (total < 0) {
+    total = 0;
+    warp_scan_ball_flat(g, px, py, pz, radius, [&](float4 q, int, bool valid) {
+      const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+      const bool keep = valid && can_beat(dx * dx + dy * dy + dz * dz, best, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
+      total += __popc(__ballot_sync(0xffffffffu, keep));
+    });
+  }
+  kind = 7;
+  if (total > LONG_CAP) return make_int2(mi, -2);
+  int off = 0;
+  if (lane == 0) off = atomicAdd(g.pool_used, total);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (off + total > g.pool_cap) return make_int2(mi, -2);
+  int n = 0;
+  warp_scan_ball_flat(g, px, py, pz, radius, [&](float4 q, int, bool valid) {
+    const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+    const bool keep = valid && can_beat(dx * dx + dy * dy + dz * dz, best, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int slot = n + __popc(m & ((1u << lane) - 1));
+    if (keep && slot < total) g.pool[off + slot] = q;
+    n += __popc(m);
+  });
+  __syncwarp();
+  // the count came from another instance of the same scan: should the two ever disagree (a differently contracted fma), a
+  // longer list is not trusted (scan fallback) and a shorter one is padded with c0 (a duplicate candidate is harmless)
+  if (n > total) return make_int2(mi, -2);
+  for (int i = n + lane; i < total; i += 32) g.pool[off + i] = make_float4(c0x, c0y, c0z, __int_as_float(mi));
+  __syncwarp();
+  kind = 6;
+  return make_int2(off, total);
 }
 
 // Build requested cells, one warp per REQUESTED ENUMERATION CELL (LEVEL 1) or per left-over table cell (LEVEL 2).
@@ -654,6 +726,10 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
           }
           rec = settle_cell(g, buf[w], nbuf, lst[w], g.ox + (cx + 0.5f) * tcell, g.oy + (cy + 0.5f) * tcell, g.oz + (cz + 0.5f) * tcell, at,
                             g.thalf_diag, ck);
+          if (rec.y == -2) {  // pool full: LEVEL 2 may still find room (long_list) or leaves the cell to the scans
+            if (lane == 0) g.req2[atomicAdd(g.pool_used + 3, 1)] = child;
+            continue;
+          }
         }
         __syncwarp();
         if (lane == 0) {
@@ -664,8 +740,9 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
       }
     } else {
       int2 rec;
-      if (overflow) { rec = make_int2(mi, -2); kind = 7; }  // (mi: best centroid seen by this lane's rows; any centroid seeds the scan)
+      if (overflow) { rec = make_int2(__shfl_sync(0xffffffffu, mi, 0), -2); kind = 7; }  // (mi: a centroid seen by lane 0's rows; any centroid seeds a scan)
       else rec = settle_cell(g, buf[w], nbuf, lst[w], px, py, pz, a, rho, kind);
+      if (rec.y == -2) rec = long_list(g, px, py, pz, a, rho, rec.x, overflow ? nbuf : -1, mb, kind);
       __syncwarp();
       if (lane == 0) {
         g.trec[cell] = rec;

@@ -83,18 +83,96 @@ __device__ __forceinline__ int canon_nearest(const Grid& gc, const float* __rest
 // (16 warps per SM), which then only reads the result (lighting 1.42 ms -> 0.47 + 0.36 ms).  Consecutive lookups are
 // consecutive samples of a ray and mostly share a cell, so the lanes of a warp walk the same list with broadcast loads;
 // bucketing the lookups of a block by list length (as sample_warp_kernel does) breaks that and was slower (0.82 ms).
+//
+// Two passes.  0.5 % of the lookups fall into cells whose candidates did not fit the builder's buffers (cells that see a dense
+// cluster or a whole ring of centroids); they used to cost a ball scan through the grid each -- several thousand instructions,
+// scattered one or two per warp, so that almost every fifth warp walked through a scan with one or two lanes busy: about
+// half of the kernel's 82 M warp instructions (ncu: 16 of 32 lanes busy, 44 % warps active).  Now the builder writes those
+// cells' lists straight into the pool (long_list, geom.cuh), pass 1 (canon_nearest_kernel) answers every lookup whose list has
+// at most COOP_LIST entries and queues the others, and pass 2 (canon_long_kernel) gives every queued lookup to a whole warp:
+// 32 candidates per step and a butterfly argmin (or warp_scan_ball_flat where there is no list: pool full); same arithmetic,
+// strict '<', lowest index on ties, so the result is the one list_nearest / scan_nearest return.  gc.pool_used[19] counts the
+// queue, [18] is pass 1's work counter (both zeroed by ensure_cells in front of every launch).
+constexpr int COOP_LIST = 256;  // lists longer than this are walked by a whole warp (canon_long_kernel)
 __global__ void __launch_bounds__(256) canon_nearest_kernel(const float4* __restrict__ active, const unsigned long long* __restrict__ n_ptr,
-                                                            int64_t n_host, Grid gc, const float* __restrict__ cent, int F, int* __restrict__ out) {
+                                                            int64_t n_host, Grid gc, const float* __restrict__ cent, int F, int* __restrict__ out,
+                                                            int* __restrict__ queue) {
   const int64_t n = n_ptr ? (int64_t)*n_ptr : n_host;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    const float4 p = active[t];
-    out[t] = canon_nearest(gc, cent, F, p.x, p.y, p.z);
-    if (gc.debug) {  // profile bit 2: which path the lookups take (dsnerf_debug_table [13] list, [14] scan, [15] exhaustive)
+  const int lane = threadIdx.x & 31;
+  // lists hold 1..COOP_LIST candidates and long ones come in runs: warps take chunks of 64 consecutive lookups from a work
+  // counter (gc.pool_used[18]) instead of striding (132 vs 162-184 us; chunks of 256 are as slow as striding)
+  unsigned int* work = reinterpret_cast<unsigned int*>(gc.pool_used + 18);
+  for (;;) {
+    unsigned int c = 0;
+    if (lane == 0) c = atomicAdd(work, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if ((int64_t)c * 64 >= n) break;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int64_t t = (int64_t)c * 64 + h * 32 + lane;
+    bool deferred = false;
+    if (t < n) {
+      const float4 p = active[t];
       const int cell = live_cell(gc, p.x, p.y, p.z);
-      const int c = cell < 0 ? -1 : gc.trec[cell].y;
-      atomicAdd(gc.pool_used + (c >= 0 ? 13 : (c == -2 ? 14 : 15)), 1);
-      if (c > 0) atomicAdd(gc.pool_used + 10, c);
+      int idx = -1;
+      if (cell >= 0) {
+        const int2 rec = gc.trec[cell];
+        deferred = rec.y == -2 || rec.y > COOP_LIST;
+        if (rec.y >= 0 && !deferred) idx = list_nearest(gc, rec.x, rec.y, p.x, p.y, p.z);
+      }
+      if (idx < 0 && !deferred) idx = brute_nearest(cent, F, p.x, p.y, p.z);  // outside the table / far from the canonical mesh (rare for warped points)
+      out[t] = idx;
+      if (gc.debug) {  // profile bit 2: which path the lookups take (dsnerf_debug_table [13] list, [14] scan, [15] exhaustive)
+        const int c2 = cell < 0 ? -1 : gc.trec[cell].y;
+        atomicAdd(gc.pool_used + (c2 >= 0 ? 13 : (c2 == -2 ? 14 : 15)), 1);
+        if (c2 > 0) atomicAdd(gc.pool_used + 10, c2);
+      }
     }
+    const unsigned m = __ballot_sync(0xffffffffu, deferred);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(gc.pool_used + 19, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (deferred) queue[base + __popc(m & ((1u << lane) - 1))] = (int)t;
+    }
+  }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) canon_long_kernel(const float4* __restrict__ active, Grid gc, const int* __restrict__ queue, int* __restrict__ out) {
+  const int nq = gc.pool_used[19];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += warps) {
+    const int t = queue[i];
+    const float4 p = active[t];
+    const float px = p.x, py = p.y, pz = p.z;
+    const int2 rec = gc.trec[live_cell(gc, px, py, pz)];
+    float best = 3.0e38f;
+    int besti = 0x7fffffff;
+    auto take = [&](float4 q) {
+      const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
+      float d = xmul(dx, dx);
+      d = xfma(dy, dy, d);
+      d = xfma(dz, dz, d);
+      const int id = __float_as_int(q.w);
+      if (d < best || (d == best && id < besti)) { best = d; besti = id; }
+    };
+    if (rec.y >= 0) {  // long candidate list: 32 candidates per step
+      const float4* __restrict__ L = gc.pool + rec.x;
+      for (int k = lane; k < rec.y; k += 32) take(__ldg(L + k));
+    } else {           // no list (pool full / longer than LONG_CAP): ball scan through the centroid kept in the record
+      const float dx = xsub(px, __ldg(gc.cent + 3 * rec.x)), dy = xsub(py, __ldg(gc.cent + 3 * rec.x + 1)), dz = xsub(pz, __ldg(gc.cent + 3 * rec.x + 2));
+      const float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+      warp_scan_ball_flat(gc, px, py, pz, sqrtf(d * 1.0001f + 1e-12f) * 1.0001f, [&](float4 q, int, bool valid) { if (valid) take(q); });
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) out[t] = besti;
   }
 }
 

@@ -819,6 +819,41 @@ __device__ __forceinline__ int table_nearest(const Grid& g, int cell, float px, 
   return scan_nearest(g, px, py, pz, rec.x);
 }
 
+// The same search by a whole warp (all lanes pass the same point and record, all lanes get the result): 32 candidates per
+// step and a butterfly argmin for a candidate list, warp_scan_ball_flat where the cell has no list (pool full).  Same
+// arithmetic, strict '<', lowest index on ties: the result is the one list_nearest / scan_nearest return.  For lookups
+// through lists longer than COOP_LIST (cells that see a dense cluster or a whole ring of centroids): a lane walking such a
+// list alone keeps its whole warp (and, in sample_warp_kernel, its block) waiting.
+constexpr int COOP_LIST = 256;
+__device__ __forceinline__ int warp_nearest(const Grid& g, int2 rec, float px, float py, float pz) {
+  const int lane = threadIdx.x & 31;
+  float best = 3.0e38f;
+  int besti = 0x7fffffff;
+  auto take = [&](float4 q) {
+    const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
+    float d = xmul(dx, dx);
+    d = xfma(dy, dy, d);
+    d = xfma(dz, dz, d);
+    const int id = __float_as_int(q.w);
+    if (d < best || (d == best && id < besti)) { best = d; besti = id; }
+  };
+  if (rec.y >= 0) {
+    const float4* __restrict__ L = g.pool + rec.x;
+    for (int k = lane; k < rec.y; k += 32) take(__ldg(L + k));
+  } else {
+    const float dx = xsub(px, __ldg(g.cent + 3 * rec.x)), dy = xsub(py, __ldg(g.cent + 3 * rec.x + 1)), dz = xsub(pz, __ldg(g.cent + 3 * rec.x + 2));
+    const float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
+    warp_scan_ball_flat(g, px, py, pz, sqrtf(d * 1.0001f + 1e-12f) * 1.0001f, [&](float4 q, int, bool valid) { if (valid) take(q); });
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  return besti;
+}
+
 // ---------------------------------------------------------------------------------------------
 // geometry_guided_ray_marching, utils/pts_utils.py:18-53 (near/far only).
 // vq = (vertex - o0, |vertex - o0|^2) per vertex, prepared by gg_prep_kernel.
@@ -1108,6 +1143,8 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
   __shared__ int qn;
   __shared__ int bin_count[16], bin_start[16];
   __shared__ unsigned char flag[WARP_SPB];
+  constexpr int LONG_SLOTS = 256;     // cooperative searches per block (further bin-15 entries are searched per lane)
+  __shared__ int long_idx[LONG_SLOTS];
   const int64_t P = a.R * a.N;
   const int64_t s0 = (int64_t)blockIdx.x * WARP_SPB;
   const int lane = threadIdx.x & 31;
@@ -1128,7 +1165,7 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
       const int cell = live_cell(g, px, py, pz);
       if (cell >= 0) {
         const int cnt = g.trec[cell].y;
-        if (cnt != -1) my_bin[k] = cnt < 0 ? 15 : min(14, cnt >> 3);
+        if (cnt != -1) my_bin[k] = (cnt < 0 || cnt > COOP_LIST) ? 15 : min(14, cnt >> 3);
       }
     }
     if (my_bin[k] >= 0) atomicAdd(&bin_count[my_bin[k]], 1);
@@ -1146,6 +1183,16 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
   __syncthreads();
   const int n = qn;
   if (a.count_candidates && threadIdx.x == 0 && n) atomicAdd(a.counters + 2, (unsigned long long)n);
+  // bin 15 (the head of the queue) = lookups through a list longer than COOP_LIST or through a cell without a list: one warp
+  // each (warp_nearest) before the per-lane searches, so that no lane walks hundreds of candidates while its block waits
+  const int n_long = min(bin_count[15], LONG_SLOTS);
+  for (int i = threadIdx.x >> 5; i < n_long; i += WARP_THREADS / 32) {
+    float px, py, pz;
+    sample_position(a, s0 + queue[i], px, py, pz);
+    const int idx = warp_nearest(g, g.trec[table_cell(g, px, py, pz)], px, py, pz);
+    if (lane == 0) long_idx[i] = idx;
+  }
+  if (n_long) __syncthreads();  // (block uniform)
   for (int q0 = 0; q0 < n; q0 += WARP_THREADS) {
     const int qi = q0 + threadIdx.x;
     bool act = false;
@@ -1155,7 +1202,7 @@ __global__ void __launch_bounds__(WARP_THREADS) sample_warp_kernel(WarpArgs a, G
       t = queue[qi];
       float px, py, pz;
       sample_position(a, s0 + t, px, py, pz);
-      idx = table_nearest(g, table_cell(g, px, py, pz), px, py, pz);
+      idx = qi < n_long ? long_idx[qi] : table_nearest(g, table_cell(g, px, py, pz), px, py, pz);
       if (idx >= 0) {
         int i0 = a.faces[3 * idx], i1 = a.faces[3 * idx + 1], i2 = a.faces[3 * idx + 2];
         float u, v, h;

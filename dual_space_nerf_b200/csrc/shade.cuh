@@ -93,7 +93,6 @@ __device__ __forceinline__ int canon_nearest(const Grid& gc, const float* __rest
 // 32 candidates per step and a butterfly argmin (or warp_scan_ball_flat where there is no list: pool full); same arithmetic,
 // strict '<', lowest index on ties, so the result is the one list_nearest / scan_nearest return.  gc.pool_used[19] counts the
 // queue, [18] is pass 1's work counter (both zeroed by ensure_cells in front of every launch).
-constexpr int COOP_LIST = 256;  // lists longer than this are walked by a whole warp (canon_long_kernel)
 __global__ void __launch_bounds__(256) canon_nearest_kernel(const float4* __restrict__ active, const unsigned long long* __restrict__ n_ptr,
                                                             int64_t n_host, Grid gc, const float* __restrict__ cent, int F, int* __restrict__ out,
                                                             int* __restrict__ queue) {
@@ -148,30 +147,7 @@ __global__ void __launch_bounds__(256, 4) canon_long_kernel(const float4* __rest
     const float4 p = active[t];
     const float px = p.x, py = p.y, pz = p.z;
     const int2 rec = gc.trec[live_cell(gc, px, py, pz)];
-    float best = 3.0e38f;
-    int besti = 0x7fffffff;
-    auto take = [&](float4 q) {
-      const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
-      float d = xmul(dx, dx);
-      d = xfma(dy, dy, d);
-      d = xfma(dz, dz, d);
-      const int id = __float_as_int(q.w);
-      if (d < best || (d == best && id < besti)) { best = d; besti = id; }
-    };
-    if (rec.y >= 0) {  // long candidate list: 32 candidates per step
-      const float4* __restrict__ L = gc.pool + rec.x;
-      for (int k = lane; k < rec.y; k += 32) take(__ldg(L + k));
-    } else {           // no list (pool full / longer than LONG_CAP): ball scan through the centroid kept in the record
-      const float dx = xsub(px, __ldg(gc.cent + 3 * rec.x)), dy = xsub(py, __ldg(gc.cent + 3 * rec.x + 1)), dz = xsub(pz, __ldg(gc.cent + 3 * rec.x + 2));
-      const float d = xfma(dz, dz, xfma(dy, dy, xmul(dx, dx)));
-      warp_scan_ball_flat(gc, px, py, pz, sqrtf(d * 1.0001f + 1e-12f) * 1.0001f, [&](float4 q, int, bool valid) { if (valid) take(q); });
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-      if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-    }
+    const int besti = warp_nearest(gc, rec, px, py, pz);
     if (lane == 0) out[t] = besti;
   }
 }

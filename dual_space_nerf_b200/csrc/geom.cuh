@@ -824,7 +824,10 @@ __device__ __forceinline__ int table_nearest(const Grid& g, int cell, float px, 
 // arithmetic, strict '<', lowest index on ties: the result is the one list_nearest / scan_nearest return.  For lookups
 // through lists longer than COOP_LIST (cells that see a dense cluster or a whole ring of centroids): a lane walking such a
 // list alone keeps its whole warp (and, in sample_warp_kernel, its block) waiting.
-constexpr int COOP_LIST = 256;
+#ifndef DSN_COOP_LIST
+#define DSN_COOP_LIST 256
+#endif
+constexpr int COOP_LIST = DSN_COOP_LIST;
 __device__ __forceinline__ int warp_nearest(const Grid& g, int2 rec, float px, float py, float pz) {
   const int lane = threadIdx.x & 31;
   float best = 3.0e38f;

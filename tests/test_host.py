@@ -148,6 +148,45 @@ def test_sharded_render_equals_unsharded_gloo_world2():
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def test_candidate_filter_keeps_every_possible_winner():
+    """The lookup table's candidate lists (csrc/geom.cuh: can_beat, settle_cell, long_list) rest on one inequality: with c0 the
+    nearest centroid of a cube's centre x and a its half edge, a centroid c can be the nearest one of SOME point of the cube
+    only if |x - c|^2 - |x - c0|^2 <= 2 a |c - c0|_1 (the difference of the two squared distances is linear in the point).
+    Checked here with the kernel's fp32 slack on the synthetic mesh's centroids (dense clusters at the poles included): the
+    brute-force nearest centroid of random points of random cubes is always in the filtered list, and the 1-NN over the list
+    (strict '<', lowest index on ties, the rule of pytorch3d's knn_points as called at utils/render_utils.py:95) equals the
+    1-NN over all centroids."""
+    from dual_space_nerf_b200 import scene as S
+
+    sc = S.make_scene(8, 8)
+    cent = sc["canonical"][sc["faces"]].mean(1).astype(np.float32)
+    rng = np.random.RandomState(3)
+    lo, hi = cent.min(0), cent.max(0)
+    a = np.float32(0.0125)  # half edge of a 2.5 cm table cell
+    worst = 0
+    for trial in range(60):
+        # cube centres: near the surface, near the poles (dense clusters) and inside the body (rings of near-equidistant centroids)
+        if trial % 3 == 0:
+            x = cent[rng.randint(len(cent))] + rng.uniform(-0.05, 0.05, 3)
+        elif trial % 3 == 1:
+            x = cent[np.argmax(cent[:, trial % 3 + 1] * (1 if trial % 2 else -1))] + rng.uniform(-0.03, 0.03, 3)
+        else:
+            x = rng.uniform(lo, hi)
+        x = x.astype(np.float32)
+        d = ((cent - x) ** 2).sum(1, dtype=np.float32)
+        i0 = int(np.argmin(d))
+        l1 = np.abs(cent - cent[i0]).sum(1, dtype=np.float32)
+        keep = d - d[i0] <= 2.0 * a * l1 * np.float32(1.0002) + np.float32(1e-7) + np.float32(2e-6) * d  # can_beat
+        worst = max(worst, int(keep.sum()))
+        pts = (x + rng.uniform(-a, a, (400, 3))).astype(np.float32)
+        dd = ((pts[:, None, :] - cent[None, :, :]) ** 2).sum(-1, dtype=np.float32)
+        nn = dd.argmin(1)            # first minimum = lowest index on ties
+        assert keep[nn].all(), (trial, int((~keep[nn]).sum()))
+        idx = np.flatnonzero(keep)
+        assert np.array_equal(idx[dd[:, idx].argmin(1)], nn)
+    assert worst > 256  # the sample holds cubes whose list exceeds the builder's scratch list (the long_list path)
+
+
 def test_pe_sincos_algorithm_accuracy():
     """The tensor-core kernel's positional encoding does not call sincosf: csrc/mlp_tc.cuh:pe_sincos reduces 2^k * x / 2pi
     exactly (two-float) and evaluates sin / cos (2 pi r), |r| <= 1/8, by polynomials.  Restated here operation by operation

@@ -395,7 +395,10 @@ __device__ __forceinline__ void warp_scan_ball(const Grid& g, float px, float py
 // batch into one flat index space, and the lanes walk that space 32 items at a time (the row of an item is found by a 5-step
 // binary search over the lanes' prefix values through shuffles).  The warp stays converged, so the visitor may use ballots:
 // visit(q, j, valid) is called by ALL lanes, q = g.sorted[j] where valid.
-template <class Visit>
+// BATCH > 1: the records of BATCH consecutive steps are loaded before the first of them is visited.  One step is one dependent
+// L2 access of the warp; the second build level runs one warp per cell through three scans of a few thousand centroids each,
+// and that chain IS the kernel's duration (8 % of the warp slots in use), so there the loads are worth the registers.
+template <int BATCH = 1, class Visit>
 __device__ __forceinline__ void warp_scan_ball_flat(const Grid& g, float px, float py, float pz, float rho, Visit&& visit) {
   const int lane = threadIdx.x & 31;
   const float rho2 = rho * rho;
@@ -438,22 +441,28 @@ __device__ __forceinline__ void warp_scan_ball_flat(const Grid& g, float px, flo
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const int excl = incl - cnt;
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      const int t = t0 + lane;
-      const bool valid = t < total;
-      // the row of item t: the first lane whose inclusive prefix exceeds t
-      int lo = 0;
+    for (int t0 = 0; t0 < total; t0 += 32 * BATCH) {
+      float4 q[BATCH];
+      int j[BATCH];
 #pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
-        if (probe <= t) lo += step;
+      for (int u = 0; u < BATCH; ++u) {
+        const int t = t0 + 32 * u + lane;
+        // the row of item t: the first lane whose inclusive prefix exceeds t
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+          if (probe <= t) lo += step;
+        }
+        lo = min(lo, 31);
+        const int rb = __shfl_sync(0xffffffffu, b, lo), re = __shfl_sync(0xffffffffu, excl, lo);
+        j[u] = rb + (t - re);
+        q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < total) q[u] = __ldg(g.sorted + j[u]);
       }
-      lo = min(lo, 31);
-      const int rb = __shfl_sync(0xffffffffu, b, lo), re = __shfl_sync(0xffffffffu, excl, lo);
-      const int j = rb + (t - re);
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) q = __ldg(g.sorted + j);
-      visit(q, j, valid);
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u)
+        if (u == 0 || t0 + 32 * u < total) visit(q[u], j[u], t0 + 32 * u + lane < total);  // (warp uniform)
     }
   }
   __syncwarp();
@@ -588,7 +597,7 @@ __device__ __forceinline__ int2 long_list(const Grid& g, float px, float py, flo
   int total = known_total;  // >= 0: the caller has just run this very scan (same ball, same filter) and counted
   if (total < 0) {
     total = 0;
-    warp_scan_ball_flat(g, px, py, pz, radius, [&](float4 q, int, bool valid) {
+    warp_scan_ball_flat<4>(g, px, py, pz, radius, [&](float4 q, int, bool valid) {
       const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
       const bool keep = valid && can_beat(dx * dx + dy * dy + dz * dz, best, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
       total += __popc(__ballot_sync(0xffffffffu, keep));
@@ -601,7 +610,7 @@ __device__ __forceinline__ int2 long_list(const Grid& g, float px, float py, flo
   off = __shfl_sync(0xffffffffu, off, 0);
   if (off + total > g.pool_cap) return make_int2(mi, -2);
   int n = 0;
-  warp_scan_ball_flat(g, px, py, pz, radius, [&](float4 q, int, bool valid) {
+  warp_scan_ball_flat<4>(g, px, py, pz, radius, [&](float4 q, int, bool valid) {
     const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
     const bool keep = valid && can_beat(dx * dx + dy * dy + dz * dz, best, a, fabsf(q.x - c0x) + fabsf(q.y - c0y) + fabsf(q.z - c0z));
     const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -660,7 +669,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
     float mb = dref2;
     int mi = cref;
     int nbuf = 0;  // warp uniform: the candidates are appended through ballots (the flat scan keeps the warp converged)
-    warp_scan_ball_flat(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
+    warp_scan_ball_flat<LEVEL == 2 ? 4 : 1>(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
       float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
       float d = dx * dx + dy * dy + dz * dz;
       bool keep = false;
@@ -689,7 +698,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
       const float c0x = __ldg(g.cent + 3 * mi), c0y = __ldg(g.cent + 3 * mi + 1), c0z = __ldg(g.cent + 3 * mi + 2);
       __syncwarp();
       nbuf = 0;
-      warp_scan_ball_flat(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
+      warp_scan_ball_flat<LEVEL == 2 ? 4 : 1>(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
         float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
         bool keep = false;
         if (valid) {

@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
     float mb = dref2;
     int mi = cref;
     int nbuf = 0;  // warp uniform: the candidates are appended through ballots (the flat scan keeps the warp converged)
-    warp_scan_ball_flat<LEVEL == 2 ? 4 : 1>(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
+    warp_scan_ball_flat<LEVEL == 2 ? 4 : 2>(g, px, py, pz, (sqrtf(dref2) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
       float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
       float d = dx * dx + dy * dy + dz * dz;
       bool keep = false;
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_cells_kernel(Grid g) {
       const float c0x = __ldg(g.cent + 3 * mi), c0y = __ldg(g.cent + 3 * mi + 1), c0z = __ldg(g.cent + 3 * mi + 2);
       __syncwarp();
       nbuf = 0;
-      warp_scan_ball_flat<LEVEL == 2 ? 4 : 1>(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
+      warp_scan_ball_flat<LEVEL == 2 ? 4 : 2>(g, px, py, pz, (sqrtf(mb) + 2.0f * rho) * 1.0002f + 1e-5f, [&](float4 q, int j, bool valid) {
         float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
         bool keep = false;
         if (valid) {
